@@ -1,0 +1,41 @@
+# Builds libpacmensl_b200.so (CUDA kernels + C ABI + host C++ mirror of the reference API) for sm_100a,
+# and the CPU oracle.  `make` here cross-compiles without a GPU.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX_HOST := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -ccbin $(CXX_HOST) -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function,-Wno-deprecated-declarations
+CXXFLAGS := -O2 -g -std=c++17 -fPIC -Wall -Wno-unused-function -fvisibility=hidden -Iinclude -Ipacmensl_b200/host
+
+BUILD := build
+LIB := pacmensl_b200/lib/libpacmensl_b200.so
+
+CU_SRCS := $(wildcard pacmensl_b200/csrc/*.cu)
+CU_OBJS := $(patsubst pacmensl_b200/csrc/%.cu,$(BUILD)/%.cu.o,$(CU_SRCS))
+HOST_SRCS := $(wildcard pacmensl_b200/host/*.cpp)
+HOST_OBJS := $(patsubst pacmensl_b200/host/%.cpp,$(BUILD)/%.host.o,$(HOST_SRCS))
+
+all: $(LIB) oracle
+
+$(BUILD)/%.cu.o: pacmensl_b200/csrc/%.cu pacmensl_b200/csrc/fsp_common.cuh include/fsp_b200.h
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(BUILD)/%.host.o: pacmensl_b200/host/%.cpp $(wildcard pacmensl_b200/host/*.h) include/fsp_b200.h pacmensl_b200/fixtures/fsp_models.h
+	@mkdir -p $(BUILD)
+	$(CXX_HOST) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): $(CU_OBJS) $(HOST_OBJS)
+	@mkdir -p pacmensl_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart_static -ldl -lpthread -lrt
+
+oracle:
+	$(MAKE) -s -C oracle
+
+ptxas-info:
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c pacmensl_b200/csrc/fspmat.cu -o /dev/null
+
+clean:
+	rm -rf $(BUILD) $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean ptxas-info

@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- FSP Action() bandwidth on the synthetic 3-D birth-death lattice (BASELINE.json config 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--lattice 465] [--tv]
+
+A "step" is one Action(t, x, y) over the whole lattice vector.  Metric = algorithmic GB moved per
+second, bytes/row = 16 + 12 R + 8 (R_tv + [R_ti>0]) (+ sinks), SURVEY.md section 8(d).
+One JSON line is printed by rank 0.  For N > 1 launch with torchrun (one rank per GPU): the lattice is
+split into N contiguous row blocks (strong scaling, halo exchange over NCCL).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lattice", type=int, default=465, help="states per species axis (L+1); N = lattice^3")
+    ap.add_argument("--tv", action="store_true", help="time-varying births (R_tv = 3)")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 default, 1/2/4 rows per thread)")
+    ap.add_argument("--cpu-lattice", type=int, default=128, help="lattice edge of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-expand", action="store_true", help="skip the Expand() closure check of the lattice set")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def lattice_bytes_per_row(tv):
+    R, ntv = 6, (3 if tv else 0)
+    return 16 + 12 * R + 8 * (ntv + (1 if R - ntv > 0 else 0))
+
+
+def cpu_baseline(args, all_threads=True):
+    """Reference-shaped multi-pass Action (oracle port) on a bounded sample of the same workload."""
+    import numpy as np
+    from oracle import oracle as O
+    L = args.cpu_lattice
+    name = "birth_death_3d_tv" if args.tv else "birth_death_3d"
+    st = O.StateSet(fixture=name, bounds=[L - 1] * 3)
+    st.expand()
+    A = O.FspMatrix(constrained=True)
+    assert A.generate_fixture(st, name) == 0
+    n = st.n
+    rng = np.random.default_rng(12345)
+    x = rng.random(A.nrows)
+    x[n:] = 0.0
+    x /= x.sum()
+    y = np.empty_like(x)
+    for _ in range(3):
+        A.action_into(0.0, x, y)
+    ts = []
+    for _ in range(args.cpu_steps):
+        t0 = time.perf_counter()
+        A.action_into(0.0, x, y)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    nbytes = n * lattice_bytes_per_row(args.tv) + 12 * 3 * L * L + 8 * 3
+    return {"value": nbytes / med / 1e9, "unit": "GB/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "%d^3 = %d-state lattice, median of %d reference-shaped (SpMV+AXPY per matrix) OpenMP Actions; "
+                      "oracle/fsp_oracle.c (the PETSc reference cannot be built in this image)" % (L, n, args.cpu_steps),
+            "ms_per_step": med * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args)
+    line = {
+        "metric": "FSP Action() GB/s", "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.cpu_steps, "warmup": 3, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "synthetic 3-D birth-death lattice Action() (CPU sample %d^3)" % args.cpu_lattice,
+                   "tv": bool(args.tv)},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from pacmensl_b200 import _capi
+    from pacmensl_b200.lattice import build_birth_death_lattice, tcoef
+    L = _capi.lib()
+    _capi.check(L.fsp_device_set(local_rank), "fsp_device_set")
+
+    Ledge = args.lattice
+    t_build0 = time.perf_counter()
+    if world == 1:
+        M, N = build_birth_death_lattice([Ledge - 1] * 3, tv=args.tv, expand=not args.no_expand)
+        part = None
+    else:
+        from pacmensl_b200.partition import build_partitioned_lattice
+        M, N, part = build_partitioned_lattice([Ledge - 1] * 3, args.tv, rank, world, dist, expand=not args.no_expand)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build0
+    M.set_variant(args.variant)
+    n_rows = M.n_rows
+    bytes_local = M.action_bytes()
+
+    g = torch.Generator(device="cuda").manual_seed(12345 + rank)
+    x = torch.rand(n_rows, generator=g, dtype=torch.float64, device="cuda")
+    if M.n < n_rows:
+        x[M.n:] = 0.0
+    s = x.sum()
+    if dist is not None:
+        dist.all_reduce(s)
+    x /= s
+    y = torch.empty_like(x)
+    coef = tcoef(0.3, args.tv)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        if part is None:
+            M.action(coef, x, y, stream=stream)
+        else:
+            part.action(M, coef, x, y, stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps, CUDA events on the launching stream -------------------------
+    launches0 = L.fsp_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = L.fsp_launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        dist.barrier()
+        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+        tot = torch.tensor([bytes_local, float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tot)
+        bytes_total, launches_total = float(tot[0].item()), int(tot[1].item())
+    else:
+        bytes_total, launches_total = bytes_local, launches
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = bytes_total / (ms_per_step * 1e-3) / 1e9
+
+    # dominant kernel: the fused Action kernel; per-launch duration from a second event-timed loop on rank 0
+    # (single-GPU launches only; at N > 1 this still times the local SpMV launch without the halo exchange)
+    kms = None
+    if rank == 0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ghost = part.ghost if part is not None else None
+        e0.record()
+        for _ in range(args.steps):
+            M.action(coef, x, y, ghost=ghost, sink_out=(part.sink_buf if part is not None else None), stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / args.steps
+    if dist is not None:
+        dist.barrier()
+
+    # ---- e2e: the same Action through the C ABI with HOST buffers (H2D x, D2H y inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(n_rows, dtype=torch.float64).pin_memory()
+        yh = torch.empty(n_rows, dtype=torch.float64).pin_memory()
+        xh.copy_(x)
+        k2 = max(3, min(args.steps, 10))
+        sptr = C.c_void_p(stream)
+
+        def e2e_step():
+            # NB fsp_memcpy_* synchronise the stream, like a blocking host API call would
+            _capi.check(L.fsp_memcpy_h2d(C.c_void_p(x.data_ptr()), C.c_void_p(xh.data_ptr()), n_rows * 8, sptr), "h2d")
+            step()
+            _capi.check(L.fsp_memcpy_d2h(C.c_void_p(yh.data_ptr()), C.c_void_p(y.data_ptr()), n_rows * 8, sptr), "d2h")
+
+        e2e_step()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / k2
+        if dist is not None:
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": bytes_total / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(n_rows * 8),
+               "d2h_bytes_per_step": int(n_rows * 8), "ms_per_step": dt * 1e3, "steps": k2}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ach = bytes_local / (kms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "action_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if tj.get("lattice") == Ledge and bool(tj.get("tv")) == bool(args.tv) and world == 1:
+                    traffic = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        line = {
+            "metric": "FSP Action() GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (x ~ U(0,1) normalised, torch Philox seed 12345)",
+            "config": {"workload": "synthetic 3-D birth-death lattice %d^3 = %d states, S=3 R=6 K=3 sinks, %s, "
+                                   "Action(t,x,y) through FspMatrixConstrained layout" % (Ledge, N, "R_tv=3" if args.tv else "time-invariant"),
+                       "states": N, "bytes_per_row": lattice_bytes_per_row(args.tv),
+                       "l2": "inputs (%.2f GB per Action) exceed the 126 MB L2; no flush needed" % (bytes_total / 1e9),
+                       "partition": "1 block" if world == 1 else "%d contiguous row blocks, halo over NCCL" % world,
+                       "kernel_variant": args.variant, "build_seconds": round(t_build, 2)},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "action_kernel (fspmat.cu)",
+                         "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_local},
+            "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            cb = cpu_baseline(args)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,242 @@
+/*
+ * fsp_b200.h -- C ABI of the B200-native FSP time-stepping core (libpacmensl_b200.so).
+ *
+ * This is the drop-in boundary between host C++ (the pacmensl:: classes that mirror the reference
+ * API, pacmensl_b200/host/) and the hand-written sm_100a CUDA kernels (pacmensl_b200/csrc/).
+ * Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success and a
+ * non-zero code on failure (the reference convention, src/Sys/ErrorHandling.h:29-54), never throw,
+ * and are called from one host thread per device.
+ *
+ * Each group names the reference interface it replaces (paths relative to the reference tree).
+ * Pointers named *_dev are device pointers on the current device; `stream` is a cudaStream_t passed
+ * as void* (NULL = the library's default stream for this thread's device).
+ */
+#ifndef FSP_B200_H_
+#define FSP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSP_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------
+ * Runtime: device selection, memory, streams.
+ * Replaces PetscInitialize/VecCreate storage management (src/Sys/Sys.cpp:31-63,
+ * src/PetscWrap/PetscWrap.h:12-60) for device-resident vectors.
+ * ---------------------------------------------------------------------------------------------- */
+FSP_API int         fsp_device_count(int *count);
+FSP_API int         fsp_device_set(int device);
+FSP_API int         fsp_device_get(int *device);
+FSP_API int         fsp_device_sm_count(int *count);
+FSP_API const char *fsp_last_error(void);
+FSP_API int         fsp_malloc(void **ptr_dev, size_t bytes);
+FSP_API int         fsp_free(void *ptr_dev);
+FSP_API int         fsp_malloc_host(void **ptr_host, size_t bytes); /* pinned */
+FSP_API int         fsp_free_host(void *ptr_host);
+FSP_API int         fsp_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+FSP_API int         fsp_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+FSP_API int         fsp_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes, void *stream);
+FSP_API int         fsp_memset(void *dst_dev, int byte, size_t bytes, void *stream);
+FSP_API int         fsp_stream_create(void **stream);
+FSP_API int         fsp_stream_destroy(void *stream);
+FSP_API int         fsp_stream_sync(void *stream);
+FSP_API int         fsp_device_sync(void);
+FSP_API int         fsp_event_create(void **event);
+FSP_API int         fsp_event_destroy(void *event);
+FSP_API int         fsp_event_record(void *event, void *stream);
+FSP_API int         fsp_event_elapsed_ms(void *start, void *stop, float *ms); /* syncs on stop */
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+FSP_API long long   fsp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device vectors (fp64).  Replaces the PETSc Vec BLAS-1 calls on the hot path:
+ *   VecSet/VecCopy/VecScale/VecAXPY/VecDot/VecNorm/VecMAXPY/VecSum  (src/OdeSolver/KrylovFsp.cpp:138,
+ *   153,244-252,280-309; src/Matrix/FspMatrixBase.cpp:39,50,58) and the SUNDIALS N_Vector ops CVODE
+ *   uses (N_VLinearSum, N_VWrmsNorm, N_VDotProd, N_VScale, N_VConst; src/OdeSolver/CvodeFsp.cpp:150).
+ * Reductions write fp64 results to `out_dev` (device memory, asynchronous) -- read them with
+ * fsp_memcpy_d2h, or use the *_h variants which synchronise the stream and return on the host.
+ * Reductions are deterministic for a given (n, device).
+ * ---------------------------------------------------------------------------------------------- */
+FSP_API int fspvec_set(double *y_dev, double alpha, long n, void *stream);
+FSP_API int fspvec_copy(double *y_dev, const double *x_dev, long n, void *stream);
+FSP_API int fspvec_scale(double *y_dev, double alpha, long n, void *stream);
+/* y += alpha x */
+FSP_API int fspvec_axpy(double *y_dev, double alpha, const double *x_dev, long n, void *stream);
+/* z = a x + b y  (z may alias x or y) */
+FSP_API int fspvec_linear_sum(double *z_dev, double a, const double *x_dev, double b, const double *y_dev, long n,
+                              void *stream);
+/* y = beta*y + sum_k alpha[k] X[k]  (VecMAXPY; X_dev_ptrs is a HOST array of m device pointers, m <= 64) */
+FSP_API int fspvec_maxpy(double *y_dev, double beta, int m, const double *alpha_host,
+                         const double *const *X_dev_ptrs, long n, void *stream);
+/* out[k] = <x, Y[k]>, k < m <= 8, one pass over x */
+FSP_API int fspvec_mdot(double *out_dev, const double *x_dev, int m, const double *const *Y_dev_ptrs, long n,
+                        void *stream);
+FSP_API int fspvec_dot(double *out_dev, const double *x_dev, const double *y_dev, long n, void *stream);
+FSP_API int fspvec_norm2sq(double *out_dev, const double *x_dev, long n, void *stream); /* sum x_i^2 */
+FSP_API int fspvec_sum(double *out_dev, const double *x_dev, long n, void *stream);
+FSP_API int fspvec_norm1(double *out_dev, const double *x_dev, long n, void *stream);
+/* sum (x_i * w_i)^2 : building block of N_VWrmsNorm */
+FSP_API int fspvec_wsqsum(double *out_dev, const double *x_dev, const double *w_dev, long n, void *stream);
+/* w_i = 1 / (rtol*|y_i| + atol)  (CVODE error weights, cvEwtSetSS); out = min_i(rtol|y_i|+atol) */
+FSP_API int fspvec_ewt(double *w_dev, const double *y_dev, double rtol, double atol, long n, double *min_out_dev,
+                       void *stream);
+/* Fused modified-Gram-Schmidt step used by the Arnoldi/IOP loop (KrylovFsp.cpp:302-309):
+ *   w -= (*h_dev) * v ;  out = <w, u>    (u may be NULL: then out = <w, w>)            */
+FSP_API int fspvec_axpy_dot(double *w_dev, const double *h_dev, double sign, const double *v_dev,
+                            const double *u_dev, double *out_dev, long n, void *stream);
+/* w *= 1/sqrt(*normsq_dev)  (VecScale with a device-resident scalar; KrylovFsp.cpp:308) */
+FSP_API int fspvec_scale_rsqrt(double *w_dev, const double *normsq_dev, long n, void *stream);
+/* host-result conveniences (synchronise `stream`) */
+FSP_API int fspvec_dot_h(double *out_host, const double *x_dev, const double *y_dev, long n, void *stream);
+FSP_API int fspvec_norm2_h(double *out_host, const double *x_dev, long n, void *stream);
+FSP_API int fspvec_sum_h(double *out_host, const double *x_dev, long n, void *stream);
+FSP_API int fspvec_norm1_h(double *out_host, const double *x_dev, long n, void *stream);
+/* ExpandVec (src/PetscWrap/PetscWrap.cpp:26-56): p_new = 0; p_new[new_idx[i]] = p_old[i] */
+FSP_API int fspvec_scatter(double *p_new_dev, long n_new, const double *p_old_dev, const int *new_idx_dev,
+                           long n_old, void *stream);
+/* out[i] = x[idx[i]]  (MakeDiscreteDistribution_ scatter, src/Fsp/FspSolverMultiSinks.cpp:703-735) */
+FSP_API int fspvec_gather(double *out_dev, const double *x_dev, const int *idx_dev, long n, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * State set on the device: state list + hash directory.
+ * Replaces Zoltan_DD_{Create,Find,Update} and the Armadillo column bookkeeping in
+ *   StateSetBase::AddStates      src/StateSet/StateSetBase.cpp:188-258
+ *   StateSetBase::State2Index    src/StateSet/StateSetBase.cpp:309-423
+ *   StateSetConstrained::Expand / CheckValidityStates / CheckConstraints
+ *                                src/StateSet/StateSetConstrained.cpp:33-82,132-221
+ * States are int32, S per state, state i at states[i*S .. i*S+S-1] (the reference's column-major
+ * arma::Mat<int>, src/StateSet/StateSetBase.h:83).  Index = insertion order (np = 1 semantics);
+ * new states of one Expand wave are appended in first-discovery order of the reaction-major child
+ * list (StateSetConstrained.cpp:175-179 + Sys/pacmenMath.h:204-213).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fspset_s *fspset_t;
+/* host callback with the reference's fsp_constr_multi_fn contract (StateSetConstrained.h:32-33):
+ * out[K*j + k] = lhs_k(state j).  Called on host copies of candidate states. */
+typedef int (*fspset_constr_fn)(int num_species, int num_constr, int num_states, int *states, int *out, void *args);
+
+FSP_API int fspset_create(fspset_t *out, int num_species, int num_reactions, const int *SM_host /* S x R col-major */);
+FSP_API int fspset_destroy(fspset_t h);
+/* lhs == NULL => default identity constraints evaluated on the device (requires K == S) */
+FSP_API int fspset_set_shape(fspset_t h, int num_constr, fspset_constr_fn lhs, const int *bounds_host, void *args);
+FSP_API int fspset_set_bounds(fspset_t h, int num_constr, const int *bounds_host);
+/* AddStates: X is S x m (host or device, `on_device`); present states and in-batch duplicates are shed,
+ * the rest appended in order with status 1.  Returns -1 if num_species mismatches (KAT-S2). */
+FSP_API int fspset_add_states(fspset_t h, int num_species, long m, const int *X, int on_device);
+FSP_API int fspset_expand(fspset_t h);
+FSP_API int fspset_num_states(fspset_t h, int *n);
+/* State2Index: idx[j] = index of X[:, j] or -1 (negative coordinate or absent). */
+FSP_API int fspset_state2index(fspset_t h, long m, const int *X, int x_on_device, int *idx, int idx_on_device);
+/* idx[i] = State2Index(state_i + sign * nu)  for all stored states i in [first, first+count) */
+FSP_API int fspset_lookup_shifted(fspset_t h, const int *nu_host, int sign, long first, long count, int *idx_dev);
+/* CheckConstraints on state_i + nu for stored states: satisfied_dev[k*count + i] in {0,1}
+ * (constraint-major like StateSetConstrained.cpp:71; negative coordinates => satisfied). */
+FSP_API int fspset_check_constraints_shifted(fspset_t h, const int *nu_host, long first, long count,
+                                             int *satisfied_dev);
+/* Sink column lists (FspMatrixConstrained.cpp:170-194): for each constraint k, the ascending indices
+ * (relative to `first`) of stored states whose destination state_i + nu violates constraint k, written k
+ * after k into idx_out_dev (capacity `cap`); counts_host[k] = list lengths. */
+FSP_API int fspset_sink_lists(fspset_t h, const int *nu_host, long first, long count, int *idx_out_dev, long cap,
+                              long *counts_host);
+FSP_API int fspset_states_dev(fspset_t h, const int **states_dev); /* borrowed, valid until next mutation */
+FSP_API int fspset_copy_states(fspset_t h, long first, long count, int *out_host);
+FSP_API int fspset_copy_status(fspset_t h, long first, long count, signed char *out_host);
+/* Fill the set with the full lexicographic box lattice 0..bounds[s] (species 0 fastest;
+ * Sys/pacmenMath.h:33-59 convention) -- the synthetic workload of SURVEY.md section 8(d). */
+FSP_API int fspset_add_box_lattice(fspset_t h, const int *upper_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * Propensity evaluation on the device for models given in mass-action form
+ *   d_r(x) = rate[r] * prod_s binom-like falling factorial of x_s of order ord[r*S+s] (0,1,2)
+ * (an extension: the reference only has host std::function callbacks, src/Models/Model.h:44-60;
+ * host callbacks remain supported through fspmat_generate with host arrays).
+ * out_dev[i] = d_r(state_i + sign*nu) for stored states in [first, first+count).
+ * ---------------------------------------------------------------------------------------------- */
+FSP_API int fspset_eval_mass_action(fspset_t h, double rate, const int *order_host /* S */, const int *nu_host,
+                                    int sign, long first, long count, double *out_dev);
+
+/* ------------------------------------------------------------------------------------------------
+ * The FSP operator A(t) = sum_r c_r(t) A_r (+ sink rows).
+ * Replaces FspMatrixBase / FspMatrixConstrained storage and Action:
+ *   GenerateValues  src/Matrix/FspMatrixBase.cpp:76-251, src/Matrix/FspMatrixConstrained.cpp:121-282
+ *   Action          src/Matrix/FspMatrixBase.cpp:36-62,  src/Matrix/FspMatrixConstrained.cpp:31-64
+ *   GetLocalMVFlops src/Matrix/FspMatrixBase.cpp:429-444, src/Matrix/FspMatrixConstrained.cpp:447-465
+ *   Destroy         src/Matrix/FspMatrixBase.cpp:258-275
+ * Layout handed to fspmat_generate ("reaction-plane ELL"): P = n_tv + n_ti planes of length n (leading
+ * dimension ld), TV reactions first.  Plane p, row i:
+ *   col[p*ld+i]  local index of x_i - nu_r in x (>= 0), -1 = absent, <= -2 = ghost slot -(col+2)
+ *   off[p*ld+i]  d_r(x_i - nu_r)        diag[p*ld+i]  d_r(x_i)  (positive)
+ * Sink entries: segment (p, k) = sink_ptr[p*K+k] .. sink_ptr[p*K+k+1] of (sink_idx, sink_val):
+ *   row N+k gets  c_p * sink_val * x[sink_idx].
+ * The library re-packs into its HBM layout (TI diagonals merged, planes padded/aligned).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fspmat_s *fspmat_t;
+
+typedef struct fspmat_desc {
+  int           n_states;     /* local states n */
+  int           n_rows;       /* local rows: n, or n + K on the rank that owns the sinks */
+  int           n_reactions;  /* R: length of the coefficient vector t_fun fills */
+  int           n_tv, n_ti;
+  const int    *tv_reactions; /* host, [n_tv] reaction ids */
+  const int    *ti_reactions; /* host, [n_ti] */
+  const int    *col;
+  const double *off;
+  const double *diag;
+  long          ld;
+  int           arrays_on_device; /* 0: col/off/diag/sink_idx/sink_val are host pointers; 1: device */
+  int           n_constr;         /* K (0 for FspMatrixBase) */
+  const long   *sink_ptr;         /* host, [(n_tv+n_ti)*K + 1] */
+  const int    *sink_idx;
+  const double *sink_val;
+  int           owns_sinks;       /* 1 if rows n..n+K-1 of y live on this rank */
+  long          n_ghost;          /* number of ghost slots referenced by col <= -2 */
+} fspmat_desc;
+
+FSP_API int fspmat_create(fspmat_t *out);
+FSP_API int fspmat_destroy(fspmat_t h);
+FSP_API int fspmat_generate(fspmat_t h, const fspmat_desc *desc);
+FSP_API int fspmat_clear(fspmat_t h); /* Destroy(): frees values, object reusable */
+/* y = A(t) x.  coef_host[r] = c_r(t) for r < R (only TV entries are read; TI reactions use 1).
+ * x_dev, y_dev have n_rows entries; ghost_dev has n_ghost entries (may be NULL when n_ghost == 0).
+ * On a rank that does not own the sinks, the K partial sink sums are written to sink_out_dev
+ * (K doubles) instead of y; pass NULL to drop them. */
+FSP_API int fspmat_action(fspmat_t h, const double *coef_host, const double *x_dev, const double *ghost_dev,
+                          double *y_dev, double *sink_out_dev, void *stream);
+FSP_API int fspmat_flops(fspmat_t h, long *nflops);
+FSP_API int fspmat_num_rows(fspmat_t h, int *n_rows);
+/* algorithmic bytes of one Action: n*(16 + 12 P + 8 (n_tv + [n_ti>0])) + 12 nnz_sink + 8 K */
+FSP_API int fspmat_action_bytes(fspmat_t h, double *bytes);
+/* kernel variant selection for tuning/benchmarks: 0 = default */
+FSP_API int fspmat_set_variant(fspmat_t h, int variant);
+/* dense export for tests: out_host is n_rows x n_rows column-major (ghost columns dropped) */
+FSP_API int fspmat_dense(fspmat_t h, const double *coef_host, double *out_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU plumbing (one process per GPU).  Replaces PETSc VecScatter ghost exchange inside
+ * MatMult(MATMPISELL), the sink VecScatter ADD (FspMatrixConstrained.cpp:57-60) and the
+ * MPI_Allreduce behind VecDot/VecNorm (KrylovFsp.cpp:280-309).
+ * NCCL is resolved at run time with dlopen (the already-loaded libnccl.so.2 if any).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fspcomm_s *fspcomm_t;
+#define FSPCOMM_ID_BYTES 128
+FSP_API int fspcomm_unique_id(char id[FSPCOMM_ID_BYTES]);
+FSP_API int fspcomm_create(fspcomm_t *out, const char id[FSPCOMM_ID_BYTES], int rank, int size);
+FSP_API int fspcomm_destroy(fspcomm_t c);
+FSP_API int fspcomm_rank(fspcomm_t c, int *rank, int *size);
+FSP_API int fspcomm_allreduce_sum(fspcomm_t c, double *buf_dev, long n, void *stream);
+FSP_API int fspcomm_allreduce_max(fspcomm_t c, double *buf_dev, long n, void *stream);
+FSP_API int fspcomm_reduce_sum(fspcomm_t c, double *buf_dev, long n, int root, void *stream);
+FSP_API int fspcomm_allgather_int(fspcomm_t c, const int *send_dev, int *recv_dev, long n_per_rank, void *stream);
+/* halo exchange: send_counts/recv_counts are host arrays [size]; send buffer is packed per peer in rank
+ * order, ghost buffer receives per peer in rank order. */
+FSP_API int fspcomm_halo_exchange(fspcomm_t c, const double *send_dev, const long *send_counts_host,
+                                  double *ghost_dev, const long *recv_counts_host, void *stream);
+/* pack: out[i] = x[idx[i]] is fspvec_gather */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSP_B200_H_ */

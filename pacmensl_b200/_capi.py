@@ -1,0 +1,141 @@
+"""ctypes binding of the C ABI declared in include/fsp_b200.h (libpacmensl_b200.so).
+
+The product path is the CUDA library; there is NO CPU fallback: importing this module raises if the
+shared object is missing (build it with `make` or `python -c "import __graft_entry__ as g; g.build()"`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpacmensl_b200.so")
+
+vp, ci, cl, cd = C.c_void_p, C.c_int, C.c_long, C.c_double
+ip, dp, lp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_long)
+vpp = C.POINTER(C.c_void_p)
+
+CONSTR_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_void_p)
+PROP_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, C.c_int, ip, dp, C.c_void_p)
+TCOEF_FN = C.CFUNCTYPE(C.c_int, C.c_double, C.c_int, dp, C.c_void_p)
+
+
+class FspMatDesc(C.Structure):
+    _fields_ = [
+        ("n_states", ci), ("n_rows", ci), ("n_reactions", ci), ("n_tv", ci), ("n_ti", ci),
+        ("tv_reactions", ip), ("ti_reactions", ip),
+        ("col", vp), ("off", vp), ("diag", vp), ("ld", cl),
+        ("arrays_on_device", ci), ("n_constr", ci),
+        ("sink_ptr", lp), ("sink_idx", vp), ("sink_val", vp),
+        ("owns_sinks", ci), ("n_ghost", cl),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/fsp_b200.h declares
+SIGNATURES = {
+    "fsp_device_count": (ci, [ip]),
+    "fsp_device_set": (ci, [ci]),
+    "fsp_device_get": (ci, [ip]),
+    "fsp_device_sm_count": (ci, [ip]),
+    "fsp_last_error": (C.c_char_p, []),
+    "fsp_malloc": (ci, [vpp, C.c_size_t]),
+    "fsp_free": (ci, [vp]),
+    "fsp_malloc_host": (ci, [vpp, C.c_size_t]),
+    "fsp_free_host": (ci, [vp]),
+    "fsp_memcpy_h2d": (ci, [vp, vp, C.c_size_t, vp]),
+    "fsp_memcpy_d2h": (ci, [vp, vp, C.c_size_t, vp]),
+    "fsp_memcpy_d2d": (ci, [vp, vp, C.c_size_t, vp]),
+    "fsp_memset": (ci, [vp, ci, C.c_size_t, vp]),
+    "fsp_stream_create": (ci, [vpp]),
+    "fsp_stream_destroy": (ci, [vp]),
+    "fsp_stream_sync": (ci, [vp]),
+    "fsp_device_sync": (ci, []),
+    "fsp_event_create": (ci, [vpp]),
+    "fsp_event_destroy": (ci, [vp]),
+    "fsp_event_record": (ci, [vp, vp]),
+    "fsp_event_elapsed_ms": (ci, [vp, vp, C.POINTER(C.c_float)]),
+    "fsp_launch_count": (C.c_longlong, []),
+    "fspvec_set": (ci, [vp, cd, cl, vp]),
+    "fspvec_copy": (ci, [vp, vp, cl, vp]),
+    "fspvec_scale": (ci, [vp, cd, cl, vp]),
+    "fspvec_axpy": (ci, [vp, cd, vp, cl, vp]),
+    "fspvec_linear_sum": (ci, [vp, cd, vp, cd, vp, cl, vp]),
+    "fspvec_maxpy": (ci, [vp, cd, ci, dp, vpp, cl, vp]),
+    "fspvec_mdot": (ci, [vp, vp, ci, vpp, cl, vp]),
+    "fspvec_dot": (ci, [vp, vp, vp, cl, vp]),
+    "fspvec_norm2sq": (ci, [vp, vp, cl, vp]),
+    "fspvec_sum": (ci, [vp, vp, cl, vp]),
+    "fspvec_norm1": (ci, [vp, vp, cl, vp]),
+    "fspvec_wsqsum": (ci, [vp, vp, vp, cl, vp]),
+    "fspvec_ewt": (ci, [vp, vp, cd, cd, cl, vp, vp]),
+    "fspvec_axpy_dot": (ci, [vp, vp, cd, vp, vp, vp, cl, vp]),
+    "fspvec_scale_rsqrt": (ci, [vp, vp, cl, vp]),
+    "fspvec_dot_h": (ci, [dp, vp, vp, cl, vp]),
+    "fspvec_norm2_h": (ci, [dp, vp, cl, vp]),
+    "fspvec_sum_h": (ci, [dp, vp, cl, vp]),
+    "fspvec_norm1_h": (ci, [dp, vp, cl, vp]),
+    "fspvec_scatter": (ci, [vp, cl, vp, vp, cl, vp]),
+    "fspvec_gather": (ci, [vp, vp, vp, cl, vp]),
+    "fspset_create": (ci, [vpp, ci, ci, ip]),
+    "fspset_destroy": (ci, [vp]),
+    "fspset_set_shape": (ci, [vp, ci, vp, ip, vp]),
+    "fspset_set_bounds": (ci, [vp, ci, ip]),
+    "fspset_add_states": (ci, [vp, ci, cl, vp, ci]),
+    "fspset_expand": (ci, [vp]),
+    "fspset_num_states": (ci, [vp, ip]),
+    "fspset_state2index": (ci, [vp, cl, vp, ci, vp, ci]),
+    "fspset_lookup_shifted": (ci, [vp, ip, ci, cl, cl, vp]),
+    "fspset_check_constraints_shifted": (ci, [vp, ip, cl, cl, vp]),
+    "fspset_sink_lists": (ci, [vp, ip, cl, cl, vp, cl, lp]),
+    "fspset_states_dev": (ci, [vp, vpp]),
+    "fspset_copy_states": (ci, [vp, cl, cl, ip]),
+    "fspset_copy_status": (ci, [vp, cl, cl, C.POINTER(C.c_byte)]),
+    "fspset_add_box_lattice": (ci, [vp, ip]),
+    "fspset_eval_mass_action": (ci, [vp, cd, ip, ip, ci, cl, cl, vp]),
+    "fspmat_create": (ci, [vpp]),
+    "fspmat_destroy": (ci, [vp]),
+    "fspmat_generate": (ci, [vp, C.POINTER(FspMatDesc)]),
+    "fspmat_clear": (ci, [vp]),
+    "fspmat_action": (ci, [vp, dp, vp, vp, vp, vp, vp]),
+    "fspmat_flops": (ci, [vp, lp]),
+    "fspmat_num_rows": (ci, [vp, ip]),
+    "fspmat_action_bytes": (ci, [vp, dp]),
+    "fspmat_set_variant": (ci, [vp, ci]),
+    "fspmat_dense": (ci, [vp, dp, dp]),
+    "fspcomm_unique_id": (ci, [C.c_char_p]),
+    "fspcomm_create": (ci, [vpp, C.c_char_p, ci, ci]),
+    "fspcomm_destroy": (ci, [vp]),
+    "fspcomm_rank": (ci, [vp, ip, ip]),
+    "fspcomm_allreduce_sum": (ci, [vp, vp, cl, vp]),
+    "fspcomm_allreduce_max": (ci, [vp, vp, cl, vp]),
+    "fspcomm_reduce_sum": (ci, [vp, vp, cl, ci, vp]),
+    "fspcomm_allgather_int": (ci, [vp, vp, vp, cl, vp]),
+    "fspcomm_halo_exchange": (ci, [vp, vp, lp, vp, lp, vp]),
+}
+
+_LIB = None
+
+
+def lib():
+    """Load libpacmensl_b200.so; raises (no fallback) if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "pacmensl_b200: %s is missing -- the CUDA library must be built (run `make` in the repo "
+                "root); there is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+class FspError(RuntimeError):
+    pass
+
+
+def check(ierr, what=""):
+    if ierr != 0:
+        msg = lib().fsp_last_error()
+        raise FspError("%s failed (%d): %s" % (what, ierr, msg.decode() if msg else ""))

@@ -1,0 +1,76 @@
+// fsp_common.cuh -- shared helpers for the sm_100a kernels behind include/fsp_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fsp_b200.h"
+
+namespace fspb {
+
+void        set_error(const char *fmt, ...);
+cudaStream_t resolve_stream(void *stream);
+void        count_launch(int n = 1);
+int         sm_count();
+
+#define FSP_CUDA_CHECK(expr)                                                                     \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      fspb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -1;                                                                                 \
+    }                                                                                            \
+  } while (0)
+
+#define FSP_LAUNCH_CHECK()                                                                  \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) {                                                                \
+      fspb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -1;                                                                            \
+    }                                                                                       \
+    fspb::count_launch();                                                                   \
+  } while (0)
+
+// ---- streaming (read-once) loads / write-once stores: keep x resident in L1/L2 instead ----------
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_stream(const double2 *p) { return __ldcs(p); }
+__device__ __forceinline__ int ld_stream(const int *p) { return __ldcs(p); }
+__device__ __forceinline__ int2 ld_stream(const int2 *p) { return __ldcs(p); }
+__device__ __forceinline__ int4 ld_stream(const int4 *p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(double2 *p, double2 v) { __stcs(p, v); }
+
+// ---- warp / block reductions (fixed shape => deterministic) ---------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum; result valid in thread 0. smem must hold >= 32 doubles. blockDim.x multiple of 32.
+__device__ __forceinline__ double block_sum(double v, double *smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect smem reuse across consecutive calls
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = lane < nw ? smem[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+}  // namespace fspb

@@ -1,0 +1,90 @@
+// fsp_runtime.cu -- device selection, memory, streams, events, error string (include/fsp_b200.h "Runtime").
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "fsp_common.cuh"
+
+namespace fspb {
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+cudaStream_t resolve_stream(void *stream) { return (cudaStream_t) stream; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    cached = p.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+}  // namespace fspb
+
+using namespace fspb;
+
+extern "C" {
+
+int fsp_device_count(int *count) { FSP_CUDA_CHECK(cudaGetDeviceCount(count)); return 0; }
+int fsp_device_set(int device) { FSP_CUDA_CHECK(cudaSetDevice(device)); return 0; }
+int fsp_device_get(int *device) { FSP_CUDA_CHECK(cudaGetDevice(device)); return 0; }
+int fsp_device_sm_count(int *count) { *count = sm_count(); return 0; }
+const char *fsp_last_error(void) { return g_err; }
+int fsp_malloc(void **p, size_t bytes) { FSP_CUDA_CHECK(cudaMalloc(p, bytes ? bytes : 8)); return 0; }
+int fsp_free(void *p) { if (p) FSP_CUDA_CHECK(cudaFree(p)); return 0; }
+int fsp_malloc_host(void **p, size_t bytes) { FSP_CUDA_CHECK(cudaMallocHost(p, bytes ? bytes : 8)); return 0; }
+int fsp_free_host(void *p) { if (p) FSP_CUDA_CHECK(cudaFreeHost(p)); return 0; }
+int fsp_memcpy_h2d(void *d, const void *s, size_t b, void *st) {
+  FSP_CUDA_CHECK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, resolve_stream(st)));
+  FSP_CUDA_CHECK(cudaStreamSynchronize(resolve_stream(st)));
+  return 0;
+}
+int fsp_memcpy_d2h(void *d, const void *s, size_t b, void *st) {
+  FSP_CUDA_CHECK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, resolve_stream(st)));
+  FSP_CUDA_CHECK(cudaStreamSynchronize(resolve_stream(st)));
+  return 0;
+}
+int fsp_memcpy_d2d(void *d, const void *s, size_t b, void *st) {
+  FSP_CUDA_CHECK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToDevice, resolve_stream(st)));
+  return 0;
+}
+int fsp_memset(void *d, int byte, size_t b, void *st) {
+  FSP_CUDA_CHECK(cudaMemsetAsync(d, byte, b, resolve_stream(st)));
+  return 0;
+}
+int fsp_stream_create(void **s) {
+  cudaStream_t st;
+  FSP_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *s = (void *) st;
+  return 0;
+}
+int fsp_stream_destroy(void *s) { if (s) FSP_CUDA_CHECK(cudaStreamDestroy((cudaStream_t) s)); return 0; }
+int fsp_stream_sync(void *s) { FSP_CUDA_CHECK(cudaStreamSynchronize(resolve_stream(s))); return 0; }
+int fsp_device_sync(void) { FSP_CUDA_CHECK(cudaDeviceSynchronize()); return 0; }
+int fsp_event_create(void **e) {
+  cudaEvent_t ev;
+  FSP_CUDA_CHECK(cudaEventCreate(&ev));
+  *e = (void *) ev;
+  return 0;
+}
+int fsp_event_destroy(void *e) { if (e) FSP_CUDA_CHECK(cudaEventDestroy((cudaEvent_t) e)); return 0; }
+int fsp_event_record(void *e, void *s) { FSP_CUDA_CHECK(cudaEventRecord((cudaEvent_t) e, resolve_stream(s))); return 0; }
+int fsp_event_elapsed_ms(void *a, void *b, float *ms) {
+  FSP_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t) b));
+  FSP_CUDA_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t) a, (cudaEvent_t) b));
+  return 0;
+}
+long long fsp_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

@@ -1,0 +1,596 @@
+// fspmat.cu -- the FSP operator y = A(t) x on the device (include/fsp_b200.h "The FSP operator").
+//
+// Replaces FspMatrixBase::Action / FspMatrixConstrained::Action of the reference
+// (src/Matrix/FspMatrixBase.cpp:36-62, src/Matrix/FspMatrixConstrained.cpp:31-64): there the action is
+// (R_tv + 1) PETSc MatMult passes into a work vector, each followed by a VecAXPY, then K tiny sink
+// MatMults and a VecScatter ADD.  Here it is ONE kernel launch that
+//   * reads every matrix byte exactly once with streaming (evict-first) 128-bit loads,
+//   * scales by the time-varying coefficients c_r(t) (passed by value as kernel arguments),
+//   * fuses the diagonal term, the gathered off-diagonal terms and the accumulation,
+//   * and computes the K sink rows in trailing CTAs with warp-shuffle reductions and a fixed-order
+//     (deterministic) final sum.
+//
+// HBM layout ("reaction-plane ELL"): P = n_tv + n_ti planes of leading dimension ld (multiple of 32
+// elements so every plane starts 128/256-byte aligned):
+//   col  int32 [P][ld]   local column of x_i - nu_r ; -1 = none ; <= -2 = ghost slot -(col+2)
+//   off  fp64  [P][ld]   d_r(x_i - nu_r)  (0 where col == -1)
+//   diag fp64  [ND][ld]  ND = n_tv + (n_ti > 0): one plane per TV reaction (+d_r(x_i)) and ONE merged
+//                        plane sum_{r in TI} d_r(x_i)
+// Algorithmic bytes per row = 8 (x) + 8 (y) + 12 P + 8 ND  (SURVEY.md section 8d).
+// Roofline: HBM bandwidth; arithmetic intensity ~0.15 flop/byte, so no tensor cores.
+#include <algorithm>
+#include <vector>
+
+#include "fsp_common.cuh"
+
+using namespace fspb;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxPlanes = 32;
+constexpr int kSinkChunk = 4096;  // sink entries per sink CTA
+
+struct Coefs {
+  double c[kMaxPlanes];   // per off-diagonal plane (TI planes: 1.0)
+  double cd[kMaxPlanes];  // per diagonal plane (merged TI plane: 1.0)
+};
+
+struct MatView {
+  int           n;       // local states (rows of the main block)
+  int           P, ND;
+  long          ld;
+  const int    *col;
+  const double *off;
+  const double *diag;
+  // sinks
+  int           K, G;          // G = groups = ND
+  int           main_blocks;   // CTAs [0, main_blocks) do rows, the rest do sink chunks
+  int           sink_blocks;
+  const int    *sb_seg;        // [sink_blocks] segment id g*K + k
+  const long   *sb_begin;      // [sink_blocks]
+  const long   *sb_end;        // [sink_blocks]
+  const int    *sink_idx;
+  const double *sink_val;
+  double       *sink_partials; // [sink_blocks]
+  unsigned     *sink_counter;
+  int           owns_sinks;
+};
+
+__device__ __forceinline__ double fetch_x(const double *__restrict__ x, const double *__restrict__ ghost, int c) {
+  // c >= 0: local entry; c == -1: absent neighbour (contributes 0); c <= -2: ghost slot
+  if (c >= 0) return __ldg(x + c);
+  if (c == -1) return 0.0;
+  return __ldg(ghost + (-(c + 2)));
+}
+
+// ---- sink rows: trailing CTAs --------------------------------------------------------------------
+__device__ __forceinline__ void sink_role(const MatView &m, const Coefs &cf, const double *__restrict__ x,
+                                          double *__restrict__ y, double *__restrict__ sink_out) {
+  __shared__ double smem[32];
+  __shared__ bool   is_last;
+  const int sb = blockIdx.x - m.main_blocks;
+  double    acc = 0.0;
+  if (m.sink_blocks > 0 && sb < m.sink_blocks) {
+    const long b = m.sb_begin[sb], e = m.sb_end[sb];
+    for (long q = b + threadIdx.x; q < e; q += blockDim.x) {
+      acc = fma(ld_stream(m.sink_val + q), __ldg(x + ld_stream(m.sink_idx + q)), acc);
+    }
+  }
+  double r = block_sum(acc, smem);
+  if (threadIdx.x == 0) m.sink_partials[sb] = r;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicAdd(m.sink_counter, 1u);
+    is_last = (prev == (unsigned) m.sink_blocks - 1u);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // fixed-order final sum: warp w handles constraints k = w, w + nwarps, ...
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = warp; k < m.K; k += nw) {
+    double s = 0.0;
+    for (int b = lane; b < m.sink_blocks; b += 32) {
+      int seg = m.sb_seg[b];
+      if (seg >= 0 && seg % m.K == k) s = fma(cf.cd[seg / m.K], __ldcg(m.sink_partials + b), s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (m.owns_sinks) y[m.n + k] = s;
+      if (sink_out) sink_out[k] = s;
+    }
+  }
+  if (threadIdx.x == 0) *m.sink_counter = 0u;
+}
+
+// ---- main rows: V rows per thread, P planes unrolled at compile time ------------------------------
+template <int P>
+__device__ __forceinline__ double row_scalar(const MatView &m, const Coefs &cf, const double *__restrict__ x,
+                                             const double *__restrict__ ghost, long i) {
+  int    c[P];
+  double o[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    c[p] = ld_stream(m.col + p * m.ld + i);
+    o[p] = ld_stream(m.off + p * m.ld + i);
+  }
+  const double xi = __ldg(x + i);
+  double       d = 0.0;
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(m.diag + g * m.ld + i), d);
+  double acc = 0.0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) acc = fma(cf.c[p] * o[p], fetch_x(x, ghost, c[p]), acc);
+  return fma(-d, xi, acc);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads) action_kernel_v2(MatView m, Coefs cf, const double *__restrict__ x,
+                                                             const double *__restrict__ ghost,
+                                                             double *__restrict__ y, double *__restrict__ sink_out) {
+  if ((int) blockIdx.x >= m.main_blocks) {
+    sink_role(m, cf, x, y, sink_out);
+    return;
+  }
+  const long i0 = 2 * ((long) blockIdx.x * kThreads + threadIdx.x);
+  if (i0 + 1 < m.n) {
+    int2    c[P];
+    double2 o[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      c[p] = ld_stream(reinterpret_cast<const int2 *>(m.col + p * m.ld + i0));
+      o[p] = ld_stream(reinterpret_cast<const double2 *>(m.off + p * m.ld + i0));
+    }
+    const double2 xi = __ldg(reinterpret_cast<const double2 *>(x + i0));
+    double2       d = make_double2(0.0, 0.0);
+    for (int g = 0; g < m.ND; ++g) {
+      double2 dg = ld_stream(reinterpret_cast<const double2 *>(m.diag + g * m.ld + i0));
+      d.x = fma(cf.cd[g], dg.x, d.x);
+      d.y = fma(cf.cd[g], dg.y, d.y);
+    }
+    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      acc.x = fma(cf.c[p] * o[p].x, fetch_x(x, ghost, c[p].x), acc.x);
+      acc.y = fma(cf.c[p] * o[p].y, fetch_x(x, ghost, c[p].y), acc.y);
+    }
+    acc.x = fma(-d.x, xi.x, acc.x);
+    acc.y = fma(-d.y, xi.y, acc.y);
+    st_stream(reinterpret_cast<double2 *>(y + i0), acc);
+  } else if (i0 < m.n) {
+    y[i0] = row_scalar<P>(m, cf, x, ghost, i0);
+  }
+}
+
+// 4 rows per thread: int4 column loads, 2 x double2 value loads per plane
+template <int P>
+__global__ void __launch_bounds__(kThreads) action_kernel_v4(MatView m, Coefs cf, const double *__restrict__ x,
+                                                             const double *__restrict__ ghost,
+                                                             double *__restrict__ y, double *__restrict__ sink_out) {
+  if ((int) blockIdx.x >= m.main_blocks) {
+    sink_role(m, cf, x, y, sink_out);
+    return;
+  }
+  const long i0 = 4 * ((long) blockIdx.x * kThreads + threadIdx.x);
+  if (i0 + 3 < m.n) {
+    int4    c[P];
+    double2 oa[P], ob[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      c[p] = ld_stream(reinterpret_cast<const int4 *>(m.col + p * m.ld + i0));
+      oa[p] = ld_stream(reinterpret_cast<const double2 *>(m.off + p * m.ld + i0));
+      ob[p] = ld_stream(reinterpret_cast<const double2 *>(m.off + p * m.ld + i0 + 2));
+    }
+    const double2 xa = __ldg(reinterpret_cast<const double2 *>(x + i0));
+    const double2 xb = __ldg(reinterpret_cast<const double2 *>(x + i0 + 2));
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    for (int g = 0; g < m.ND; ++g) {
+      double2 da = ld_stream(reinterpret_cast<const double2 *>(m.diag + g * m.ld + i0));
+      double2 db = ld_stream(reinterpret_cast<const double2 *>(m.diag + g * m.ld + i0 + 2));
+      d0 = fma(cf.cd[g], da.x, d0);
+      d1 = fma(cf.cd[g], da.y, d1);
+      d2 = fma(cf.cd[g], db.x, d2);
+      d3 = fma(cf.cd[g], db.y, d3);
+    }
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      a0 = fma(cf.c[p] * oa[p].x, fetch_x(x, ghost, c[p].x), a0);
+      a1 = fma(cf.c[p] * oa[p].y, fetch_x(x, ghost, c[p].y), a1);
+      a2 = fma(cf.c[p] * ob[p].x, fetch_x(x, ghost, c[p].z), a2);
+      a3 = fma(cf.c[p] * ob[p].y, fetch_x(x, ghost, c[p].w), a3);
+    }
+    st_stream(reinterpret_cast<double2 *>(y + i0), make_double2(fma(-d0, xa.x, a0), fma(-d1, xa.y, a1)));
+    st_stream(reinterpret_cast<double2 *>(y + i0 + 2), make_double2(fma(-d2, xb.x, a2), fma(-d3, xb.y, a3)));
+  } else {
+    for (long i = i0; i < m.n && i < i0 + 4; ++i) y[i] = row_scalar<P>(m, cf, x, ghost, i);
+  }
+}
+
+// 1 row per thread (also the path for unaligned x / y)
+template <int P>
+__global__ void __launch_bounds__(kThreads) action_kernel_v1(MatView m, Coefs cf, const double *__restrict__ x,
+                                                             const double *__restrict__ ghost,
+                                                             double *__restrict__ y, double *__restrict__ sink_out) {
+  if ((int) blockIdx.x >= m.main_blocks) {
+    sink_role(m, cf, x, y, sink_out);
+    return;
+  }
+  const long i = (long) blockIdx.x * kThreads + threadIdx.x;
+  if (i < m.n) y[i] = row_scalar<P>(m, cf, x, ghost, i);
+}
+
+// generic number of planes (P > 16): runtime loop
+__global__ void __launch_bounds__(kThreads) action_kernel_generic(MatView m, Coefs cf, const double *__restrict__ x,
+                                                                  const double *__restrict__ ghost,
+                                                                  double *__restrict__ y,
+                                                                  double *__restrict__ sink_out) {
+  if ((int) blockIdx.x >= m.main_blocks) {
+    sink_role(m, cf, x, y, sink_out);
+    return;
+  }
+  const long i = (long) blockIdx.x * kThreads + threadIdx.x;
+  if (i >= m.n) return;
+  const double xi = __ldg(x + i);
+  double       d = 0.0;
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(m.diag + g * m.ld + i), d);
+  double acc = 0.0;
+  for (int p = 0; p < m.P; ++p) {
+    int c = ld_stream(m.col + p * m.ld + i);
+    acc = fma(cf.c[p] * ld_stream(m.off + p * m.ld + i), fetch_x(x, ghost, c), acc);
+  }
+  y[i] = fma(-d, xi, acc);
+}
+
+typedef void (*action_fn)(MatView, Coefs, const double *, const double *, double *, double *);
+
+template <int P>
+action_fn pick_variant(int rows_per_thread) {
+  switch (rows_per_thread) {
+    case 1: return action_kernel_v1<P>;
+    case 4: return action_kernel_v4<P>;
+    default: return action_kernel_v2<P>;
+  }
+}
+
+action_fn pick_kernel(int P, int rows_per_thread) {
+  switch (P) {
+#define FSP_CASE(N) case N: return pick_variant<N>(rows_per_thread);
+    FSP_CASE(1) FSP_CASE(2) FSP_CASE(3) FSP_CASE(4) FSP_CASE(5) FSP_CASE(6) FSP_CASE(7) FSP_CASE(8)
+    FSP_CASE(9) FSP_CASE(10) FSP_CASE(11) FSP_CASE(12) FSP_CASE(13) FSP_CASE(14) FSP_CASE(15) FSP_CASE(16)
+#undef FSP_CASE
+    default: return nullptr;
+  }
+}
+
+// ---- generate-time packing kernels -----------------------------------------------------------------
+__global__ void pack_planes_kernel(int n, int P, long ld_in, long ld, const int *__restrict__ col_in,
+                                   const double *__restrict__ off_in, int *__restrict__ col,
+                                   double *__restrict__ off) {
+  long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  int  p = blockIdx.y;
+  if (i >= ld) return;
+  int    c = -1;
+  double o = 0.0;
+  if (i < n) {
+    c = col_in[p * ld_in + i];
+    o = c == -1 ? 0.0 : off_in[p * ld_in + i];  // dropped entries must not inject NaN/Inf
+  }
+  col[p * ld + i] = c;
+  off[p * ld + i] = o;
+}
+
+__global__ void pack_diag_kernel(int n, int n_tv, int n_ti, long ld_in, long ld, const double *__restrict__ diag_in,
+                                 double *__restrict__ diag) {
+  long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld) return;
+  for (int g = 0; g < n_tv; ++g) diag[g * ld + i] = i < n ? diag_in[g * ld_in + i] : 0.0;
+  if (n_ti > 0) {
+    // merged TI diagonal, summed in ti_reactions_ order like the reference's ADD_VALUES
+    // (src/Matrix/FspMatrixBase.cpp:229-243): ((-d0) + (-d1)) + ... == -((d0 + d1) + ...)
+    double s = 0.0;
+    if (i < n)
+      for (int q = 0; q < n_ti; ++q) s += diag_in[(n_tv + q) * ld_in + i];
+    diag[n_tv * ld + i] = s;
+  }
+}
+
+// nnz bookkeeping for GetLocalMVFlops (src/Matrix/FspMatrixBase.cpp:429-444): counts[0..n_tv) = stored
+// off-diagonal entries per TV matrix, counts[n_tv] = distinct off-diagonal columns per row of the merged
+// TI matrix (ADD_VALUES merges entries landing on the same (i, j)).
+__global__ void count_nnz_kernel(int n, int n_tv, int n_ti, long ld, const int *__restrict__ col,
+                                 unsigned long long *__restrict__ counts) {
+  long               i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long local[kMaxPlanes + 1];
+  for (int g = 0; g <= n_tv; ++g) local[g] = 0;
+  if (i < n) {
+    for (int g = 0; g < n_tv; ++g) {
+      int c = col[g * ld + i];
+      local[g] += (c != -1 && c != (int) i) ? 1 : 0;
+    }
+    for (int q = 0; q < n_ti; ++q) {
+      int c = col[(n_tv + q) * ld + i];
+      if (c == -1 || c == (int) i) continue;
+      bool dup = false;
+      for (int q2 = 0; q2 < q; ++q2) dup |= (col[(n_tv + q2) * ld + i] == c);
+      local[n_tv] += dup ? 0 : 1;
+    }
+  }
+  for (int g = 0; g <= n_tv; ++g) {
+    unsigned long long v = local[g];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[g], v);
+  }
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------------------
+struct fspmat_s {
+  bool has_values = false;
+  int  n = 0, n_rows = 0, R = 0, n_tv = 0, n_ti = 0, P = 0, ND = 0, K = 0, owns_sinks = 0;
+  long n_ghost = 0, ld = 0;
+  std::vector<int> tv, ti;
+  int     *d_col = nullptr;
+  double  *d_off = nullptr;
+  double  *d_diag = nullptr;
+  // sinks (merged into G = ND groups)
+  long     sink_nnz = 0;
+  int     *d_sink_idx = nullptr;
+  double  *d_sink_val = nullptr;
+  int      sink_blocks = 0;
+  int     *d_sb_seg = nullptr;
+  long    *d_sb_begin = nullptr, *d_sb_end = nullptr;
+  double  *d_sink_partials = nullptr;
+  unsigned *d_sink_counter = nullptr;
+  std::vector<long> seg_ptr;  // [G*K + 1] host copy of merged segments
+  long     flops = 0;
+  double   bytes = 0.0;
+  int      variant = 0;
+};
+
+static int free_values(fspmat_s *h) {
+  cudaFree(h->d_col); cudaFree(h->d_off); cudaFree(h->d_diag);
+  cudaFree(h->d_sink_idx); cudaFree(h->d_sink_val);
+  cudaFree(h->d_sb_seg); cudaFree(h->d_sb_begin); cudaFree(h->d_sb_end);
+  cudaFree(h->d_sink_partials); cudaFree(h->d_sink_counter);
+  int variant = h->variant;
+  *h = fspmat_s();
+  h->variant = variant;
+  return 0;
+}
+
+extern "C" {
+
+int fspmat_create(fspmat_t *out) {
+  *out = new fspmat_s();
+  return 0;
+}
+
+int fspmat_destroy(fspmat_t h) {
+  if (!h) return 0;
+  free_values(h);
+  delete h;
+  return 0;
+}
+
+int fspmat_clear(fspmat_t h) { return free_values(h); }
+
+int fspmat_set_variant(fspmat_t h, int variant) {
+  h->variant = variant;
+  return 0;
+}
+
+int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
+  free_values(h);
+  const int P = d->n_tv + d->n_ti;
+  if (P > kMaxPlanes) { set_error("fspmat_generate: %d reactions exceed the supported %d", P, kMaxPlanes); return -1; }
+  if (d->n_states < 0 || d->n_rows < d->n_states) { set_error("fspmat_generate: bad sizes"); return -1; }
+  h->n = d->n_states; h->n_rows = d->n_rows; h->R = d->n_reactions;
+  h->n_tv = d->n_tv; h->n_ti = d->n_ti; h->P = P; h->ND = d->n_tv + (d->n_ti > 0 ? 1 : 0);
+  h->K = d->n_constr; h->owns_sinks = d->owns_sinks; h->n_ghost = d->n_ghost;
+  h->tv.assign(d->tv_reactions, d->tv_reactions + d->n_tv);
+  h->ti.assign(d->ti_reactions, d->ti_reactions + d->n_ti);
+  const long n = h->n;
+  h->ld = ((n + 31) / 32) * 32;
+  if (h->ld == 0) h->ld = 32;
+  const long ld = h->ld;
+  cudaStream_t st = 0;
+
+  if (P > 0) {
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_col, sizeof(int) * P * ld));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_off, sizeof(double) * P * ld));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_diag, sizeof(double) * std::max(h->ND, 1) * ld));
+    const int *col_in = d->col; const double *off_in = d->off, *diag_in = d->diag;
+    int *t_col = nullptr; double *t_off = nullptr, *t_diag = nullptr;
+    long ld_in = d->ld;
+    if (!d->arrays_on_device) {
+      // stage through the device with a dense leading dimension
+      FSP_CUDA_CHECK(cudaMalloc(&t_col, sizeof(int) * P * std::max(n, 1L)));
+      FSP_CUDA_CHECK(cudaMalloc(&t_off, sizeof(double) * P * std::max(n, 1L)));
+      FSP_CUDA_CHECK(cudaMalloc(&t_diag, sizeof(double) * P * std::max(n, 1L)));
+      if (n > 0) {
+        FSP_CUDA_CHECK(cudaMemcpy2D(t_col, sizeof(int) * n, d->col, sizeof(int) * d->ld, sizeof(int) * n, P, cudaMemcpyHostToDevice));
+        FSP_CUDA_CHECK(cudaMemcpy2D(t_off, sizeof(double) * n, d->off, sizeof(double) * d->ld, sizeof(double) * n, P, cudaMemcpyHostToDevice));
+        FSP_CUDA_CHECK(cudaMemcpy2D(t_diag, sizeof(double) * n, d->diag, sizeof(double) * d->ld, sizeof(double) * n, P, cudaMemcpyHostToDevice));
+      }
+      col_in = t_col; off_in = t_off; diag_in = t_diag; ld_in = n;
+    }
+    dim3 grid((unsigned) ((ld + 255) / 256), P);
+    pack_planes_kernel<<<grid, 256, 0, st>>>((int) n, P, ld_in, ld, col_in, off_in, h->d_col, h->d_off);
+    FSP_LAUNCH_CHECK();
+    pack_diag_kernel<<<(unsigned) ((ld + 255) / 256), 256, 0, st>>>((int) n, h->n_tv, h->n_ti, ld_in, ld, diag_in, h->d_diag);
+    FSP_LAUNCH_CHECK();
+    FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(t_col); cudaFree(t_off); cudaFree(t_diag);
+  }
+
+  // ---- flops: 2 nnz per matrix (+ rows per TV axpy); FspMatrixBase.cpp:429-444 -------------------
+  std::vector<unsigned long long> counts(h->n_tv + 1, 0ull);
+  if (P > 0 && n > 0) {
+    unsigned long long *d_counts;
+    FSP_CUDA_CHECK(cudaMalloc(&d_counts, sizeof(unsigned long long) * (h->n_tv + 1)));
+    FSP_CUDA_CHECK(cudaMemset(d_counts, 0, sizeof(unsigned long long) * (h->n_tv + 1)));
+    count_nnz_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>((int) n, h->n_tv, h->n_ti, ld, h->d_col, d_counts);
+    FSP_LAUNCH_CHECK();
+    FSP_CUDA_CHECK(cudaMemcpy(counts.data(), d_counts, sizeof(unsigned long long) * (h->n_tv + 1), cudaMemcpyDeviceToHost));
+    cudaFree(d_counts);
+  }
+  long flops = 0;
+  if (h->n_ti > 0) flops += 2 * ((long) counts[h->n_tv] + n);
+  for (int g = 0; g < h->n_tv; ++g) flops += 2 * ((long) counts[g] + n) + h->n_rows;
+
+  // ---- sinks: merge TI planes' segments into one group per constraint ----------------------------
+  const int K = h->K, G = h->ND;
+  long total_sink = 0;
+  if (K > 0) {
+    const long *sp = d->sink_ptr;
+    long nnz_in = sp ? sp[(long) P * K] : 0;
+    std::vector<int>    idx_in(nnz_in);
+    std::vector<double> val_in(nnz_in);
+    if (nnz_in > 0) {
+      cudaMemcpyKind kind = d->arrays_on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost;
+      FSP_CUDA_CHECK(cudaMemcpy(idx_in.data(), d->sink_idx, sizeof(int) * nnz_in, kind));
+      FSP_CUDA_CHECK(cudaMemcpy(val_in.data(), d->sink_val, sizeof(double) * nnz_in, kind));
+    }
+    std::vector<int>    idx; idx.reserve(nnz_in);
+    std::vector<double> val; val.reserve(nnz_in);
+    h->seg_ptr.assign((size_t) G * K + 1, 0);
+    long ti_sink_distinct = 0;
+    std::vector<long> tv_sink_nnz(h->n_tv, 0);
+    for (int g = 0; g < G; ++g) {
+      for (int k = 0; k < K; ++k) {
+        h->seg_ptr[(size_t) g * K + k] = (long) idx.size();
+        if (g < h->n_tv) {
+          for (long q = sp[(long) g * K + k]; q < sp[(long) g * K + k + 1]; ++q) { idx.push_back(idx_in[q]); val.push_back(val_in[q]); }
+          tv_sink_nnz[g] += sp[(long) g * K + k + 1] - sp[(long) g * K + k];
+        } else {
+          size_t start = idx.size();
+          for (int q2 = 0; q2 < h->n_ti; ++q2) {
+            int p = h->n_tv + q2;
+            for (long q = sp[(long) p * K + k]; q < sp[(long) p * K + k + 1]; ++q) { idx.push_back(idx_in[q]); val.push_back(val_in[q]); }
+          }
+          // distinct (k, i) pairs, as PETSc's ADD_VALUES would store them (FspMatrixConstrained.cpp:220-240)
+          std::vector<int> tmp(idx.begin() + start, idx.end());
+          std::sort(tmp.begin(), tmp.end());
+          ti_sink_distinct += (long) (std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+        }
+      }
+    }
+    h->seg_ptr[(size_t) G * K] = (long) idx.size();
+    total_sink = (long) idx.size();
+    h->sink_nnz = total_sink;
+    // FspMatrixConstrained.cpp:447-465
+    if (h->n_ti > 0) flops += 2 * ti_sink_distinct;
+    for (int g = 0; g < h->n_tv; ++g) flops += 2 * tv_sink_nnz[g] + K;
+
+    // chunk the segments into sink CTAs
+    std::vector<int>  sb_seg;
+    std::vector<long> sb_b, sb_e;
+    for (int s = 0; s < G * K; ++s) {
+      for (long b = h->seg_ptr[s]; b < h->seg_ptr[s + 1]; b += kSinkChunk) {
+        sb_seg.push_back(s); sb_b.push_back(b); sb_e.push_back(std::min(b + kSinkChunk, h->seg_ptr[s + 1]));
+      }
+    }
+    if (sb_seg.empty()) { sb_seg.push_back(-1); sb_b.push_back(0); sb_e.push_back(0); }
+    h->sink_blocks = (int) sb_seg.size();
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_sink_idx, sizeof(int) * std::max(total_sink, 1L)));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_sink_val, sizeof(double) * std::max(total_sink, 1L)));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_sb_seg, sizeof(int) * h->sink_blocks));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_sb_begin, sizeof(long) * h->sink_blocks));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_sb_end, sizeof(long) * h->sink_blocks));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_sink_partials, sizeof(double) * h->sink_blocks));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_sink_counter, sizeof(unsigned)));
+    FSP_CUDA_CHECK(cudaMemset(h->d_sink_counter, 0, sizeof(unsigned)));
+    if (total_sink > 0) {
+      FSP_CUDA_CHECK(cudaMemcpy(h->d_sink_idx, idx.data(), sizeof(int) * total_sink, cudaMemcpyHostToDevice));
+      FSP_CUDA_CHECK(cudaMemcpy(h->d_sink_val, val.data(), sizeof(double) * total_sink, cudaMemcpyHostToDevice));
+    }
+    FSP_CUDA_CHECK(cudaMemcpy(h->d_sb_seg, sb_seg.data(), sizeof(int) * h->sink_blocks, cudaMemcpyHostToDevice));
+    FSP_CUDA_CHECK(cudaMemcpy(h->d_sb_begin, sb_b.data(), sizeof(long) * h->sink_blocks, cudaMemcpyHostToDevice));
+    FSP_CUDA_CHECK(cudaMemcpy(h->d_sb_end, sb_e.data(), sizeof(long) * h->sink_blocks, cudaMemcpyHostToDevice));
+  }
+  h->flops = flops;
+  h->bytes = (double) n * (16.0 + 12.0 * P + 8.0 * h->ND) + 12.0 * (double) total_sink + 8.0 * K;
+  h->has_values = true;
+  return 0;
+}
+
+int fspmat_action(fspmat_t h, const double *coef_host, const double *x, const double *ghost, double *y,
+                  double *sink_out, void *stream) {
+  cudaStream_t st = resolve_stream(stream);
+  if (!h->has_values) {  // FspMatrixBase.cpp:41 -- an operator without values acts as zero
+    return 0;
+  }
+  Coefs cf;
+  for (int g = 0; g < h->n_tv; ++g) { cf.c[g] = coef_host[h->tv[g]]; cf.cd[g] = cf.c[g]; }
+  for (int q = 0; q < h->n_ti; ++q) cf.c[h->n_tv + q] = 1.0;
+  if (h->n_ti > 0) cf.cd[h->n_tv] = 1.0;
+
+  MatView m;
+  m.n = h->n; m.P = h->P; m.ND = h->ND; m.ld = h->ld;
+  m.col = h->d_col; m.off = h->d_off; m.diag = h->d_diag;
+  m.K = h->K; m.G = h->ND;
+  m.sink_blocks = (h->K > 0 && (h->owns_sinks || sink_out)) ? h->sink_blocks : 0;
+  m.sb_seg = h->d_sb_seg; m.sb_begin = h->d_sb_begin; m.sb_end = h->d_sb_end;
+  m.sink_idx = h->d_sink_idx; m.sink_val = h->d_sink_val;
+  m.sink_partials = h->d_sink_partials; m.sink_counter = h->d_sink_counter;
+  m.owns_sinks = h->owns_sinks;
+
+  int rows_per_thread = h->variant == 1 ? 1 : (h->variant == 4 ? 4 : 2);
+  if (h->variant == 0) rows_per_thread = 2;
+  // vector paths need 16-byte aligned x and y
+  if (((uintptr_t) x & 15u) || ((uintptr_t) y & 15u)) rows_per_thread = 1;
+  action_fn fn = pick_kernel(h->P, rows_per_thread);
+  if (!fn) { fn = action_kernel_generic; rows_per_thread = 1; }
+  long per_block = (long) kThreads * rows_per_thread;
+  m.main_blocks = (int) ((h->n + per_block - 1) / per_block);
+  int grid = m.main_blocks + m.sink_blocks;
+  if (grid == 0) return 0;
+  fn<<<grid, kThreads, 0, st>>>(m, cf, x, ghost, y, sink_out);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fspmat_flops(fspmat_t h, long *nflops) { *nflops = h->flops; return 0; }
+int fspmat_num_rows(fspmat_t h, int *n_rows) { *n_rows = h->n_rows; return 0; }
+int fspmat_action_bytes(fspmat_t h, double *bytes) { *bytes = h->bytes; return 0; }
+
+int fspmat_dense(fspmat_t h, const double *coef_host, double *out) {
+  const long nr = h->n_rows, n = h->n, ld = h->ld;
+  for (long q = 0; q < nr * nr; ++q) out[q] = 0.0;
+  if (!h->has_values) return 0;
+  std::vector<int>    col((size_t) h->P * ld);
+  std::vector<double> off((size_t) h->P * ld), diag((size_t) std::max(h->ND, 1) * ld);
+  if (h->P > 0) {
+    FSP_CUDA_CHECK(cudaMemcpy(col.data(), h->d_col, sizeof(int) * h->P * ld, cudaMemcpyDeviceToHost));
+    FSP_CUDA_CHECK(cudaMemcpy(off.data(), h->d_off, sizeof(double) * h->P * ld, cudaMemcpyDeviceToHost));
+    FSP_CUDA_CHECK(cudaMemcpy(diag.data(), h->d_diag, sizeof(double) * h->ND * ld, cudaMemcpyDeviceToHost));
+  }
+  for (int p = 0; p < h->P; ++p) {
+    double c = p < h->n_tv ? coef_host[h->tv[p]] : 1.0;
+    for (long i = 0; i < n; ++i) {
+      int j = col[(size_t) p * ld + i];
+      if (j >= 0) out[(size_t) j * nr + i] += c * off[(size_t) p * ld + i];
+    }
+  }
+  for (int g = 0; g < h->ND; ++g) {
+    double c = g < h->n_tv ? coef_host[h->tv[g]] : 1.0;
+    for (long i = 0; i < n; ++i) out[(size_t) i * nr + i] -= c * diag[(size_t) g * ld + i];
+  }
+  if (h->K > 0 && h->owns_sinks && h->sink_nnz > 0) {
+    std::vector<int>    idx(h->sink_nnz);
+    std::vector<double> val(h->sink_nnz);
+    FSP_CUDA_CHECK(cudaMemcpy(idx.data(), h->d_sink_idx, sizeof(int) * h->sink_nnz, cudaMemcpyDeviceToHost));
+    FSP_CUDA_CHECK(cudaMemcpy(val.data(), h->d_sink_val, sizeof(double) * h->sink_nnz, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < h->ND; ++g) {
+      double c = g < h->n_tv ? coef_host[h->tv[g]] : 1.0;
+      for (int k = 0; k < h->K; ++k)
+        for (long q = h->seg_ptr[(size_t) g * h->K + k]; q < h->seg_ptr[(size_t) g * h->K + k + 1]; ++q)
+          out[(size_t) idx[q] * nr + (n + k)] += c * val[q];
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,421 @@
+// fspvec.cu -- fp64 device-vector kernels (include/fsp_b200.h "Device vectors").
+//
+// Replaces the PETSc Vec BLAS-1 calls of the hot path (VecSet/Copy/Scale/AXPY/Dot/Norm/MAXPY,
+// reference src/OdeSolver/KrylovFsp.cpp:138,153,244-252,280-309) and the N_Vector ops CVODE needs.
+// All kernels are HBM-bound streaming passes: grid-stride loops with 128-bit loads where the base
+// pointers allow it, grids sized as a multiple of the SM count, and two-stage fixed-shape reductions
+// (per-block partials -> last block sums them in a fixed order), so results are deterministic.
+#include "fsp_common.cuh"
+
+using namespace fspb;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxRed = 8;          // outputs per reduction kernel
+constexpr int kMaxBlocks = 148 * 8; // partials per output
+constexpr int kSlots = 64;          // scratch ring (reductions in flight across streams)
+
+struct RedScratch {
+  double   *partials = nullptr;  // [kSlots][kMaxRed][kMaxBlocks]
+  unsigned *counters = nullptr;  // [kSlots]
+  int       next = 0;
+  int       device = -1;
+};
+thread_local RedScratch g_scratch[16];
+
+int get_scratch(double **partials, unsigned **counter) {
+  int dev = 0;
+  FSP_CUDA_CHECK(cudaGetDevice(&dev));
+  RedScratch &s = g_scratch[dev & 15];
+  if (!s.partials) {
+    FSP_CUDA_CHECK(cudaMalloc(&s.partials, sizeof(double) * kSlots * kMaxRed * kMaxBlocks));
+    FSP_CUDA_CHECK(cudaMalloc(&s.counters, sizeof(unsigned) * kSlots));
+    FSP_CUDA_CHECK(cudaMemset(s.counters, 0, sizeof(unsigned) * kSlots));
+    s.device = dev;
+  }
+  int slot = s.next;
+  s.next = (s.next + 1) % kSlots;
+  *partials = s.partials + (size_t) slot * kMaxRed * kMaxBlocks;
+  *counter = s.counters + slot;
+  return 0;
+}
+
+inline int grid_for(long n, int per_thread = 4) {
+  long b = (n + (long) kThreads * per_thread - 1) / ((long) kThreads * per_thread);
+  long cap = (long) sm_count() * 8;
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  if (b < 1) b = 1;
+  return (int) (b < cap ? b : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise kernels
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(kThreads) map_kernel(F f, long n) {
+  long stride = (long) gridDim.x * blockDim.x;
+  long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  // 2-way unrolled grid-stride loop: independent loads in flight
+  for (; i + stride < n; i += 2 * stride) {
+    f(i);
+    f(i + stride);
+  }
+  if (i < n) f(i);
+}
+
+// pairs of doubles per thread (128-bit accesses) when every base pointer is 16B aligned
+template <class F2>
+__global__ void __launch_bounds__(kThreads) map2_kernel(F2 f, long n2) {
+  long stride = (long) gridDim.x * blockDim.x;
+  long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n2; i += 2 * stride) {
+    f(i);
+    f(i + stride);
+  }
+  if (i < n2) f(i);
+}
+
+inline bool aligned16(const void *p) { return (((uintptr_t) p) & 15u) == 0; }
+
+struct SetF {
+  double *y; double a;
+  __device__ void operator()(long i) const { y[i] = a; }
+};
+struct CopyF {
+  double *y; const double *x;
+  __device__ void operator()(long i) const { y[i] = x[i]; }
+};
+struct Copy2F {
+  double2 *y; const double2 *x;
+  __device__ void operator()(long i) const { y[i] = x[i]; }
+};
+struct ScaleF {
+  double *y; double a;
+  __device__ void operator()(long i) const { y[i] *= a; }
+};
+struct Scale2F {
+  double2 *y; double a;
+  __device__ void operator()(long i) const { double2 v = y[i]; v.x *= a; v.y *= a; y[i] = v; }
+};
+struct AxpyF {
+  double *y; double a; const double *x;
+  __device__ void operator()(long i) const { y[i] = fma(a, x[i], y[i]); }
+};
+struct Axpy2F {
+  double2 *y; double a; const double2 *x;
+  __device__ void operator()(long i) const {
+    double2 v = y[i], w = x[i];
+    v.x = fma(a, w.x, v.x); v.y = fma(a, w.y, v.y);
+    y[i] = v;
+  }
+};
+struct LinSumF {
+  double *z; double a; const double *x; double b; const double *y;
+  __device__ void operator()(long i) const { z[i] = a * x[i] + b * y[i]; }
+};
+struct ScaleRsqrtF {
+  double *w; const double *nsq;
+  __device__ void operator()(long i) const { w[i] *= 1.0 / sqrt(*nsq); }
+};
+struct ScatterF {
+  double *pn; const double *po; const int *idx;
+  __device__ void operator()(long i) const { int j = idx[i]; if (j >= 0) pn[j] = po[i]; }
+};
+struct GatherF {
+  double *o; const double *x; const int *idx;
+  __device__ void operator()(long i) const { int j = idx[i]; o[i] = j >= 0 ? x[j] : 0.0; }
+};
+
+constexpr int kMaxpy = 64;
+struct MaxpyArgs {
+  const double *X[kMaxpy];
+  double        a[kMaxpy];
+};
+__global__ void __launch_bounds__(kThreads) maxpy_kernel(double *y, double beta, int m, MaxpyArgs args, long n) {
+  long stride = (long) gridDim.x * blockDim.x;
+  for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double acc = beta == 0.0 ? 0.0 : beta * y[i];
+    int k = 0;
+    for (; k + 4 <= m; k += 4) {  // 4 independent loads in flight per thread
+      double x0 = __ldcs(args.X[k] + i), x1 = __ldcs(args.X[k + 1] + i), x2 = __ldcs(args.X[k + 2] + i),
+             x3 = __ldcs(args.X[k + 3] + i);
+      acc = fma(args.a[k], x0, acc);
+      acc = fma(args.a[k + 1], x1, acc);
+      acc = fma(args.a[k + 2], x2, acc);
+      acc = fma(args.a[k + 3], x3, acc);
+    }
+    for (; k < m; ++k) acc = fma(args.a[k], __ldcs(args.X[k] + i), acc);
+    y[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions: M outputs per pass
+// ---------------------------------------------------------------------------------------------
+enum RedOp { RED_SUM = 0, RED_MIN = 1 };
+
+template <int M, int OP, class F>
+__global__ void __launch_bounds__(kThreads) reduce_kernel(F f, long n, double *partials, unsigned *counter,
+                                                          double *out) {
+  __shared__ double smem[32];
+  __shared__ bool   is_last;
+  double acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = OP == RED_MIN ? 1.0e300 : 0.0;
+  long stride = (long) gridDim.x * blockDim.x;
+  for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i, acc);
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    double r;
+    if (OP == RED_MIN) {
+      // min via block_sum-shaped reduction
+      double v = warp_min(acc[m]);
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      __syncthreads();
+      if (lane == 0) smem[warp] = v;
+      __syncthreads();
+      r = 1.0e300;
+      if (warp == 0) { r = lane < nw ? smem[lane] : 1.0e300; r = warp_min(r); }
+    } else {
+      r = block_sum(acc[m], smem);
+    }
+    if (threadIdx.x == 0) partials[(size_t) m * kMaxBlocks + blockIdx.x] = r;
+  }
+  __threadfence();
+  if (threadIdx.x == 0) {
+    unsigned prev = atomicAdd(counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      double v = OP == RED_MIN ? 1.0e300 : 0.0;
+      for (int b = threadIdx.x; b < (int) gridDim.x; b += blockDim.x) {
+        double p = __ldcg(&partials[(size_t) m * kMaxBlocks + b]);
+        v = OP == RED_MIN ? fmin(v, p) : v + p;
+      }
+      double r;
+      if (OP == RED_MIN) {
+        double w = warp_min(v);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        __syncthreads();
+        if (lane == 0) smem[warp] = w;
+        __syncthreads();
+        r = 1.0e300;
+        if (warp == 0) { r = lane < nw ? smem[lane] : 1.0e300; r = warp_min(r); }
+      } else {
+        r = block_sum(v, smem);
+      }
+      if (threadIdx.x == 0) out[m] = r;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+template <int M, int OP, class F>
+int launch_reduce(F f, long n, double *out_dev, void *stream) {
+  double   *partials;
+  unsigned *counter;
+  if (get_scratch(&partials, &counter)) return -1;
+  int grid = grid_for(n);
+  reduce_kernel<M, OP, F><<<grid, kThreads, 0, resolve_stream(stream)>>>(f, n, partials, counter, out_dev);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+struct DotF {
+  const double *x, *y;
+  __device__ void operator()(long i, double (&acc)[1]) const { acc[0] = fma(x[i], y[i], acc[0]); }
+};
+struct SumF {
+  const double *x;
+  __device__ void operator()(long i, double (&acc)[1]) const { acc[0] += x[i]; }
+};
+struct Norm1F {
+  const double *x;
+  __device__ void operator()(long i, double (&acc)[1]) const { acc[0] += fabs(x[i]); }
+};
+struct WsqF {
+  const double *x, *w;
+  __device__ void operator()(long i, double (&acc)[1]) const { double v = x[i] * w[i]; acc[0] = fma(v, v, acc[0]); }
+};
+template <int M>
+struct MdotF {
+  const double *x;
+  const double *Y[M];
+  __device__ void operator()(long i, double (&acc)[M]) const {
+    double xi = x[i];
+#pragma unroll
+    for (int m = 0; m < M; ++m) acc[m] = fma(xi, Y[m][i], acc[m]);
+  }
+};
+struct EwtF {
+  double *w; const double *y; double rtol, atol;
+  __device__ void operator()(long i, double (&acc)[1]) const {
+    double t = rtol * fabs(y[i]) + atol;
+    w[i] = 1.0 / t;
+    acc[0] = fmin(acc[0], t);
+  }
+};
+struct AxpyDotF {
+  double *w; const double *h; double sign; const double *v; const double *u;
+  __device__ void operator()(long i, double (&acc)[1]) const {
+    double wi = fma(-sign * (*h), v[i], w[i]);
+    w[i] = wi;
+    acc[0] = fma(wi, u ? u[i] : wi, acc[0]);
+  }
+};
+
+template <class F>
+int launch_map(F f, long n, void *stream) {
+  if (n <= 0) return 0;
+  map_kernel<F><<<grid_for(n, 2), kThreads, 0, resolve_stream(stream)>>>(f, n);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+template <class F2>
+int launch_map2(F2 f, long n2, void *stream) {
+  if (n2 <= 0) return 0;
+  map2_kernel<F2><<<grid_for(n2, 2), kThreads, 0, resolve_stream(stream)>>>(f, n2);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int M>
+int mdot_impl(double *out, const double *x, const double *const *Y, long n, void *stream) {
+  MdotF<M> f;
+  f.x = x;
+  for (int m = 0; m < M; ++m) f.Y[m] = Y[m];
+  return launch_reduce<M, RED_SUM>(f, n, out, stream);
+}
+
+int host_result(double *out_host, double *tmp_dev, void *stream) {
+  FSP_CUDA_CHECK(cudaMemcpyAsync(out_host, tmp_dev, sizeof(double), cudaMemcpyDeviceToHost, resolve_stream(stream)));
+  FSP_CUDA_CHECK(cudaStreamSynchronize(resolve_stream(stream)));
+  return 0;
+}
+
+thread_local double *g_tmp[16] = {nullptr};
+int tmp_scalar(double **p) {
+  int dev = 0;
+  FSP_CUDA_CHECK(cudaGetDevice(&dev));
+  if (!g_tmp[dev & 15]) FSP_CUDA_CHECK(cudaMalloc(&g_tmp[dev & 15], sizeof(double) * 16));
+  *p = g_tmp[dev & 15];
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fspvec_set(double *y, double a, long n, void *s) { return launch_map(SetF{y, a}, n, s); }
+
+int fspvec_copy(double *y, const double *x, long n, void *s) {
+  if (n <= 0 || y == x) return 0;
+  if (aligned16(y) && aligned16(x) && (n % 2 == 0))
+    return launch_map2(Copy2F{(double2 *) y, (const double2 *) x}, n / 2, s);
+  return launch_map(CopyF{y, x}, n, s);
+}
+
+int fspvec_scale(double *y, double a, long n, void *s) {
+  if (aligned16(y) && (n % 2 == 0)) return launch_map2(Scale2F{(double2 *) y, a}, n / 2, s);
+  return launch_map(ScaleF{y, a}, n, s);
+}
+
+int fspvec_axpy(double *y, double a, const double *x, long n, void *s) {
+  if (aligned16(y) && aligned16(x) && (n % 2 == 0))
+    return launch_map2(Axpy2F{(double2 *) y, a, (const double2 *) x}, n / 2, s);
+  return launch_map(AxpyF{y, a, x}, n, s);
+}
+
+int fspvec_linear_sum(double *z, double a, const double *x, double b, const double *y, long n, void *s) {
+  return launch_map(LinSumF{z, a, x, b, y}, n, s);
+}
+
+int fspvec_maxpy(double *y, double beta, int m, const double *alpha, const double *const *X, long n, void *s) {
+  if (m < 0 || m > kMaxpy) { set_error("fspvec_maxpy: m=%d out of range (max %d)", m, kMaxpy); return -1; }
+  if (n <= 0) return 0;
+  MaxpyArgs args;
+  for (int k = 0; k < m; ++k) { args.X[k] = X[k]; args.a[k] = alpha[k]; }
+  maxpy_kernel<<<grid_for(n, 1), kThreads, 0, resolve_stream(s)>>>(y, beta, m, args, n);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fspvec_mdot(double *out, const double *x, int m, const double *const *Y, long n, void *s) {
+  switch (m) {
+    case 1: return mdot_impl<1>(out, x, Y, n, s);
+    case 2: return mdot_impl<2>(out, x, Y, n, s);
+    case 3: return mdot_impl<3>(out, x, Y, n, s);
+    case 4: return mdot_impl<4>(out, x, Y, n, s);
+    case 5: return mdot_impl<5>(out, x, Y, n, s);
+    case 6: return mdot_impl<6>(out, x, Y, n, s);
+    case 7: return mdot_impl<7>(out, x, Y, n, s);
+    case 8: return mdot_impl<8>(out, x, Y, n, s);
+    default: set_error("fspvec_mdot: m=%d out of range (1..8)", m); return -1;
+  }
+}
+
+int fspvec_dot(double *out, const double *x, const double *y, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(DotF{x, y}, n, out, s);
+}
+int fspvec_norm2sq(double *out, const double *x, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(DotF{x, x}, n, out, s);
+}
+int fspvec_sum(double *out, const double *x, long n, void *s) { return launch_reduce<1, RED_SUM>(SumF{x}, n, out, s); }
+int fspvec_norm1(double *out, const double *x, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(Norm1F{x}, n, out, s);
+}
+int fspvec_wsqsum(double *out, const double *x, const double *w, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(WsqF{x, w}, n, out, s);
+}
+int fspvec_ewt(double *w, const double *y, double rtol, double atol, long n, double *min_out, void *s) {
+  double *tmp = min_out;
+  if (!tmp && tmp_scalar(&tmp)) return -1;
+  return launch_reduce<1, RED_MIN>(EwtF{w, y, rtol, atol}, n, tmp, s);
+}
+int fspvec_axpy_dot(double *w, const double *h, double sign, const double *v, const double *u, double *out, long n,
+                    void *s) {
+  return launch_reduce<1, RED_SUM>(AxpyDotF{w, h, sign, v, u}, n, out, s);
+}
+int fspvec_scale_rsqrt(double *w, const double *nsq, long n, void *s) { return launch_map(ScaleRsqrtF{w, nsq}, n, s); }
+
+int fspvec_dot_h(double *out, const double *x, const double *y, long n, void *s) {
+  double *tmp;
+  if (tmp_scalar(&tmp)) return -1;
+  if (fspvec_dot(tmp, x, y, n, s)) return -1;
+  return host_result(out, tmp, s);
+}
+int fspvec_norm2_h(double *out, const double *x, long n, void *s) {
+  double *tmp;
+  if (tmp_scalar(&tmp)) return -1;
+  if (fspvec_norm2sq(tmp, x, n, s)) return -1;
+  if (host_result(out, tmp, s)) return -1;
+  *out = sqrt(*out);
+  return 0;
+}
+int fspvec_sum_h(double *out, const double *x, long n, void *s) {
+  double *tmp;
+  if (tmp_scalar(&tmp)) return -1;
+  if (fspvec_sum(tmp, x, n, s)) return -1;
+  return host_result(out, tmp, s);
+}
+int fspvec_norm1_h(double *out, const double *x, long n, void *s) {
+  double *tmp;
+  if (tmp_scalar(&tmp)) return -1;
+  if (fspvec_norm1(tmp, x, n, s)) return -1;
+  return host_result(out, tmp, s);
+}
+
+int fspvec_scatter(double *pn, long n_new, const double *po, const int *idx, long n_old, void *s) {
+  if (fspvec_set(pn, 0.0, n_new, s)) return -1;
+  return launch_map(ScatterF{pn, po, idx}, n_old, s);
+}
+int fspvec_gather(double *o, const double *x, const int *idx, long n, void *s) {
+  return launch_map(GatherF{o, x, idx}, n, s);
+}
+
+}  // extern "C"
