@@ -14,7 +14,7 @@ CU_OBJS := $(patsubst pacmensl_b200/csrc/%.cu,$(BUILD)/%.cu.o,$(CU_SRCS))
 HOST_SRCS := $(wildcard pacmensl_b200/host/*.cpp)
 HOST_OBJS := $(patsubst pacmensl_b200/host/%.cpp,$(BUILD)/%.host.o,$(HOST_SRCS))
 
-all: $(LIB) oracle
+all: $(LIB) oracle cpptests examples
 
 $(BUILD)/%.cu.o: pacmensl_b200/csrc/%.cu pacmensl_b200/csrc/fsp_common.cuh include/fsp_b200.h
 	@mkdir -p $(BUILD)
@@ -31,6 +31,18 @@ $(LIB): $(CU_OBJS) $(HOST_OBJS)
 oracle:
 	$(MAKE) -s -C oracle
 
+# C++ host-layer test programs (shaped after the reference's gtest programs); run by tests/test_gpu_host_cpp.py
+CPP_TESTS := $(patsubst tests/cpp/%.cpp,$(BUILD)/tests/%,$(wildcard tests/cpp/test_*.cpp))
+EXAMPLES := $(patsubst examples/%.cpp,$(BUILD)/examples/%,$(wildcard examples/*.cpp))
+$(BUILD)/tests/%: tests/cpp/%.cpp tests/cpp/mini_gtest.h tests/cpp/pacmensl_test_env.h $(LIB)
+	@mkdir -p $(BUILD)/tests
+	$(CXX_HOST) -O1 -g -std=c++17 -Wall -Wno-unused-function -Iinclude -Ipacmensl_b200/host -Ipacmensl_b200/fixtures -Itests/cpp $< -o $@ -Lpacmensl_b200/lib -lpacmensl_b200 -Wl,-rpath,'$$ORIGIN/../../pacmensl_b200/lib'
+$(BUILD)/examples/%: examples/%.cpp $(LIB)
+	@mkdir -p $(BUILD)/examples
+	$(CXX_HOST) -O2 -g -std=c++17 -Wall -Wno-unused-function -Iinclude -Ipacmensl_b200/host -Ipacmensl_b200/fixtures $< -o $@ -Lpacmensl_b200/lib -lpacmensl_b200 -Wl,-rpath,'$$ORIGIN/../../pacmensl_b200/lib'
+cpptests: $(CPP_TESTS)
+examples: $(EXAMPLES)
+
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c pacmensl_b200/csrc/fspmat.cu -o /dev/null
 
@@ -38,4 +50,4 @@ clean:
 	rm -rf $(BUILD) $(LIB)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean ptxas-info
+.PHONY: all oracle clean ptxas-info cpptests examples

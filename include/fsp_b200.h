@@ -69,6 +69,17 @@ FSP_API int fspvec_axpy(double *y_dev, double alpha, const double *x_dev, long n
 /* z = a x + b y  (z may alias x or y) */
 FSP_API int fspvec_linear_sum(double *z_dev, double a, const double *x_dev, double b, const double *y_dev, long n,
                               void *stream);
+/* z = w * (a x + b y) elementwise (w == NULL: no weights).  Fuses the scaled operator application of the
+ * GMRES loop:  V_{l+1} = s1 .* (v - gamma J v)  and the unscaling x ./ s2 (via fspvec_div). */
+FSP_API int fspvec_wlincomb(double *z_dev, const double *w_dev, double a, const double *x_dev, double b,
+                            const double *y_dev, long n, void *stream);
+/* z = x ./ w */
+FSP_API int fspvec_div(double *z_dev, const double *x_dev, const double *w_dev, long n, void *stream);
+/* z = x .* w */
+FSP_API int fspvec_prod(double *z_dev, const double *x_dev, const double *w_dev, long n, void *stream);
+/* z = c0 x0 + c1 x1 + c2 x2 (three-term linear combination; x2 may be NULL) */
+FSP_API int fspvec_lincomb3(double *z_dev, double c0, const double *x0_dev, double c1, const double *x1_dev, double c2,
+                            const double *x2_dev, long n, void *stream);
 /* y = beta*y + sum_k alpha[k] X[k]  (VecMAXPY; X_dev_ptrs is a HOST array of m device pointers, m <= 64) */
 FSP_API int fspvec_maxpy(double *y_dev, double beta, int m, const double *alpha_host,
                          const double *const *X_dev_ptrs, long n, void *stream);
@@ -84,6 +95,9 @@ FSP_API int fspvec_wsqsum(double *out_dev, const double *x_dev, const double *w_
 /* w_i = 1 / (rtol*|y_i| + atol)  (CVODE error weights, cvEwtSetSS); out = min_i(rtol|y_i|+atol) */
 FSP_API int fspvec_ewt(double *w_dev, const double *y_dev, double rtol, double atol, long n, double *min_out_dev,
                        void *stream);
+/* out = max_i |x_i| / (a |y_i| + b)   (CVODE's upper bound on the first step, cvUpperBoundH0) */
+FSP_API int fspvec_ratio_absmax(double *out_dev, const double *x_dev, const double *y_dev, double a, double b, long n,
+                                void *stream);
 /* Fused modified-Gram-Schmidt step used by the Arnoldi/IOP loop (KrylovFsp.cpp:302-309):
  *   w -= (*h_dev) * v ;  out = <w, u>    (u may be NULL: then out = <w, w>)            */
 FSP_API int fspvec_axpy_dot(double *w_dev, const double *h_dev, double sign, const double *v_dev,
@@ -98,6 +112,10 @@ FSP_API int fspvec_norm1_h(double *out_host, const double *x_dev, long n, void *
 /* ExpandVec (src/PetscWrap/PetscWrap.cpp:26-56): p_new = 0; p_new[new_idx[i]] = p_old[i] */
 FSP_API int fspvec_scatter(double *p_new_dev, long n_new, const double *p_old_dev, const int *new_idx_dev,
                            long n_old, void *stream);
+/* multi-GPU ExpandVec helper: p_new[gidx[i] - own_start] = vals[i] for the entries that land in
+ * [own_start, own_start + n_new); p_new must have been zeroed by the caller (VecSetUp does). */
+FSP_API int fspvec_scatter_range(double *p_new_dev, long n_new, const double *vals_dev, const int *gidx_dev, long n,
+                                 long own_start, void *stream);
 /* out[i] = x[idx[i]]  (MakeDiscreteDistribution_ scatter, src/Fsp/FspSolverMultiSinks.cpp:703-735) */
 FSP_API int fspvec_gather(double *out_dev, const double *x_dev, const int *idx_dev, long n, void *stream);
 
@@ -211,6 +229,13 @@ FSP_API int fspmat_num_rows(fspmat_t h, int *n_rows);
 FSP_API int fspmat_action_bytes(fspmat_t h, double *bytes);
 /* kernel variant selection for tuning/benchmarks: 0 = default */
 FSP_API int fspmat_set_variant(fspmat_t h, int variant);
+/* Multi-GPU set-up (the analogue of PETSc's VecScatter creation for MATMPISELL): col_dev holds GLOBAL column
+ * indices (-1 = none).  Entries outside [own_start, own_end) are collected into a sorted unique ghost list
+ * (*ghost_gid_dev_out, device memory owned by the caller -> fsp_free) and col_dev is rewritten in place to the
+ * local encoding of fspmat_generate (>= 0 local, -1 none, <= -2 ghost slot -(col+2)). */
+FSP_API int fspmat_build_ghosts(int *col_dev, long n_entries, int own_start, int own_end, int **ghost_gid_dev_out,
+                                long *n_ghost);
+FSP_API int fspmat_shift_indices(int *idx_dev, long n, int delta);
 /* dense export for tests: out_host is n_rows x n_rows column-major (ghost columns dropped) */
 FSP_API int fspmat_dense(fspmat_t h, const double *coef_host, double *out_host);
 
@@ -229,11 +254,17 @@ FSP_API int fspcomm_rank(fspcomm_t c, int *rank, int *size);
 FSP_API int fspcomm_allreduce_sum(fspcomm_t c, double *buf_dev, long n, void *stream);
 FSP_API int fspcomm_allreduce_max(fspcomm_t c, double *buf_dev, long n, void *stream);
 FSP_API int fspcomm_reduce_sum(fspcomm_t c, double *buf_dev, long n, int root, void *stream);
+FSP_API int fspcomm_allgather_f64(fspcomm_t c, const double *send_dev, double *recv_dev, long n_per_rank, void *stream);
 FSP_API int fspcomm_allgather_int(fspcomm_t c, const int *send_dev, int *recv_dev, long n_per_rank, void *stream);
 /* halo exchange: send_counts/recv_counts are host arrays [size]; send buffer is packed per peer in rank
  * order, ghost buffer receives per peer in rank order. */
 FSP_API int fspcomm_halo_exchange(fspcomm_t c, const double *send_dev, const long *send_counts_host,
                                   double *ghost_dev, const long *recv_counts_host, void *stream);
+/* recv_host[p] = what rank p put in its send_host[me] (host arrays of length size) */
+FSP_API int fspcomm_alltoall_counts(fspcomm_t c, const long *send_host, long *recv_host, void *stream);
+/* int32 variant of the halo exchange (index lists at set-up time) */
+FSP_API int fspcomm_exchange_int(fspcomm_t c, const int *send_dev, const long *send_counts_host, int *recv_dev,
+                                 const long *recv_counts_host, void *stream);
 /* pack: out[i] = x[idx[i]] is fspvec_gather */
 
 #ifdef __cplusplus

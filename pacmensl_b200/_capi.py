@@ -58,6 +58,10 @@ SIGNATURES = {
     "fspvec_scale": (ci, [vp, cd, cl, vp]),
     "fspvec_axpy": (ci, [vp, cd, vp, cl, vp]),
     "fspvec_linear_sum": (ci, [vp, cd, vp, cd, vp, cl, vp]),
+    "fspvec_wlincomb": (ci, [vp, vp, cd, vp, cd, vp, cl, vp]),
+    "fspvec_div": (ci, [vp, vp, vp, cl, vp]),
+    "fspvec_prod": (ci, [vp, vp, vp, cl, vp]),
+    "fspvec_lincomb3": (ci, [vp, cd, vp, cd, vp, cd, vp, cl, vp]),
     "fspvec_maxpy": (ci, [vp, cd, ci, dp, vpp, cl, vp]),
     "fspvec_mdot": (ci, [vp, vp, ci, vpp, cl, vp]),
     "fspvec_dot": (ci, [vp, vp, vp, cl, vp]),
@@ -66,6 +70,7 @@ SIGNATURES = {
     "fspvec_norm1": (ci, [vp, vp, cl, vp]),
     "fspvec_wsqsum": (ci, [vp, vp, vp, cl, vp]),
     "fspvec_ewt": (ci, [vp, vp, cd, cd, cl, vp, vp]),
+    "fspvec_ratio_absmax": (ci, [vp, vp, vp, cd, cd, cl, vp]),
     "fspvec_axpy_dot": (ci, [vp, vp, cd, vp, vp, vp, cl, vp]),
     "fspvec_scale_rsqrt": (ci, [vp, vp, cl, vp]),
     "fspvec_dot_h": (ci, [dp, vp, vp, cl, vp]),
@@ -74,6 +79,7 @@ SIGNATURES = {
     "fspvec_norm1_h": (ci, [dp, vp, cl, vp]),
     "fspvec_scatter": (ci, [vp, cl, vp, vp, cl, vp]),
     "fspvec_gather": (ci, [vp, vp, vp, cl, vp]),
+    "fspvec_scatter_range": (ci, [vp, cl, vp, vp, cl, cl, vp]),
     "fspset_create": (ci, [vpp, ci, ci, ip]),
     "fspset_destroy": (ci, [vp]),
     "fspset_set_shape": (ci, [vp, ci, vp, ip, vp]),
@@ -100,6 +106,8 @@ SIGNATURES = {
     "fspmat_action_bytes": (ci, [vp, dp]),
     "fspmat_set_variant": (ci, [vp, ci]),
     "fspmat_dense": (ci, [vp, dp, dp]),
+    "fspmat_build_ghosts": (ci, [vp, cl, ci, ci, vpp, lp]),
+    "fspmat_shift_indices": (ci, [vp, cl, ci]),
     "fspcomm_unique_id": (ci, [C.c_char_p]),
     "fspcomm_create": (ci, [vpp, C.c_char_p, ci, ci]),
     "fspcomm_destroy": (ci, [vp]),
@@ -108,7 +116,10 @@ SIGNATURES = {
     "fspcomm_allreduce_max": (ci, [vp, vp, cl, vp]),
     "fspcomm_reduce_sum": (ci, [vp, vp, cl, ci, vp]),
     "fspcomm_allgather_int": (ci, [vp, vp, vp, cl, vp]),
+    "fspcomm_allgather_f64": (ci, [vp, vp, vp, cl, vp]),
     "fspcomm_halo_exchange": (ci, [vp, vp, lp, vp, lp, vp]),
+    "fspcomm_alltoall_counts": (ci, [vp, lp, lp, vp]),
+    "fspcomm_exchange_int": (ci, [vp, vp, lp, vp, lp, vp]),
 }
 
 _LIB = None

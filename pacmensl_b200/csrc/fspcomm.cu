@@ -130,6 +130,14 @@ int fspcomm_reduce_sum(fspcomm_t c, double *buf, long n, int root, void *stream)
   FSP_NCCL_CHECK(g_nccl.Reduce(buf, buf, (size_t) n, ncclFloat64, ncclSum, root, c->comm, resolve_stream(stream)));
   return 0;
 }
+int fspcomm_allgather_f64(fspcomm_t c, const double *send, double *recv, long n_per_rank, void *stream) {
+  if (!c || c->size == 1) {
+    if (send != recv) FSP_CUDA_CHECK(cudaMemcpyAsync(recv, send, sizeof(double) * n_per_rank, cudaMemcpyDeviceToDevice, resolve_stream(stream)));
+    return 0;
+  }
+  FSP_NCCL_CHECK(g_nccl.AllGather(send, recv, (size_t) n_per_rank, ncclFloat64, c->comm, resolve_stream(stream)));
+  return 0;
+}
 int fspcomm_allgather_int(fspcomm_t c, const int *send, int *recv, long n_per_rank, void *stream) {
   if (!c || c->size == 1) {
     if (send != recv) FSP_CUDA_CHECK(cudaMemcpyAsync(recv, send, sizeof(int) * n_per_rank, cudaMemcpyDeviceToDevice, resolve_stream(stream)));
@@ -152,6 +160,42 @@ int fspcomm_halo_exchange(fspcomm_t c, const double *send, const long *send_coun
     ro += recv_counts[p];
   }
   FSP_NCCL_CHECK(g_nccl.GroupEnd());
+  return 0;
+}
+
+int fspcomm_alltoall_counts(fspcomm_t c, const long *send_host, long *recv_host, void *stream) {
+  if (!c || c->size == 1) { recv_host[0] = send_host[0]; return 0; }
+  const int    P = c->size;
+  cudaStream_t st = resolve_stream(stream);
+  double      *d_send = nullptr, *d_all = nullptr;
+  FSP_CUDA_CHECK(cudaMalloc(&d_send, sizeof(double) * P));
+  FSP_CUDA_CHECK(cudaMalloc(&d_all, sizeof(double) * P * P));
+  double hs[256], hall[256 * 8];
+  if (P > 256 || P * P > 2048) { set_error("fspcomm_alltoall_counts: too many ranks"); return -1; }
+  for (int p = 0; p < P; ++p) hs[p] = (double) send_host[p];
+  FSP_CUDA_CHECK(cudaMemcpyAsync(d_send, hs, sizeof(double) * P, cudaMemcpyHostToDevice, st));
+  FSP_NCCL_CHECK(g_nccl.AllGather(d_send, d_all, (size_t) P, ncclFloat64, c->comm, st));
+  FSP_CUDA_CHECK(cudaMemcpyAsync(hall, d_all, sizeof(double) * P * P, cudaMemcpyDeviceToHost, st));
+  FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int p = 0; p < P; ++p) recv_host[p] = (long) hall[p * P + c->rank];
+  cudaFree(d_send); cudaFree(d_all);
+  return 0;
+}
+
+int fspcomm_exchange_int(fspcomm_t c, const int *send, const long *send_counts, int *recv, const long *recv_counts,
+                         void *stream) {
+  if (!c || c->size == 1) return 0;
+  cudaStream_t st = resolve_stream(stream);
+  FSP_NCCL_CHECK(g_nccl.GroupStart());
+  long so = 0, ro = 0;
+  for (int p = 0; p < c->size; ++p) {
+    if (send_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Send(send + so, (size_t) send_counts[p], ncclInt32, p, c->comm, st));
+    if (recv_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Recv(recv + ro, (size_t) recv_counts[p], ncclInt32, p, c->comm, st));
+    so += send_counts[p];
+    ro += recv_counts[p];
+  }
+  FSP_NCCL_CHECK(g_nccl.GroupEnd());
+  FSP_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;
 }
 

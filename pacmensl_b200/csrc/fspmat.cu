@@ -18,6 +18,8 @@
 //                        plane sum_{r in TI} d_r(x_i)
 // Algorithmic bytes per row = 8 (x) + 8 (y) + 12 P + 8 ND  (SURVEY.md section 8d).
 // Roofline: HBM bandwidth; arithmetic intensity ~0.15 flop/byte, so no tensor cores.
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <vector>
 
@@ -125,7 +127,7 @@ __device__ __forceinline__ double row_scalar(const MatView &m, const Coefs &cf, 
 }
 
 template <int P>
-__global__ void __launch_bounds__(kThreads) action_kernel_v2(MatView m, Coefs cf, const double *__restrict__ x,
+__global__ void __launch_bounds__(kThreads) fsp_action_rows2(MatView m, Coefs cf, const double *__restrict__ x,
                                                              const double *__restrict__ ghost,
                                                              double *__restrict__ y, double *__restrict__ sink_out) {
   if ((int) blockIdx.x >= m.main_blocks) {
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kThreads) action_kernel_v2(MatView m, Coefs cf
 
 // 4 rows per thread: int4 column loads, 2 x double2 value loads per plane
 template <int P>
-__global__ void __launch_bounds__(kThreads) action_kernel_v4(MatView m, Coefs cf, const double *__restrict__ x,
+__global__ void __launch_bounds__(kThreads) fsp_action_rows4(MatView m, Coefs cf, const double *__restrict__ x,
                                                              const double *__restrict__ ghost,
                                                              double *__restrict__ y, double *__restrict__ sink_out) {
   if ((int) blockIdx.x >= m.main_blocks) {
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(kThreads) action_kernel_v4(MatView m, Coefs cf
 
 // 1 row per thread (also the path for unaligned x / y)
 template <int P>
-__global__ void __launch_bounds__(kThreads) action_kernel_v1(MatView m, Coefs cf, const double *__restrict__ x,
+__global__ void __launch_bounds__(kThreads) fsp_action_rows1(MatView m, Coefs cf, const double *__restrict__ x,
                                                              const double *__restrict__ ghost,
                                                              double *__restrict__ y, double *__restrict__ sink_out) {
   if ((int) blockIdx.x >= m.main_blocks) {
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(kThreads) action_kernel_v1(MatView m, Coefs cf
 }
 
 // generic number of planes (P > 16): runtime loop
-__global__ void __launch_bounds__(kThreads) action_kernel_generic(MatView m, Coefs cf, const double *__restrict__ x,
+__global__ void __launch_bounds__(kThreads) fsp_action_generic(MatView m, Coefs cf, const double *__restrict__ x,
                                                                   const double *__restrict__ ghost,
                                                                   double *__restrict__ y,
                                                                   double *__restrict__ sink_out) {
@@ -247,9 +249,9 @@ typedef void (*action_fn)(MatView, Coefs, const double *, const double *, double
 template <int P>
 action_fn pick_variant(int rows_per_thread) {
   switch (rows_per_thread) {
-    case 1: return action_kernel_v1<P>;
-    case 4: return action_kernel_v4<P>;
-    default: return action_kernel_v2<P>;
+    case 1: return fsp_action_rows1<P>;
+    case 4: return fsp_action_rows4<P>;
+    default: return fsp_action_rows2<P>;
   }
 }
 
@@ -321,6 +323,29 @@ __global__ void count_nnz_kernel(int n, int n_tv, int n_ti, long ld, const int *
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[g], v);
   }
+}
+
+
+struct OutOfRange {
+  int lo, hi;
+  __host__ __device__ bool operator()(const int &c) const { return c >= 0 && (c < lo || c >= hi); }
+};
+__global__ void remap_cols_kernel(int *col, long n, int lo, int hi, const int *ghost, long n_ghost) {
+  long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int c = col[q];
+  if (c < 0) return;
+  if (c >= lo && c < hi) { col[q] = c - lo; return; }
+  long a = 0, b = n_ghost;  // lower_bound in the sorted ghost list
+  while (a < b) {
+    long mid = (a + b) >> 1;
+    if (ghost[mid] < c) a = mid + 1; else b = mid;
+  }
+  col[q] = -((int) a + 2);
+}
+__global__ void shift_idx_kernel(int *idx, long n, int delta) {
+  long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) idx[q] += delta;
 }
 
 }  // namespace
@@ -537,17 +562,64 @@ int fspmat_action(fspmat_t h, const double *coef_host, const double *x, const do
   m.sink_partials = h->d_sink_partials; m.sink_counter = h->d_sink_counter;
   m.owns_sinks = h->owns_sinks;
 
-  int rows_per_thread = h->variant == 1 ? 1 : (h->variant == 4 ? 4 : 2);
-  if (h->variant == 0) rows_per_thread = 2;
+  // variant 0 = default = 1 row per thread: 32 registers -> full occupancy, measured fastest on B200
+  // (465^3 lattice: 7.0 TB/s vs 6.7 TB/s for 2 rows and 5.8 TB/s for 4 rows per thread, profiles/)
+  int rows_per_thread = h->variant == 2 ? 2 : (h->variant == 4 ? 4 : 1);
   // vector paths need 16-byte aligned x and y
   if (((uintptr_t) x & 15u) || ((uintptr_t) y & 15u)) rows_per_thread = 1;
   action_fn fn = pick_kernel(h->P, rows_per_thread);
-  if (!fn) { fn = action_kernel_generic; rows_per_thread = 1; }
+  if (!fn) { fn = fsp_action_generic; rows_per_thread = 1; }
   long per_block = (long) kThreads * rows_per_thread;
   m.main_blocks = (int) ((h->n + per_block - 1) / per_block);
   int grid = m.main_blocks + m.sink_blocks;
   if (grid == 0) return 0;
   fn<<<grid, kThreads, 0, st>>>(m, cf, x, ghost, y, sink_out);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fspmat_build_ghosts(int *col, long n, int lo, int hi, int **ghost_out, long *n_ghost) {
+  *ghost_out = nullptr;
+  *n_ghost = 0;
+  if (n <= 0) return 0;
+  int *d_sel = nullptr, *d_sorted = nullptr, *d_uniq = nullptr, *d_num = nullptr;
+  void *d_tmp = nullptr;
+  size_t need = 0, cap = 0;
+  FSP_CUDA_CHECK(cudaMalloc(&d_num, sizeof(int)));
+  FSP_CUDA_CHECK(cudaMalloc(&d_sel, sizeof(int) * n));
+  OutOfRange pred{lo, hi};
+  cub::DeviceSelect::If(nullptr, need, col, d_sel, d_num, (int) n, pred);
+  FSP_CUDA_CHECK(cudaMalloc(&d_tmp, need)); cap = need;
+  FSP_CUDA_CHECK(cub::DeviceSelect::If(d_tmp, need, col, d_sel, d_num, (int) n, pred));
+  count_launch();
+  int n_sel = 0;
+  FSP_CUDA_CHECK(cudaMemcpy(&n_sel, d_num, sizeof(int), cudaMemcpyDeviceToHost));
+  int n_u = 0;
+  if (n_sel > 0) {
+    FSP_CUDA_CHECK(cudaMalloc(&d_sorted, sizeof(int) * n_sel));
+    FSP_CUDA_CHECK(cudaMalloc(&d_uniq, sizeof(int) * n_sel));
+    cub::DeviceRadixSort::SortKeys(nullptr, need, d_sel, d_sorted, n_sel);
+    if (need > cap) { cudaFree(d_tmp); FSP_CUDA_CHECK(cudaMalloc(&d_tmp, need)); cap = need; }
+    FSP_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(d_tmp, need, d_sel, d_sorted, n_sel));
+    count_launch();
+    cub::DeviceSelect::Unique(nullptr, need, d_sorted, d_uniq, d_num, n_sel);
+    if (need > cap) { cudaFree(d_tmp); FSP_CUDA_CHECK(cudaMalloc(&d_tmp, need)); cap = need; }
+    FSP_CUDA_CHECK(cub::DeviceSelect::Unique(d_tmp, need, d_sorted, d_uniq, d_num, n_sel));
+    count_launch();
+    FSP_CUDA_CHECK(cudaMemcpy(&n_u, d_num, sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  remap_cols_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(col, n, lo, hi, d_uniq, n_u);
+  FSP_LAUNCH_CHECK();
+  FSP_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaFree(d_sel); cudaFree(d_sorted); cudaFree(d_tmp); cudaFree(d_num);
+  *ghost_out = d_uniq;
+  *n_ghost = n_u;
+  return 0;
+}
+
+int fspmat_shift_indices(int *idx, long n, int delta) {
+  if (n <= 0) return 0;
+  shift_idx_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(idx, n, delta);
   FSP_LAUNCH_CHECK();
   return 0;
 }

@@ -114,6 +114,29 @@ struct LinSumF {
   double *z; double a; const double *x; double b; const double *y;
   __device__ void operator()(long i) const { z[i] = a * x[i] + b * y[i]; }
 };
+struct WLinCombF {
+  double *z; const double *w; double a; const double *x; double b; const double *y;
+  __device__ void operator()(long i) const {
+    double v = a * x[i] + b * y[i];
+    z[i] = w ? w[i] * v : v;
+  }
+};
+struct DivF {
+  double *z; const double *x; const double *w;
+  __device__ void operator()(long i) const { z[i] = x[i] / w[i]; }
+};
+struct ProdF {
+  double *z; const double *x; const double *w;
+  __device__ void operator()(long i) const { z[i] = x[i] * w[i]; }
+};
+struct LinComb3F {
+  double *z; double c0; const double *x0; double c1; const double *x1; double c2; const double *x2;
+  __device__ void operator()(long i) const {
+    double v = c0 * x0[i] + c1 * x1[i];
+    if (x2) v += c2 * x2[i];
+    z[i] = v;
+  }
+};
 struct ScaleRsqrtF {
   double *w; const double *nsq;
   __device__ void operator()(long i) const { w[i] *= 1.0 / sqrt(*nsq); }
@@ -121,6 +144,13 @@ struct ScaleRsqrtF {
 struct ScatterF {
   double *pn; const double *po; const int *idx;
   __device__ void operator()(long i) const { int j = idx[i]; if (j >= 0) pn[j] = po[i]; }
+};
+struct ScatterRangeF {
+  double *pn; long n_new; const double *v; const int *g; long start;
+  __device__ void operator()(long i) const {
+    long j = (long) g[i] - start;
+    if (g[i] >= 0 && j >= 0 && j < n_new) pn[j] = v[i];
+  }
 };
 struct GatherF {
   double *o; const double *x; const int *idx;
@@ -260,6 +290,11 @@ struct EwtF {
     acc[0] = fmin(acc[0], t);
   }
 };
+struct RatioAbsMaxF {  // accumulates min of the NEGATED ratio so that the RED_MIN machinery yields the max
+  const double *x, *y; double a, b;
+  __device__ void operator()(long i, double (&acc)[1]) const { acc[0] = fmin(acc[0], -fabs(x[i]) / (a * fabs(y[i]) + b)); }
+};
+__global__ void negate_scalar_kernel(double *v) { *v = (*v > 1.0e299) ? 0.0 : -*v; }
 struct AxpyDotF {
   double *w; const double *h; double sign; const double *v; const double *u;
   __device__ void operator()(long i, double (&acc)[1]) const {
@@ -335,6 +370,16 @@ int fspvec_linear_sum(double *z, double a, const double *x, double b, const doub
   return launch_map(LinSumF{z, a, x, b, y}, n, s);
 }
 
+int fspvec_wlincomb(double *z, const double *w, double a, const double *x, double b, const double *y, long n, void *s) {
+  return launch_map(WLinCombF{z, w, a, x, b, y}, n, s);
+}
+int fspvec_div(double *z, const double *x, const double *w, long n, void *s) { return launch_map(DivF{z, x, w}, n, s); }
+int fspvec_prod(double *z, const double *x, const double *w, long n, void *s) { return launch_map(ProdF{z, x, w}, n, s); }
+int fspvec_lincomb3(double *z, double c0, const double *x0, double c1, const double *x1, double c2, const double *x2,
+                    long n, void *s) {
+  return launch_map(LinComb3F{z, c0, x0, c1, x1, c2, x2}, n, s);
+}
+
 int fspvec_maxpy(double *y, double beta, int m, const double *alpha, const double *const *X, long n, void *s) {
   if (m < 0 || m > kMaxpy) { set_error("fspvec_maxpy: m=%d out of range (max %d)", m, kMaxpy); return -1; }
   if (n <= 0) return 0;
@@ -377,6 +422,12 @@ int fspvec_ewt(double *w, const double *y, double rtol, double atol, long n, dou
   if (!tmp && tmp_scalar(&tmp)) return -1;
   return launch_reduce<1, RED_MIN>(EwtF{w, y, rtol, atol}, n, tmp, s);
 }
+int fspvec_ratio_absmax(double *out, const double *x, const double *y, double a, double b, long n, void *s) {
+  if (launch_reduce<1, RED_MIN>(RatioAbsMaxF{x, y, a, b}, n, out, s)) return -1;
+  negate_scalar_kernel<<<1, 1, 0, resolve_stream(s)>>>(out);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
 int fspvec_axpy_dot(double *w, const double *h, double sign, const double *v, const double *u, double *out, long n,
                     void *s) {
   return launch_reduce<1, RED_SUM>(AxpyDotF{w, h, sign, v, u}, n, out, s);
@@ -413,6 +464,9 @@ int fspvec_norm1_h(double *out, const double *x, long n, void *s) {
 int fspvec_scatter(double *pn, long n_new, const double *po, const int *idx, long n_old, void *s) {
   if (fspvec_set(pn, 0.0, n_new, s)) return -1;
   return launch_map(ScatterF{pn, po, idx}, n_old, s);
+}
+int fspvec_scatter_range(double *pn, long n_new, const double *v, const int *g, long n, long start, void *s) {
+  return launch_map(ScatterRangeF{pn, n_new, v, g, start}, n, s);
 }
 int fspvec_gather(double *o, const double *x, const int *idx, long n, void *s) {
   return launch_map(GatherF{o, x, idx}, n, s);

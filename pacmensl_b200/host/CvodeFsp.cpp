@@ -1,0 +1,92 @@
+#include "CvodeFsp.h"
+
+namespace pacmensl {
+
+CvodeFsp::CvodeFsp(MPI_Comm _comm, int lmm) : OdeSolverBase(_comm) { lmm_ = lmm; }
+
+// src/OdeSolver/CvodeFsp.cpp:137-200
+PacmenslErrorCode CvodeFsp::SetUp() {
+  if (solution_ == nullptr) return -1;
+  if (rhs_ == nullptr) return -1;
+  if (lmm_ != CV_BDF) {
+    PetscPrintf(comm_, "CvodeFsp: only the BDF method (CV_BDF) is provided.\n");
+    return -1;
+  }
+  if (solution_work_) VecDestroy(&solution_work_);
+  PetscInt petsc_err = VecDuplicate(*solution_, &solution_work_);
+  CHKERRQ(petsc_err);
+  petsc_err = VecCopy(*solution_, solution_work_);
+  CHKERRQ(petsc_err);
+  t_now_tmp = t_now_;
+
+  core_.reset(new BdfCore(comm_));
+  core_->SetTolerances(rel_tol_, abs_tol_);
+  core_->SetMaxConvFails(10000);     // CVodeSetMaxConvFails(cvode_mem, 10000)
+  core_->SetMaxNonlinIters(10000);   // CVodeSetMaxNonlinIters(cvode_mem, 10000)
+  core_->SetMaxKrylov(100);          // SUNLinSol_SPGMR(y, PREC_NONE, 100)
+  auto f = [this](double t, Vec y, Vec ydot) { return EvaluateRHS(t, y, ydot); };  // J v == A(t) v (linear ODE)
+  cvode_stat = core_->Init(t_now_tmp, solution_work_, f, f, t_final_);
+  if (cvode_stat < 0) {
+    printf("\nBDF integrator error: initialisation failed with flag = %d\n\n", cvode_stat);
+    return -1;
+  }
+  return 0;
+}
+
+// src/OdeSolver/CvodeFsp.cpp:34-78
+PetscInt CvodeFsp::Solve() {
+  if (solution_ == nullptr || rhs_ == nullptr || !core_) return -1;
+  PacmenslErrorCode ierr;
+  PetscErrorCode    petsc_err;
+  int               stop = 0;
+  PetscReal         error_excess = 0.0;
+  while (t_now_ < t_final_) {
+    cvode_stat = core_->Step(&t_now_tmp, solution_work_);
+    if (cvode_stat < 0) {
+      int rank;
+      MPI_Comm_rank(MPI_COMM_WORLD, &rank);
+      printf("\nBDF integrator error: step failed on rank %d with flag = %d\n\n", rank, cvode_stat);
+      return -1;
+    }
+    // Interpolate the solution if the last step went over the prescribed final time
+    if (t_now_tmp > t_final_) {
+      cvode_stat = core_->GetDky(t_final_, solution_work_);
+      if (cvode_stat < 0) return -1;
+      t_now_tmp = t_final_;
+    }
+    if (stop_check_ != nullptr) {
+      ierr = stop_check_(t_now_tmp, solution_work_, error_excess, stop_data_);
+      PACMENSLCHKERRQ(ierr);
+      if (error_excess > 0.0) {
+        stop = 1;
+        cvode_stat = core_->GetDky(t_now_, solution_work_);  // roll back to the last accepted time
+        if (cvode_stat < 0) return -1;
+        break;
+      }
+    }
+    t_now_ = t_now_tmp;
+    if (print_intermediate) PetscPrintf(comm_, "t_now_ = %.2e \n", t_now_);
+    if (logging_enabled && (size_t) perf_info.n_step < perf_info.model_time.size()) {
+      perf_info.model_time[perf_info.n_step] = t_now_;
+      petsc_err = VecGetSize(*solution_, &perf_info.n_eqs[size_t(perf_info.n_step)]);
+      CHKERRQ(petsc_err);
+      petsc_err = PetscTime(&perf_info.cpu_time[perf_info.n_step]);
+      CHKERRQ(petsc_err);
+      perf_info.n_step += 1;
+    }
+  }
+  petsc_err = VecCopy(solution_work_, *solution_);
+  CHKERRQ(petsc_err);
+  return stop;
+}
+
+int CvodeFsp::FreeWorkspace() {
+  OdeSolverBase::FreeWorkspace();
+  core_.reset();
+  if (solution_work_ != nullptr) VecDestroy(&solution_work_);
+  return 0;
+}
+
+CvodeFsp::~CvodeFsp() { FreeWorkspace(); }
+
+}  // namespace pacmensl

@@ -1,0 +1,33 @@
+// DiscreteDistribution.h -- result container: states + probabilities without the sinks
+// (mirrors src/Fsp/DiscreteDistribution.h:38-107).
+#pragma once
+
+#include "StateSetBase.h"
+#include "Sys.h"
+
+namespace pacmensl {
+
+struct PACMENSL_API DiscreteDistribution {
+  MPI_Comm       comm_ = MPI_COMM_NULL;
+  double         t_ = 0.0;
+  arma::Mat<int> states_;
+  Vec            p_ = nullptr;
+
+  DiscreteDistribution();
+  DiscreteDistribution(MPI_Comm comm, double t, const StateSetBase *state_set, const Vec &p);
+  DiscreteDistribution(const DiscreteDistribution &dist);
+  DiscreteDistribution(DiscreteDistribution &&dist) noexcept;
+  DiscreteDistribution &operator=(const DiscreteDistribution &);
+  DiscreteDistribution &operator=(DiscreteDistribution &&) noexcept;
+
+  PacmenslErrorCode GetStateView(int &num_states, int &num_species, int *&states);
+  PacmenslErrorCode GetProbView(int &num_states, double *&p);
+  PacmenslErrorCode RestoreProbView(double *&p);
+  PacmenslErrorCode WeightedAverage(int nout, PetscReal *fout,
+                                    std::function<PacmenslErrorCode(int num_species, int *x, int nout, PetscReal *wx, void *args)> weight_func,
+                                    void *wf_args);
+  ~DiscreteDistribution();
+};
+
+PACMENSL_API arma::Col<PetscReal> Compute1DMarginal(const DiscreteDistribution &dist, int species);
+}  // namespace pacmensl

@@ -1,0 +1,333 @@
+#include "FspMatrixBase.h"
+
+#include <algorithm>
+
+PetscErrorCode MatMult(Mat A, Vec x, Vec y) {
+  // dense host product for the small test matrices produced by ComputeRHSJacobian
+  const PetscScalar *xa;
+  PetscScalar       *ya;
+  PetscErrorCode     ierr = VecGetArrayRead(x, &xa);
+  if (ierr) return ierr;
+  std::vector<double> xs(xa, xa + x->n_local);
+  VecRestoreArrayRead(x, &xa);
+  ierr = VecGetArray(y, &ya);
+  if (ierr) return ierr;
+  const arma::Mat<double> &J = A->dense;
+  for (arma::uword i = 0; i < J.n_rows; ++i) ya[i] = 0.0;
+  for (arma::uword j = 0; j < J.n_cols; ++j)
+    for (arma::uword i = 0; i < J.n_rows; ++i) ya[i] += J(i, j) * xs[j];
+  return VecRestoreArray(y, &ya);
+}
+PetscErrorCode MatDestroy(Mat *A) {
+  if (A && *A) delete *A;
+  if (A) *A = nullptr;
+  return 0;
+}
+
+namespace pacmensl {
+
+FspMatrixBase::FspMatrixBase(MPI_Comm comm) {
+  comm_ = comm;
+  MPI_Comm_rank(comm_, &rank_);
+  MPI_Comm_size(comm_, &comm_size_);
+}
+
+FspMatrixBase::~FspMatrixBase() {
+  Destroy();
+  if (dmat_) fspmat_destroy(dmat_);
+  dmat_ = nullptr;
+  comm_ = MPI_COMM_NULL;
+}
+
+// src/Matrix/FspMatrixBase.cpp:258-275
+int FspMatrixBase::Destroy() {
+  enable_reactions_.clear();
+  tv_reactions_.clear();
+  ti_reactions_.clear();
+  if (dmat_) fspmat_clear(dmat_);
+  ghost_buf_.release();
+  send_buf_.release();
+  send_idx_.release();
+  send_counts_.clear();
+  recv_counts_.clear();
+  n_ghost_ = n_send_ = 0;
+  has_values_ = PETSC_FALSE;
+  return 0;
+}
+
+// src/Matrix/FspMatrixBase.cpp:277-300
+int FspMatrixBase::DetermineLayout_(const StateSetBase &fsp) {
+  num_states_local_ = fsp.GetNumLocalStates();
+  num_rows_local_ = num_states_local_;
+  num_rows_global_ = fsp.GetNumGlobalStates();
+  own_start_ = fsp.GetLocalStart();
+  owns_sinks_ = false;
+  num_constraints_ = 0;
+  return 0;
+}
+
+int FspMatrixBase::CollectSinks_(const StateSetBase &, const arma::Mat<Int> &, const std::vector<int> &, const double *,
+                                 long, std::vector<long> &sink_ptr, DeviceBuffer<int> &, DeviceBuffer<double> &) {
+  sink_ptr.clear();
+  return 0;
+}
+
+PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const Model &model) {
+  mass_action_ = model.mass_action_;
+  PacmenslErrorCode ierr = GenerateValues(fsp, model.stoichiometry_matrix_, model.tv_reactions_, model.prop_t_,
+                                          model.prop_x_, std::vector<int>(), model.prop_t_args_, model.prop_x_args_);
+  mass_action_.reset();
+  return ierr;
+}
+
+// src/Matrix/FspMatrixBase.cpp:76-251.  For every enabled reaction r and local state x_i:
+//   col = State2Index(x_i - nu_r) (device hash), off = prop_x(r, x_i - nu_r), diag = prop_x(r, x_i).
+PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const arma::Mat<Int> &SM,
+                                                std::vector<int> time_varying, const TcoefFun &new_prop_t,
+                                                const PropFun &new_prop_x, const std::vector<int> &enable_reactions,
+                                                void *prop_t_args, void *prop_x_args) {
+  PacmenslErrorCode ierr;
+  Destroy();
+  ierr = DetermineLayout_(fsp);
+  PACMENSLCHKERRQ(ierr);
+
+  const int n_species = fsp.GetNumSpecies();
+  const long n = fsp.GetNumLocalStates();
+  num_reactions_ = fsp.GetNumReactions();
+  time_coefficients_.set_size(num_reactions_);
+  time_coefficients_.fill(1.0);
+
+  t_fun_ = new_prop_t;
+  t_fun_args_ = prop_t_args;
+
+  enable_reactions_ = enable_reactions;
+  if (enable_reactions_.empty()) {
+    enable_reactions_.resize(num_reactions_);
+    for (int i = 0; i < num_reactions_; ++i) enable_reactions_[i] = i;
+  }
+  for (int ir : enable_reactions_) {
+    if (std::find(time_varying.begin(), time_varying.end(), ir) != time_varying.end()) tv_reactions_.push_back(ir);
+    else ti_reactions_.push_back(ir);
+  }
+  if (!tv_reactions_.empty() && !t_fun_) {
+    printf("FspMatrixBase::GenerateValues: time-varying reactions given without a time-coefficient function.\n");
+    PACMENSLCHKERRQ(-1);
+  }
+  if (!new_prop_x && !mass_action_) PACMENSLCHKERRQ(-1);
+
+  std::vector<int> planes(tv_reactions_);
+  planes.insert(planes.end(), ti_reactions_.begin(), ti_reactions_.end());
+  const int  P = (int) planes.size();
+  const long ld = n > 0 ? n : 1;
+
+  fspset_t dset = fsp.GetDeviceSet();
+  if (!dset && n > 0) PACMENSLCHKERRQ(-1);
+
+  DeviceBuffer<int>    col((size_t) P * ld);
+  DeviceBuffer<double> off((size_t) P * ld), diag((size_t) P * ld);
+  if (!col.get() || !off.get() || !diag.get()) PACMENSLCHKERRQ(-1);
+
+  std::vector<int>    shifted;
+  std::vector<double> vals;
+  const bool          on_device = (bool) mass_action_;
+  const arma::Mat<int> *states = nullptr;
+  if (!on_device && n > 0) {
+    states = &fsp.GetStatesRef();
+    shifted.resize((size_t) n * n_species);
+    vals.resize((size_t) n);
+  }
+  std::vector<int> zero_nu(n_species, 0);
+  for (int p = 0; p < P && n > 0; ++p) {
+    const int  r = planes[p];
+    const int *nu = SM.colptr(r);
+    // column indices: State2Index(x - nu) for all local states, in one batched device lookup (:133-134)
+    FSPCHKERRQ(fspset_lookup_shifted(dset, nu, -1, fsp.GetLocalStart(), n, col.get() + (size_t) p * ld));
+    if (on_device) {
+      std::vector<int> ord(n_species);
+      for (int s = 0; s < n_species; ++s) ord[s] = mass_action_->order(s, r);
+      FSPCHKERRQ(fspset_eval_mass_action(dset, mass_action_->rate[r], ord.data(), nu, -1, fsp.GetLocalStart(), n,
+                                         off.get() + (size_t) p * ld));
+      FSPCHKERRQ(fspset_eval_mass_action(dset, mass_action_->rate[r], ord.data(), zero_nu.data(), 0,
+                                         fsp.GetLocalStart(), n, diag.get() + (size_t) p * ld));
+    } else {
+      // host callbacks (API contract): prop_x on x - nu (:135-136) and on x (:180, :232)
+      const int *X = states->memptr();
+      for (long i = 0; i < n; ++i)
+        for (int s = 0; s < n_species; ++s) shifted[(size_t) i * n_species + s] = X[(size_t) i * n_species + s] - nu[s];
+      ierr = new_prop_x(r, n_species, (int) n, shifted.data(), vals.data(), prop_x_args);
+      PACMENSLCHKERRQ(ierr);
+      FSPCHKERRQ(fsp_memcpy_h2d(off.get() + (size_t) p * ld, vals.data(), sizeof(double) * n, nullptr));
+      ierr = new_prop_x(r, n_species, (int) n, X, vals.data(), prop_x_args);
+      PACMENSLCHKERRQ(ierr);
+      FSPCHKERRQ(fsp_memcpy_h2d(diag.get() + (size_t) p * ld, vals.data(), sizeof(double) * n, nullptr));
+    }
+  }
+
+  // sink rows (constrained subclass)
+  std::vector<long>    sink_ptr;
+  DeviceBuffer<int>    sink_idx;
+  DeviceBuffer<double> sink_val;
+  ierr = CollectSinks_(fsp, SM, planes, diag.get(), ld, sink_ptr, sink_idx, sink_val);
+  PACMENSLCHKERRQ(ierr);
+
+  // multi-GPU: columns outside the own block become ghost slots
+  if (comm_size_ > 1) {
+    ierr = SetupGhosts_(fsp, col.get(), (long) P * ld);
+    PACMENSLCHKERRQ(ierr);
+  }
+
+  fspmat_desc d;
+  std::memset(&d, 0, sizeof(d));
+  d.n_states = (int) n;
+  d.n_rows = num_rows_local_;
+  d.n_reactions = num_reactions_;
+  d.n_tv = (int) tv_reactions_.size();
+  d.n_ti = (int) ti_reactions_.size();
+  d.tv_reactions = tv_reactions_.data();
+  d.ti_reactions = ti_reactions_.data();
+  d.col = col.get();
+  d.off = off.get();
+  d.diag = diag.get();
+  d.ld = ld;
+  d.arrays_on_device = 1;
+  d.n_constr = num_constraints_;
+  d.sink_ptr = sink_ptr.empty() ? nullptr : sink_ptr.data();
+  d.sink_idx = sink_idx.get();
+  d.sink_val = sink_val.get();
+  d.owns_sinks = owns_sinks_ ? 1 : 0;
+  d.n_ghost = n_ghost_;
+  std::vector<long> empty_ptr;
+  if (num_constraints_ > 0 && sink_ptr.empty()) {
+    empty_ptr.assign((size_t) P * num_constraints_ + 1, 0);
+    d.sink_ptr = empty_ptr.data();
+  }
+  if (!dmat_) FSPCHKERRQ(fspmat_create(&dmat_));
+  FSPCHKERRQ(fspmat_set_variant(dmat_, kernel_variant_));
+  FSPCHKERRQ(fspmat_generate(dmat_, &d));
+  if (num_constraints_ > 0 && comm_size_ > 1) {
+    if (sink_buf_.resize((size_t) num_constraints_)) PACMENSLCHKERRQ(-1);
+  }
+  has_values_ = PETSC_TRUE;
+  return 0;
+}
+
+PacmenslErrorCode FspMatrixBase::SetTimeFun(TcoefFun new_t_fun, void *new_t_fun_args) {
+  t_fun_ = new_t_fun;
+  t_fun_args_ = new_t_fun_args;
+  return 0;
+}
+
+// src/Matrix/FspMatrixBase.cpp:36-62 (+ FspMatrixConstrained.cpp:31-64 when sinks are present)
+PacmenslErrorCode FspMatrixBase::Action(PetscReal t, Vec x, Vec y) {
+  if (has_values_ == PETSC_FALSE) return VecSet(y, 0.0);
+  if (!tv_reactions_.empty()) {
+    int ierr = t_fun_(t, num_reactions_, time_coefficients_.memptr(), t_fun_args_);
+    if (ierr != 0) VecSet(y, 0.0);
+    PACMENSLCHKERRQ(ierr);
+  }
+  return ActionWithCoefficients(time_coefficients_.memptr(), x, y);
+}
+
+PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec x, Vec y) {
+  if (has_values_ == PETSC_FALSE) return VecSet(y, 0.0);
+  if (x->n_local != num_rows_local_ || y->n_local != num_rows_local_) {
+    printf("FspMatrixBase::Action: vector sizes (%d, %d) do not match the operator (%d local rows).\n", x->n_local,
+           y->n_local, num_rows_local_);
+    PACMENSLCHKERRQ(-1);
+  }
+  void *stream = comm_ ? comm_->stream : nullptr;
+  if (comm_size_ > 1 && (n_send_ > 0 || n_ghost_ > 0)) {
+    // halo exchange of the ghost entries of x (replaces the VecScatter inside MatMult on MATMPISELL)
+    if (n_send_ > 0) FSPCHKERRQ(fspvec_gather(send_buf_.get(), x->d_data, send_idx_.get(), n_send_, stream));
+    FSPCHKERRQ(fspcomm_halo_exchange(comm_->nccl, send_buf_.get(), send_counts_.data(), ghost_buf_.get(),
+                                     recv_counts_.data(), stream));
+  }
+  double *sink_out = (comm_size_ > 1 && num_constraints_ > 0) ? sink_buf_.get() : nullptr;
+  FSPCHKERRQ(fspmat_action(dmat_, coefs, x->d_data, ghost_buf_.get(), y->d_data, sink_out, stream));
+  if (sink_out) {
+    // K partial sink sums -> owner of the sink rows (FspMatrixConstrained.cpp:57-60)
+    FSPCHKERRQ(fspcomm_allreduce_sum(comm_->nccl, sink_out, num_constraints_, stream));
+    if (owns_sinks_)
+      FSPCHKERRQ(fsp_memcpy_d2d(y->d_data + num_states_local_, sink_out, sizeof(double) * num_constraints_, stream));
+  }
+  return 0;
+}
+
+// src/Matrix/FspMatrixBase.cpp:308-427 -- dense host stand-in (tests only)
+PacmenslErrorCode FspMatrixBase::CreateRHSJacobian(Mat *A) {
+  if (comm_size_ > 1 || num_rows_local_ > 20000) {
+    printf("CreateRHSJacobian: the assembled Jacobian is only provided for small single-rank problems.\n");
+    return -1;
+  }
+  *A = new _p_Mat();
+  (*A)->comm = comm_;
+  (*A)->dense.zeros(num_rows_local_, num_rows_local_);
+  return 0;
+}
+PacmenslErrorCode FspMatrixBase::ComputeRHSJacobian(PetscReal t, Mat A) {
+  if (!A) return -1;
+  if (!tv_reactions_.empty()) {
+    int ierr = t_fun_(t, num_reactions_, time_coefficients_.memptr(), t_fun_args_);
+    PACMENSLCHKERRQ(ierr);
+  }
+  A->dense.zeros(num_rows_local_, num_rows_local_);
+  if (has_values_ == PETSC_FALSE) return 0;
+  FSPCHKERRQ(fspmat_dense(dmat_, time_coefficients_.memptr(), A->dense.memptr()));
+  return 0;
+}
+
+// src/Matrix/FspMatrixBase.cpp:429-444
+PacmenslErrorCode FspMatrixBase::GetLocalMVFlops(PetscInt *nflops) {
+  long f = 0;
+  if (dmat_) FSPCHKERRQ(fspmat_flops(dmat_, &f));
+  *nflops = (PetscInt) f;
+  return 0;
+}
+
+double FspMatrixBase::GetActionBytes() const {
+  double b = 0.0;
+  if (dmat_) fspmat_action_bytes(dmat_, &b);
+  return b;
+}
+
+void FspMatrixBase::SetKernelVariant(int v) {
+  kernel_variant_ = v;
+  if (dmat_) fspmat_set_variant(dmat_, v);
+}
+
+int FspMatrixBase::SetupGhosts_(const StateSetBase &fsp, int *col_planes_dev, long n_entries) {
+  // Build the per-peer ghost lists from the column entries outside the own block (what PETSc's
+  // VecScatter set-up does for MATMPISELL) and rewrite col to the local/ghost encoding.
+  const std::vector<int> &layout = fsp.GetLayout();
+  const int own_start = layout[rank_], own_end = layout[rank_ + 1];
+  int *ghost_gid_dev = nullptr;
+  long n_ghost = 0;
+  FSPCHKERRQ(fspmat_build_ghosts(col_planes_dev, n_entries, own_start, own_end, &ghost_gid_dev, &n_ghost));
+  n_ghost_ = n_ghost;
+  std::vector<int> gids((size_t) n_ghost);
+  if (n_ghost > 0) FSPCHKERRQ(fsp_memcpy_d2h(gids.data(), ghost_gid_dev, sizeof(int) * n_ghost, nullptr));
+  fsp_free(ghost_gid_dev);
+  // ghost ids are sorted ascending => contiguous per owning peer
+  recv_counts_.assign(comm_size_, 0);
+  for (int g : gids) {
+    int owner = (int) (std::upper_bound(layout.begin(), layout.end(), g) - layout.begin()) - 1;
+    recv_counts_[owner] += 1;
+  }
+  // tell every peer which of its entries we need: exchange counts, then the index lists
+  send_counts_.assign(comm_size_, 0);
+  FSPCHKERRQ(fspcomm_alltoall_counts(comm_->nccl, recv_counts_.data(), send_counts_.data(), comm_->stream));
+  n_send_ = 0;
+  for (int p = 0; p < comm_size_; ++p) n_send_ += send_counts_[p];
+  DeviceBuffer<int> want;
+  if (want.upload(gids.data(), gids.size())) return -1;
+  if (send_idx_.resize((size_t) (n_send_ > 0 ? n_send_ : 1))) return -1;
+  // we SEND our wanted global ids to their owners and RECEIVE the ids they want from us
+  FSPCHKERRQ(fspcomm_exchange_int(comm_->nccl, want.get(), recv_counts_.data(), send_idx_.get(), send_counts_.data(),
+                                  comm_->stream));
+  FSPCHKERRQ(fspmat_shift_indices(send_idx_.get(), n_send_, -own_start));  // global -> local
+  if (ghost_buf_.resize((size_t) (n_ghost > 0 ? n_ghost : 1))) return -1;
+  if (send_buf_.resize((size_t) (n_send_ > 0 ? n_send_ : 1))) return -1;
+  return 0;
+}
+
+}  // namespace pacmensl

@@ -1,0 +1,100 @@
+// FspMatrixBase.h -- the time-dependent FSP-truncated CME operator A(t) = sum_r c_r(t) A_r.
+// Mirrors the public surface of src/Matrix/FspMatrixBase.h:53-194.  Storage and Action are the fused
+// device operator of include/fsp_b200.h (fspmat_*): one kernel launch per Action instead of
+// (R_tv + 1) x [MatMult + VecAXPY].
+#pragma once
+
+#include "Model.h"
+#include "StateSetBase.h"
+#include "StateSetConstrained.h"
+#include "Sys.h"
+
+// Small dense host matrix standing in for PETSc's Mat in CreateRHSJacobian/ComputeRHSJacobian
+// (only used by tests on small problems; the assembled-Jacobian TsFsp path is out of scope).
+struct _p_Mat {
+  arma::Mat<double> dense;
+  MPI_Comm          comm = nullptr;
+};
+typedef _p_Mat *Mat;
+PACMENSL_API PetscErrorCode MatMult(Mat A, Vec x, Vec y);
+PACMENSL_API PetscErrorCode MatDestroy(Mat *A);
+
+namespace pacmensl {
+using Real = PetscReal;
+using Int = PetscInt;
+
+class PACMENSL_API FspMatrixBase {
+ public:
+  explicit FspMatrixBase(MPI_Comm comm);
+
+  virtual PacmenslErrorCode GenerateValues(const StateSetBase &fsp, const Model &model);
+
+  virtual PacmenslErrorCode GenerateValues(const StateSetBase &fsp, const arma::Mat<Int> &SM,
+                                           std::vector<int> time_varying, const TcoefFun &new_prop_t,
+                                           const PropFun &new_prop_x, const std::vector<int> &enable_reactions,
+                                           void *prop_t_args, void *prop_x_args);
+
+  PacmenslErrorCode SetTimeFun(TcoefFun new_t_fun, void *new_t_fun_args);
+
+  virtual int Destroy();
+
+  /// y = A(t) x.  Collective.  x must not alias y.
+  virtual PacmenslErrorCode Action(PetscReal t, Vec x, Vec y);
+  /// y = (sum_r coef[r] A_r) x with the coefficient vector supplied directly (used by SensFspMatrix).
+  PacmenslErrorCode ActionWithCoefficients(const double *coefs, Vec x, Vec y);
+
+  virtual PacmenslErrorCode CreateRHSJacobian(Mat *A);
+  virtual PacmenslErrorCode ComputeRHSJacobian(PetscReal t, Mat A);
+
+  virtual PacmenslErrorCode GetLocalMVFlops(PetscInt *nflops);
+  int GetNumLocalRows() const { return num_rows_local_; }
+  /// algorithmic bytes moved by one Action on this rank (SURVEY.md section 8d formula)
+  double GetActionBytes() const;
+  /// select a kernel variant (tuning / benchmarks)
+  void SetKernelVariant(int v);
+
+  virtual ~FspMatrixBase();
+
+ protected:
+  MPI_Comm comm_ = MPI_COMM_NULL;
+  int      rank_ = 0, comm_size_ = 1;
+
+  Int num_reactions_ = 0;
+  Int num_rows_global_ = 0;
+  Int num_rows_local_ = 0;
+  Int num_states_local_ = 0;
+  Int own_start_ = 0;
+
+  std::vector<int> enable_reactions_, tv_reactions_, ti_reactions_;
+
+  TcoefFun        t_fun_ = nullptr;
+  void           *t_fun_args_ = nullptr;
+  arma::Row<Real> time_coefficients_;
+
+  fspmat_t  dmat_ = nullptr;
+  PetscBool has_values_ = PETSC_FALSE;
+  int       kernel_variant_ = 0;
+
+  // set when GenerateValues(fsp, model) is used with a model that has a mass-action description
+  std::shared_ptr<MassActionPropensity> mass_action_;
+
+  // sink bookkeeping filled by the constrained subclass
+  int  num_constraints_ = 0;
+  bool owns_sinks_ = false;
+
+  // multi-GPU halo exchange (ghost entries of x) and sink reduction
+  long                 n_ghost_ = 0;
+  DeviceBuffer<double> ghost_buf_, send_buf_, sink_buf_;
+  DeviceBuffer<int>    send_idx_;
+  std::vector<long>    send_counts_, recv_counts_;
+  long                 n_send_ = 0;
+
+  virtual int DetermineLayout_(const StateSetBase &fsp);
+  /// Fill the sink segments for plane order `planes` (constrained subclass); default: none.
+  virtual int CollectSinks_(const StateSetBase &fsp, const arma::Mat<Int> &SM, const std::vector<int> &planes,
+                            const double *diag_planes_dev, long ld, std::vector<long> &sink_ptr,
+                            DeviceBuffer<int> &sink_idx, DeviceBuffer<double> &sink_val);
+  int SetupGhosts_(const StateSetBase &fsp, int *col_planes_dev, long n_entries);
+};
+
+}  // namespace pacmensl

@@ -1,0 +1,134 @@
+// FspSolverMultiSinks.h -- adaptive FSP driver: integrate dp/dt = A(t) p, and whenever too much
+// probability leaks into a sink, enlarge the state set and continue.
+// Mirrors src/Fsp/FspSolverMultiSinks.h:65-335 (same public methods, defaults and error behaviour).
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "CvodeFsp.h"
+#include "DiscreteDistribution.h"
+#include "FspMatrixBase.h"
+#include "FspMatrixConstrained.h"
+#include "KrylovFsp.h"
+#include "Model.h"
+#include "OdeSolverBase.h"
+#include "PetscWrap.h"
+#include "StateSetBase.h"
+#include "StateSetConstrained.h"
+#include "Sys.h"
+
+namespace pacmensl {
+
+struct FspSolverComponentTiming {
+  PetscReal StatePartitioningTime;  ///< state space expansion / partitioning
+  PetscReal MatrixGenerationTime;   ///< transition-rate matrix generation
+  PetscReal ODESolveTime;           ///< time spent in the ODE solver
+  PetscReal SolutionScatterTime;    ///< solution re-scatter on expansion
+  PetscReal RHSEvalTime;            ///< matrix-vector multiplication (host-side launch time unless synchronised)
+  PetscReal TotalTime;
+  PetscReal TotalFlops;
+};
+
+class PACMENSL_API FspSolverMultiSinks {
+  using Real = PetscReal;
+  using Int = PetscInt;
+
+ public:
+  NOT_COPYABLE_NOT_MOVABLE(FspSolverMultiSinks);
+
+  explicit FspSolverMultiSinks(MPI_Comm _comm, PartitioningType _part_type = PartitioningType::GRAPH,
+                               ODESolverType _solve_type = CVODE);
+
+  PacmenslErrorCode SetConstraintFunctions(const fsp_constr_multi_fn &lhs_constr, void *args);
+  PacmenslErrorCode SetInitialBounds(arma::Row<int> &_bounds);
+  PacmenslErrorCode SetExpansionFactors(arma::Row<PetscReal> &_expansion_factors);
+  PacmenslErrorCode SetModel(Model &model);
+  PacmenslErrorCode SetInitialDistribution(const arma::Mat<Int> &_init_states, const arma::Col<PetscReal> &_init_probs);
+  PacmenslErrorCode SetInitialDistribution(DiscreteDistribution &init_dist);
+  PacmenslErrorCode SetUp();
+  PacmenslErrorCode SetFromOptions();
+  PacmenslErrorCode SetLogging(PetscBool logging);
+  PacmenslErrorCode SetVerbosity(int verbosity_level);
+  PacmenslErrorCode SetLoadBalancingMethod(PartitioningType part_type);
+  PacmenslErrorCode SetOdesType(ODESolverType odes_type);
+  PacmenslErrorCode SetOdesPetscType(std::string ts_type);
+  PacmenslErrorCode SetKrylovOrthLength(int q);
+  PacmenslErrorCode SetKrylovDimRange(int m_min, int m_max);
+  PacmenslErrorCode SetOdeTolerances(PetscReal rel_tol, PetscReal abs_tol);
+
+  std::shared_ptr<const StateSetBase> GetStateSet();
+  std::shared_ptr<OdeSolverBase> GetOdeSolver();
+  FspSolverComponentTiming ReduceComponentTiming(char *op);
+  FiniteProblemSolverPerfInfo GetSolverPerfInfo();
+
+  DiscreteDistribution Solve(PetscReal t_final, PetscReal fsp_tol = -1.0, PetscReal t_init = 0.0);
+  std::vector<DiscreteDistribution> SolveTspan(const std::vector<PetscReal> &tspan, PetscReal fsp_tol = -1.0,
+                                               PetscReal t_init = 0.0);
+  PacmenslErrorCode ClearState();
+  ~FspSolverMultiSinks();
+
+  // ---- run statistics (extension; what the examples report) ----
+  int  GetNumExpansions() const { return num_expansions_; }
+  long GetNumRhsEvals() const { return ode_solver_ ? ode_solver_->GetNumRhsEvals() + rhs_evals_retired_ : rhs_evals_retired_; }
+
+ protected:
+  MPI_Comm comm_ = MPI_COMM_NULL;
+  int      my_rank_ = 0;
+  int      comm_size_ = 1;
+
+  PartitioningType     partitioning_type_ = PartitioningType::BLOCK;
+  PartitioningApproach repart_approach_ = PartitioningApproach::REPARTITION;
+  ODESolverType        odes_type_ = CVODE;
+
+  std::shared_ptr<StateSetConstrained>  state_set_ = nullptr;
+  std::shared_ptr<FspMatrixConstrained> A_ = nullptr;
+  std::shared_ptr<OdeSolverBase>        ode_solver_ = nullptr;
+  std::shared_ptr<Petsc<Vec>>           p_ = nullptr;
+
+  bool  set_up_ = false;
+  Model model_;
+  std::function<int(PetscReal, Vec, Vec)> tmatvec_;
+
+  arma::Mat<Int>       init_states_;
+  arma::Col<PetscReal> init_probs_;
+
+  int verbosity_ = 0;
+
+  bool                has_custom_constraints_ = false;
+  fsp_constr_multi_fn fsp_constr_funs_;
+  void               *fsp_constr_args_ = nullptr;
+  arma::Row<int>      fsp_bounds_;
+  arma::Row<Real>     fsp_expasion_factors_;
+
+  PacmenslErrorCode CheckFspTolerance_(PetscReal t, Vec p, PetscReal &tol_exceed);
+  virtual void set_expansion_parameters_() {}
+
+  PetscReal fsp_tol_ = 1.0;
+  PetscReal t_final_ = 0.0;
+  PetscReal t_now_ = 0.0;
+  PetscReal ode_rtol_ = 1.0e-6;
+  PetscReal ode_atol_ = 1.0e-14;
+
+  arma::Row<PetscReal> sinks_;
+  arma::Row<int>       to_expand_;
+
+  DiscreteDistribution Advance_(PetscReal t_final, PetscReal fsp_tol);
+  PacmenslErrorCode MakeDiscreteDistribution_(DiscreteDistribution &dist);
+
+  // phase timers (replace the seven PetscLogEvents of FspSolverMultiSinks.cpp:281-301)
+  PetscBool logging_enabled = PETSC_FALSE;
+  double    t_partition_ = 0, t_matgen_ = 0, t_ode_ = 0, t_scatter_ = 0, t_rhs_ = 0, t_setup_ = 0, t_solve_ = 0;
+  double    flops_ = 0;
+
+  bool        custom_ts_type_ = false;
+  std::string ts_type_ = "";
+  bool        custom_krylov_ = false;
+  int         q_iop_ = -1;
+  int         m_min_ = 25, m_max_ = 60;
+
+  int  num_expansions_ = 0;
+  long rhs_evals_retired_ = 0;
+};
+}  // namespace pacmensl

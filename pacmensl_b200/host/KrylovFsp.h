@@ -1,0 +1,54 @@
+// KrylovFsp.h -- Expokit-style Krylov exponential integrator with incomplete orthogonalisation.
+// Mirrors src/OdeSolver/KrylovFsp.h:34-95 / KrylovFsp.cpp:29-485 (same controller, same constants).
+// The basis generation runs as fused device kernels with device-resident Hessenberg coefficients: per
+// basis vector 1 Action + (q + 1) fused MGS passes + 1 scale, no host synchronisation inside the loop.
+#pragma once
+
+#include "OdeSolverBase.h"
+
+namespace pacmensl {
+class PACMENSL_API KrylovFsp : public OdeSolverBase {
+ public:
+  explicit KrylovFsp(MPI_Comm comm);
+
+  int SetUp() override;
+  PetscInt Solve() override;
+  PacmenslErrorCode SetOrthLength(int q);
+  PacmenslErrorCode SetKrylovDimRange(int m_min, int m_max);
+  int FreeWorkspace() override;
+  ~KrylovFsp();
+
+ protected:
+  const int max_reject_ = 10000;
+  PetscReal delta_ = 1.2, gamma_ = 0.9;  ///< safety factors
+
+  int m_min_ = 25, m_max_ = 60, m_next_ = 25;
+  int m_ = 30;
+  int q_iop = 2;
+
+  int       k1 = 2;
+  int       mb = 0, mx = 0;
+  PetscReal beta = 0.0, avnorm = 0.0;
+  std::vector<Vec>     Vm;
+  arma::Mat<PetscReal> Hm;
+  arma::Mat<PetscReal> F;
+  Vec                  av = nullptr;
+  Vec                  solution_tmp_ = nullptr;
+
+  PetscReal t_now_tmp_ = 0.0;
+  PetscReal t_step_ = 0.0;
+  PetscReal t_step_next_ = 0.0;
+  bool      first_step_initialized_ = false;
+  PetscReal btol_ = 1.0e-14;
+  int       krylov_stat_ = 0;
+
+  DeviceBuffer<double> hdev_;  ///< device-resident orthogonalisation coefficients of the current basis
+  std::vector<double>  hhost_;
+
+  int SetUpWorkSpace();
+  int GenerateBasis(const Vec &v, int m_start, PetscBool *happy_breakdown);
+  int AdvanceOneStep(const Vec &v);
+  int GetDky(PetscReal t, int deg, Vec p_vec);
+  int EstimateCost_(PetscReal tau_new, PetscInt m_new, PetscReal *cost);
+};
+}  // namespace pacmensl

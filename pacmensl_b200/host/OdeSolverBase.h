@@ -1,0 +1,69 @@
+// OdeSolverBase.h -- common interface of the ODE integrators for dp/dt = A(t) p.
+// Mirrors src/OdeSolver/OdeSolverBase.h:52-153.
+#pragma once
+
+#include "FspMatrixBase.h"
+#include "FspMatrixConstrained.h"
+#include "StateSetConstrained.h"
+#include "Sys.h"
+
+namespace pacmensl {
+enum ODESolverType { KRYLOV, CVODE, PETSC, EPIC };
+
+struct FiniteProblemSolverPerfInfo {
+  PetscInt                    n_step;
+  std::vector<PetscInt>       n_eqs;
+  std::vector<PetscLogDouble> cpu_time;
+  std::vector<PetscReal>      model_time;
+};
+
+class PACMENSL_API OdeSolverBase {
+ public:
+  explicit OdeSolverBase(MPI_Comm new_comm);
+
+  PacmenslErrorCode SetFinalTime(PetscReal _t_final);
+  PacmenslErrorCode SetInitialSolution(Vec *_sol);
+  PacmenslErrorCode SetFspMatPtr(FspMatrixBase *mat);
+  PacmenslErrorCode SetRhs(std::function<PacmenslErrorCode(PetscReal, Vec, Vec)> _rhs);
+  int SetTolerances(PetscReal _r_tol, PetscReal _abs_tol);
+  PacmenslErrorCode SetCurrentTime(PetscReal t);
+  PacmenslErrorCode SetStatusOutput(int iprint);
+  PacmenslErrorCode EnableLogging();
+  PacmenslErrorCode SetStopCondition(const std::function<PacmenslErrorCode(PetscReal, Vec, PetscReal &, void *)> &stop_check_,
+                                     void *stop_data_);
+  PacmenslErrorCode EvaluateRHS(PetscReal t, Vec x, Vec y);
+
+  virtual PacmenslErrorCode SetUp() { return 0; }
+  /// 0: reached t_final; 1: stopped by the stop condition; -1: error
+  virtual PetscInt Solve();
+  PetscReal GetCurrentTime() const;
+  FiniteProblemSolverPerfInfo GetAvgPerfInfo() const;
+  virtual PacmenslErrorCode FreeWorkspace() { solution_ = nullptr; return 0; }
+  virtual ~OdeSolverBase();
+
+  /// number of right-hand-side (Action) evaluations since construction (extension, for reports)
+  long GetNumRhsEvals() const { return num_rhs_evals_; }
+
+ protected:
+  MPI_Comm comm_ = MPI_COMM_NULL;
+  int      my_rank_ = 0, comm_size_ = 1;
+
+  Vec *solution_ = nullptr;
+  std::function<int(PetscReal t, Vec x, Vec y)> rhs_;
+  int            rhs_cost_loc_ = 0;
+  FspMatrixBase *fspmat_ = nullptr;
+
+  PetscReal t_now_ = 0.0;
+  PetscReal t_final_ = 0.0;
+
+  int print_intermediate = 0;
+  std::function<PacmenslErrorCode(PetscReal t, Vec p, PetscReal &tol_exceed, void *data)> stop_check_ = nullptr;
+  void *stop_data_ = nullptr;
+
+  PetscBool                   logging_enabled = PETSC_FALSE;
+  FiniteProblemSolverPerfInfo perf_info;
+  PetscReal                   rel_tol_ = 1.0e-6;
+  PetscReal                   abs_tol_ = 1.0e-14;
+  long                        num_rhs_evals_ = 0;
+};
+}  // namespace pacmensl

@@ -1,0 +1,179 @@
+// Host-layer parity tests for the FSP operator, shaped after the reference's tests/test_mat.cpp:
+// 1-d random walk on states 0..12, hop right with rate 2, hop left with rate 3 (x > 0).
+//   KAT-M1  FspMatrixBase:        sum(A * 1) == -2 exactly                (reference test_mat.cpp:110-151)
+//   KAT-M2  FspMatrixConstrained: sum(A * 1) == 0                          (:199-238)
+//   KAT-M3/4 the same through CreateRHSJacobian/ComputeRHSJacobian + MatMult (:153-197, 240-287)
+//   KAT-M5  Action(t, x) == J(t) x for time-varying coefficients at five times (:289-341)
+#include "pacmensl_test_env.h"
+
+using namespace pacmensl;
+
+class MatrixTest : public ::testing::Test {
+ protected:
+  void SetUp() override {
+    fsp_size = arma::Row<int>({12});
+    t_fun = [&](double t, int, double *outputs, void *) {
+      outputs[0] = 1.0 + t;
+      outputs[1] = 1.0 + 0.5 * t;
+      return 0;
+    };
+    propensity = [&](const int reaction, const int, const int num_states, const int *X, double *outputs, void *) {
+      switch (reaction) {
+        case 0: for (int i{0}; i < num_states; ++i) outputs[i] = rate_right * 1.0; break;
+        case 1: for (int i{0}; i < num_states; ++i) outputs[i] = rate_left * (X[i] > 0); break;
+        default: return -1;
+      }
+      return 0;
+    };
+    arma::Mat<PetscInt> X0(1, 1);
+    X0.fill(0);
+    state_set = new StateSetConstrained(PETSC_COMM_WORLD);
+    ASSERT_FALSE(state_set->SetStoichiometryMatrix(stoichiometry));
+    ASSERT_FALSE(state_set->SetShapeBounds(fsp_size));
+    ASSERT_FALSE(state_set->SetUp());
+    ASSERT_FALSE(state_set->AddStates(X0));
+    ASSERT_FALSE(state_set->Expand());
+  }
+  void TearDown() override { delete state_set; }
+
+  Vec make_vec(int n_local, double value) {
+    Vec P;
+    VecCreate(PETSC_COMM_WORLD, &P);
+    VecSetSizes(P, n_local, PETSC_DECIDE);
+    VecSetFromOptions(P);
+    VecSet(P, value);
+    VecSetUp(P);
+    return P;
+  }
+
+  StateSetConstrained *state_set = nullptr;
+  arma::Row<int>       fsp_size;
+  const double         rate_right = 2.0, rate_left = 3.0;
+  const arma::Mat<int> stoichiometry{1, -1};
+  pacmensl::TcoefFun   t_fun;
+  pacmensl::PropFun    propensity;
+};
+
+TEST_F(MatrixTest, mat_base_generation) {
+  ASSERT_EQ(state_set->GetNumGlobalStates(), 13);
+  FspMatrixBase A(PETSC_COMM_WORLD);
+  int ierr = A.GenerateValues(*state_set, stoichiometry, std::vector<int>(), t_fun, propensity, std::vector<int>(), nullptr, nullptr);
+  ASSERT_FALSE(ierr);
+  Vec P = make_vec(state_set->GetNumLocalStates(), 1.0), Q;
+  ASSERT_FALSE(VecDuplicate(P, &Q));
+  ASSERT_FALSE(A.Action(0.0, P, Q));
+  double Q_sum;
+  ASSERT_FALSE(VecSum(Q, &Q_sum));
+  ASSERT_DOUBLE_EQ(Q_sum, -1.0 * rate_right);
+  VecDestroy(&P);
+  VecDestroy(&Q);
+}
+
+TEST_F(MatrixTest, mat_base_jacobian) {
+  FspMatrixBase A(PETSC_COMM_WORLD);
+  ASSERT_FALSE(A.GenerateValues(*state_set, stoichiometry, std::vector<int>(), t_fun, propensity, std::vector<int>(), nullptr, nullptr));
+  Vec P = make_vec(state_set->GetNumLocalStates(), 1.0), Q;
+  ASSERT_FALSE(VecDuplicate(P, &Q));
+  Mat J;
+  ASSERT_FALSE(A.CreateRHSJacobian(&J));
+  ASSERT_FALSE(A.ComputeRHSJacobian(0.0, J));
+  ASSERT_FALSE(MatMult(J, P, Q));
+  double Q_sum;
+  ASSERT_FALSE(VecSum(Q, &Q_sum));
+  ASSERT_DOUBLE_EQ(Q_sum, -1.0 * rate_right);
+  MatDestroy(&J);
+  VecDestroy(&P);
+  VecDestroy(&Q);
+}
+
+TEST_F(MatrixTest, mat_constrained_generate_values) {
+  FspMatrixConstrained A(PETSC_COMM_WORLD);
+  ASSERT_FALSE(A.GenerateValues(*state_set, stoichiometry, std::vector<int>(), t_fun, propensity, std::vector<int>(), nullptr, nullptr));
+  ASSERT_EQ(A.GetNumLocalRows(), 14);
+  Vec P = make_vec(A.GetNumLocalRows(), 1.0), Q;
+  ASSERT_FALSE(VecDuplicate(P, &Q));
+  ASSERT_FALSE(A.Action(0.0, P, Q));
+  double Q_sum;
+  ASSERT_FALSE(VecSum(Q, &Q_sum));
+  ASSERT_DOUBLE_EQ(Q_sum, 0.0);
+  // flops bookkeeping (FspMatrixBase.cpp:429-444 + FspMatrixConstrained.cpp:447-465): 37 nnz + 1 sink nnz
+  PetscInt nflops;
+  ASSERT_FALSE(A.GetLocalMVFlops(&nflops));
+  ASSERT_EQ(nflops, 2 * 37 + 2 * 1);
+  VecDestroy(&P);
+  VecDestroy(&Q);
+}
+
+TEST_F(MatrixTest, mat_constrained_jacobian1) {
+  FspMatrixConstrained A(PETSC_COMM_WORLD);
+  ASSERT_FALSE(A.GenerateValues(*state_set, stoichiometry, std::vector<int>(), t_fun, propensity, std::vector<int>(), nullptr, nullptr));
+  Vec P = make_vec(A.GetNumLocalRows(), 1.0), Q;
+  ASSERT_FALSE(VecDuplicate(P, &Q));
+  Mat J;
+  ASSERT_FALSE(A.CreateRHSJacobian(&J));
+  ASSERT_FALSE(A.ComputeRHSJacobian(0.0, J));
+  ASSERT_FALSE(MatMult(J, P, Q));
+  double Q_sum;
+  ASSERT_FALSE(VecSum(Q, &Q_sum));
+  ASSERT_DOUBLE_EQ(Q_sum, 0.0);
+  MatDestroy(&J);
+  VecDestroy(&P);
+  VecDestroy(&Q);
+}
+
+TEST_F(MatrixTest, mat_constrained_jacobian2) {
+  PetscRandom prand;
+  ASSERT_FALSE(PetscRandomCreate(PETSC_COMM_WORLD, &prand));
+  ASSERT_FALSE(PetscRandomSetType(prand, PETSCRAND));
+  FspMatrixConstrained A(PETSC_COMM_WORLD);
+  ASSERT_FALSE(A.GenerateValues(*state_set, stoichiometry, std::vector<int>({0, 1}), t_fun, propensity, std::vector<int>(), nullptr, nullptr));
+  Vec x = make_vec(A.GetNumLocalRows(), 1.0), y, z;
+  ASSERT_FALSE(VecDuplicate(x, &y));
+  ASSERT_FALSE(VecDuplicate(x, &z));
+  std::vector<PetscReal> t_test({0.0, 0.1, 0.2, 1.0, 10.0});
+  Mat J;
+  ASSERT_FALSE(A.CreateRHSJacobian(&J));
+  PetscReal gap, maxerr = 0.0, ynorm;
+  for (auto t : t_test) {
+    VecSetRandom(x, prand);
+    ASSERT_FALSE(A.ComputeRHSJacobian(t, J));
+    ASSERT_FALSE(MatMult(J, x, y));
+    ASSERT_FALSE(A.Action(t, x, z));
+    VecNorm(y, NORM_2, &ynorm);
+    VecAXPY(z, -1.0, y);
+    VecNorm(z, NORM_2, &gap);
+    // (the reference's own check is vacuous -- it never raises maxerr, test_mat.cpp:339; this one is real)
+    if (gap / ynorm > maxerr) maxerr = gap / ynorm;
+  }
+  ASSERT_LE(maxerr, 1.0e-14);
+  MatDestroy(&J);
+  PetscRandomDestroy(&prand);
+  VecDestroy(&x);
+  VecDestroy(&y);
+  VecDestroy(&z);
+}
+
+TEST_F(MatrixTest, action_before_generate_is_zero_and_destroy_allows_regeneration) {
+  FspMatrixConstrained A(PETSC_COMM_WORLD);
+  Vec x = make_vec(14, 1.0), y = make_vec(14, 5.0);
+  ASSERT_FALSE(A.Action(0.0, x, y));  // FspMatrixBase.cpp:41
+  double s;
+  VecSum(y, &s);
+  ASSERT_EQ(s, 0.0);
+  ASSERT_FALSE(A.GenerateValues(*state_set, stoichiometry, std::vector<int>(), t_fun, propensity, std::vector<int>(), nullptr, nullptr));
+  ASSERT_FALSE(A.Destroy());
+  ASSERT_FALSE(A.GenerateValues(*state_set, stoichiometry, std::vector<int>(), t_fun, propensity, std::vector<int>(), nullptr, nullptr));
+  ASSERT_FALSE(A.Action(0.0, x, y));
+  VecSum(y, &s);
+  ASSERT_DOUBLE_EQ(s, 0.0);
+  // a failing time-coefficient callback propagates its code (FspMatrixBase.cpp:44-45)
+  FspMatrixConstrained B(PETSC_COMM_WORLD);
+  TcoefFun bad = [](double, int, double *, void *) { return -1; };
+  ASSERT_FALSE(B.GenerateValues(*state_set, stoichiometry, std::vector<int>({0}), bad, propensity, std::vector<int>(), nullptr, nullptr));
+  ASSERT_EQ(B.Action(0.0, x, y), -1);
+  // a base state set is rejected by the constrained matrix (FspMatrixConstrained.cpp:133-135)
+  StateSetBase plain(PETSC_COMM_WORLD);
+  ASSERT_EQ(B.GenerateValues(plain, stoichiometry, std::vector<int>(), t_fun, propensity, std::vector<int>(), nullptr, nullptr), -1);
+  VecDestroy(&x);
+  VecDestroy(&y);
+}
