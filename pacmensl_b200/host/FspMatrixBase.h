@@ -16,8 +16,10 @@ struct _p_Mat {
   MPI_Comm          comm = nullptr;
 };
 typedef _p_Mat *Mat;
+extern "C" {
 PACMENSL_API PetscErrorCode MatMult(Mat A, Vec x, Vec y);
 PACMENSL_API PetscErrorCode MatDestroy(Mat *A);
+}
 
 namespace pacmensl {
 using Real = PetscReal;

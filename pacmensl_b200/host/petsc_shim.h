@@ -37,6 +37,7 @@ struct pacmensl_comm_s {
   void     *stream = nullptr;
 };
 typedef pacmensl_comm_s *MPI_Comm;
+extern "C" {
 #define MPI_COMM_NULL ((MPI_Comm) nullptr)
 PACMENSL_API MPI_Comm pacmensl_comm_world();
 PACMENSL_API MPI_Comm pacmensl_comm_self();
@@ -55,6 +56,7 @@ PACMENSL_API int pacmensl_comm_world_finalize();
 // small host-side collectives over the world (device staging + NCCL); identity when size == 1
 PACMENSL_API int pacmensl_allreduce_sum(MPI_Comm comm, double *vals_host, int n);
 PACMENSL_API int pacmensl_allreduce_max(MPI_Comm comm, double *vals_host, int n);
+}  // extern "C"
 
 // ---- Vec ---------------------------------------------------------------------------------------------
 typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_FROBENIUS = 2, NORM_INFINITY = 3 } NormType;
@@ -80,6 +82,7 @@ struct _p_PetscRandom { unsigned long long state = 0x853c49e6748fea9bULL; };
 typedef _p_PetscRandom *PetscRandom;
 #define PETSCRAND "rand"
 
+extern "C" {
 PACMENSL_API PetscErrorCode VecCreate(MPI_Comm comm, Vec *v);
 PACMENSL_API PetscErrorCode VecSetSizes(Vec v, PetscInt n_local, PetscInt n_global);
 PACMENSL_API PetscErrorCode VecSetType(Vec v, VecType type);
@@ -123,6 +126,7 @@ PACMENSL_API PetscErrorCode VecGetDeviceArrayRead(Vec v, const PetscScalar **a_d
 
 PACMENSL_API PetscErrorCode PetscPrintf(MPI_Comm comm, const char *fmt, ...);
 PACMENSL_API PetscErrorCode PetscTime(PetscLogDouble *t);
+}  // extern "C"
 
 #define CHKERRQ(ierr) do { if ((ierr) != 0) return (ierr); } while (0)
 #define CHKERRMPI(ierr) CHKERRQ(ierr)
