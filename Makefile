@@ -4,7 +4,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 CXX_HOST := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -ccbin $(CXX_HOST) -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function,-Wno-deprecated-declarations
-CXXFLAGS := -O2 -g -std=c++17 -fPIC -Wall -Wno-unused-function -fvisibility=hidden -Iinclude -Ipacmensl_b200/host
+CXXFLAGS := -O2 -g -std=c++17 -fPIC -Wall -Wno-unused-function -fvisibility=hidden -Iinclude -Ipacmensl_b200/host -Ipacmensl_b200/fixtures
 
 BUILD := build
 LIB := pacmensl_b200/lib/libpacmensl_b200.so
@@ -20,7 +20,7 @@ $(BUILD)/%.cu.o: pacmensl_b200/csrc/%.cu pacmensl_b200/csrc/fsp_common.cuh inclu
 	@mkdir -p $(BUILD)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
-$(BUILD)/%.host.o: pacmensl_b200/host/%.cpp $(wildcard pacmensl_b200/host/*.h) include/fsp_b200.h pacmensl_b200/fixtures/fsp_models.h
+$(BUILD)/%.host.o: pacmensl_b200/host/%.cpp $(wildcard pacmensl_b200/host/*.h) $(wildcard include/*.h) pacmensl_b200/fixtures/fsp_models.h
 	@mkdir -p $(BUILD)
 	$(CXX_HOST) $(CXXFLAGS) -c $< -o $@
 

@@ -174,42 +174,35 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from pacmensl_b200 import _capi
-    from pacmensl_b200.lattice import build_birth_death_lattice, tcoef
+    from pacmensl_b200 import _capi, api
+    from pacmensl_b200.lattice import Lattice
     L = _capi.lib()
-    _capi.check(L.fsp_device_set(local_rank), "fsp_device_set")
+    api.init(local_rank, dist)
 
+    # ---- build: state set (device hash directory) + operator through the host C++ classes -------------------
     Ledge = args.lattice
     t_build0 = time.perf_counter()
-    if world == 1:
-        M, N = build_birth_death_lattice([Ledge - 1] * 3, tv=args.tv, expand=not args.no_expand)
-        part = None
-    else:
-        from pacmensl_b200.partition import build_partitioned_lattice
-        M, N, part = build_partitioned_lattice([Ledge - 1] * 3, args.tv, rank, world, dist, expand=not args.no_expand)
+    lat = Lattice([Ledge - 1] * 3, tv=args.tv, expand=not args.no_expand)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
-    M.set_variant(args.variant)
-    n_rows = M.n_rows
-    bytes_local = M.action_bytes()
+    lat.mat.set_variant(args.variant)
+    N = lat.n_global
+    n_rows = lat.n_rows
+    bytes_local = lat.bytes
 
     g = torch.Generator(device="cuda").manual_seed(12345 + rank)
     x = torch.rand(n_rows, generator=g, dtype=torch.float64, device="cuda")
-    if M.n < n_rows:
-        x[M.n:] = 0.0
+    if lat.n_local < n_rows:
+        x[lat.n_local:] = 0.0
     s = x.sum()
     if dist is not None:
         dist.all_reduce(s)
     x /= s
     y = torch.empty_like(x)
-    coef = tcoef(0.3, args.tv)
-    stream = torch.cuda.current_stream().cuda_stream
+    t_eval = 0.3
 
     def step():
-        if part is None:
-            M.action(coef, x, y, stream=stream)
-        else:
-            part.action(M, coef, x, y, stream)
+        lat.action(t_eval, x, y)  # FspMatrixConstrained::Action: halo exchange (N > 1) + one fused kernel launch
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -219,7 +212,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # ---- timed region: exactly K steps, CUDA events on the launching stream -------------------------
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------------------
     launches0 = L.fsp_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -243,36 +236,22 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = bytes_total / (ms_per_step * 1e-3) / 1e9
+    # At N = 1 a step IS one launch of the fused Action kernel, so the per-launch duration of the dominant kernel is
+    # the event-timed step; at N > 1 the step also holds the pack kernel + NCCL halo exchange + sink all-reduce.
+    kms = ms_per_step
 
-    # dominant kernel: the fused Action kernel; per-launch duration from a second event-timed loop on rank 0
-    # (single-GPU launches only; at N > 1 this still times the local SpMV launch without the halo exchange)
-    kms = None
-    if rank == 0:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ghost = part.ghost if part is not None else None
-        e0.record()
-        for _ in range(args.steps):
-            M.action(coef, x, y, ghost=ghost, sink_out=(part.sink_buf if part is not None else None), stream=stream)
-        e1.record()
-        torch.cuda.synchronize()
-        kms = e0.elapsed_time(e1) / args.steps
-    if dist is not None:
-        dist.barrier()
-
-    # ---- e2e: the same Action through the C ABI with HOST buffers (H2D x, D2H y inside the timed region) ----
+    # ---- e2e: the same Action through the C ABI with HOST buffers (H2D x, D2H y inside the timed region) -----
     e2e = None
     if not args.no_e2e:
         xh = torch.empty(n_rows, dtype=torch.float64).pin_memory()
         yh = torch.empty(n_rows, dtype=torch.float64).pin_memory()
         xh.copy_(x)
         k2 = max(3, min(args.steps, 10))
-        sptr = C.c_void_p(stream)
 
         def e2e_step():
-            # NB fsp_memcpy_* synchronise the stream, like a blocking host API call would
-            _capi.check(L.fsp_memcpy_h2d(C.c_void_p(x.data_ptr()), C.c_void_p(xh.data_ptr()), n_rows * 8, sptr), "h2d")
-            step()
-            _capi.check(L.fsp_memcpy_d2h(C.c_void_p(yh.data_ptr()), C.c_void_p(y.data_ptr()), n_rows * 8, sptr), "d2h")
+            ierr = lat.mat.action_host(t_eval, xh, yh)  # pfsp_mat_action_host: H2D(x) + Action + D2H(y)
+            if ierr:
+                raise SystemExit("action_host failed")
 
         e2e_step()
         torch.cuda.synchronize()
@@ -288,7 +267,9 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = {"value": bytes_total / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(n_rows * 8),
-               "d2h_bytes_per_step": int(n_rows * 8), "ms_per_step": dt * 1e3, "steps": k2}
+               "d2h_bytes_per_step": int(n_rows * 8), "ms_per_step": dt * 1e3, "steps": k2,
+               "call": "pfsp_mat_action_host (include/pacmensl_b200_host.h) with pinned host x, y"}
+        del xh, yh
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -307,22 +288,26 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (x ~ U(0,1) normalised, torch Philox seed 12345)",
             "config": {"workload": "synthetic 3-D birth-death lattice %d^3 = %d states, S=3 R=6 K=3 sinks, %s, "
-                                   "Action(t,x,y) through FspMatrixConstrained layout" % (Ledge, N, "R_tv=3" if args.tv else "time-invariant"),
+                                   "FspMatrixConstrained::Action(t,x,y)" % (Ledge, N, "R_tv=3" if args.tv else "time-invariant"),
                        "states": N, "bytes_per_row": lattice_bytes_per_row(args.tv),
                        "l2": "inputs (%.2f GB per Action) exceed the 126 MB L2; no flush needed" % (bytes_total / 1e9),
-                       "partition": "1 block" if world == 1 else "%d contiguous row blocks, halo over NCCL" % world,
+                       "partition": "1 block" if world == 1 else "%d contiguous row blocks (BLOCK), NCCL halo exchange + K-double sink all-reduce per Action" % world,
                        "kernel_variant": args.variant, "build_seconds": round(t_build, 2)},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "fsp_action_rows1<P> (pacmensl_b200/csrc/fspmat.cu)",
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "fsp_action_rows1<6> (pacmensl_b200/csrc/fspmat.cu)" + ("" if world == 1 else " + halo exchange (rank 0 share)"),
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_local},
             "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline:
             cb = cpu_baseline(args)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
+    del lat
+    api.finalize()
+    if dist is not None:
         dist.destroy_process_group()
 
 

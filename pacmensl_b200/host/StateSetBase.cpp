@@ -91,6 +91,16 @@ PacmenslErrorCode StateSetBase::AddStates(const arma::Mat<int> &X) {
   return update_layout();
 }
 
+PacmenslErrorCode StateSetBase::AddBoxLattice(const arma::Row<int> &upper) {
+  if (num_species_ != 0 && (int) upper.n_elem != num_species_) return -1;
+  if (num_species_ == 0) num_species_ = (int) upper.n_elem;
+  if (!set_up_) SetUp();
+  PacmenslErrorCode ierr = ensure_device_set();
+  PACMENSLCHKERRQ(ierr);
+  FSPCHKERRQ(fspset_add_box_lattice(dset_, upper.memptr()));
+  return update_layout();
+}
+
 // src/StateSet/StateSetBase.cpp:309-343
 arma::Row<int> StateSetBase::State2Index(const arma::Mat<int> &state) const {
   arma::Row<int> indices((arma::uword) state.n_cols);

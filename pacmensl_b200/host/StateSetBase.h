@@ -28,6 +28,9 @@ class PACMENSL_API StateSetBase {
                                            PartitioningApproach approach = PartitioningApproach::REPARTITION);
   virtual PacmenslErrorCode SetUp();
   PacmenslErrorCode AddStates(const arma::Mat<int> &X);
+  /// Extension: add the full lexicographic box lattice 0..upper[s] (species 0 fastest; the sub2ind_nd ordering of
+  /// src/Sys/pacmenMath.h:33-59), generated on the device -- the synthetic workload of SURVEY.md section 8(d).
+  PacmenslErrorCode AddBoxLattice(const arma::Row<int> &upper);
 
   arma::Row<int> State2Index(const arma::Mat<int> &state) const;
   void State2Index(arma::Mat<int> &state, int *indx) const;

@@ -128,23 +128,54 @@ def test_unaligned_vectors_fall_back_to_scalar_path(cuda, oracle):
 
 
 def test_linearity_and_mass_conservation_large(cuda, oracle):
-    # size-independent properties at a size the oracle is not asked to reproduce:
+    # size-independent properties at a size the oracle is not asked to reproduce, through the host C++ classes
+    # (StateSetConstrained::AddBoxLattice -> FspMatrixConstrained::GenerateValues with device propensities):
     # A(ax + by) = aAx + bAy and 1^T A x = 0 for the constrained box-lattice operator
     torch = cuda
     from pacmensl_b200.lattice import build_birth_death_lattice
     M, n = build_birth_death_lattice([63, 62, 61], tv=False)
+    assert n == 64 * 63 * 62
     g = torch.Generator(device="cuda").manual_seed(11)
     x = torch.rand(M.n_rows, generator=g, dtype=torch.float64, device="cuda")
     z = torch.rand(M.n_rows, generator=g, dtype=torch.float64, device="cuda")
     x[n:] = 0
     z[n:] = 0
     yx, yz, yc = (torch.empty_like(x) for _ in range(3))
-    M.action(np.ones(6), x, yx)
-    M.action(np.ones(6), z, yz)
-    M.action(np.ones(6), 2.0 * x - 0.5 * z, yc)
+    M.action(0.0, x, yx)
+    M.action(0.0, z, yz)
+    M.action(0.0, 2.0 * x - 0.5 * z, yc)
     scale = float(yx.abs().max())
     assert float((yc - (2.0 * yx - 0.5 * yz)).abs().max()) <= 1e-12 * scale
     assert abs(float(yx.sum())) <= 1e-9 * float(yx.abs().sum())
+
+
+def test_host_generate_matches_oracle_lattice(cuda, oracle):
+    # the device-generated lattice operator (hash lookups + mass-action kernels) == oracle built from host callbacks
+    torch, O = cuda, oracle
+    from pacmensl_b200.lattice import build_birth_death_lattice
+    for tv, name in ((False, "birth_death_3d"), (True, "birth_death_3d_tv")):
+        M, n = build_birth_death_lattice([12, 9, 7], tv=tv)
+        st = O.StateSet(fixture=name, bounds=[12, 9, 7])
+        st.expand()
+        A = O.FspMatrix(constrained=True)
+        A.generate_fixture(st, name)
+        assert M.flops == A.flops()
+        # orderings differ (lexicographic lattice vs BFS): compare through the state key
+        X_lat = M.set.states()
+        perm = st.state2index(X_lat)          # oracle index of each lattice state
+        assert (perm >= 0).all()
+        rng = np.random.default_rng(4)
+        x_lat = rng.random(M.n_rows)
+        x_or = np.zeros(A.nrows)
+        x_or[perm] = x_lat[:n]
+        x_or[st.n:] = x_lat[n:]
+        for t in (0.0, 7.0):
+            ierr, y_or = A.action(t, x_or)
+            yd = torch.empty(M.n_rows, dtype=torch.float64, device="cuda")
+            M.action(t, _dev(torch, x_lat), yd)
+            y = yd.cpu().numpy()
+            assert rel_err(y[:n], y_or[perm], scale=np.abs(y_or).max()) <= TOL
+            assert rel_err(y[n:], y_or[st.n:], scale=np.abs(y_or).max()) <= TOL
 
 
 def test_zero_operator_before_generate(cuda):
