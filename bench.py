@@ -24,13 +24,13 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lattice", type=int, default=465, help="states per species axis (L+1); N = lattice^3")
     ap.add_argument("--tv", action="store_true", help="time-varying births (R_tv = 3)")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = default = 1 row per thread; 2, 4 = rows per thread)")
-    ap.add_argument("--cpu-lattice", type=int, default=128, help="lattice edge of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-lattice", type=int, default=200, help="lattice edge of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -1,5 +1,6 @@
 #include "StateSetBase.h"
 
+#include <algorithm>
 #include <iostream>
 
 namespace pacmensl {
@@ -87,7 +88,29 @@ PacmenslErrorCode StateSetBase::AddStates(const arma::Mat<int> &X) {
   if (!set_up_) SetUp();
   PacmenslErrorCode ierr = ensure_device_set();
   PACMENSLCHKERRQ(ierr);
-  if (X.n_cols > 0) FSPCHKERRQ(fspset_add_states(dset_, (int) X.n_rows, (long) X.n_cols, X.memptr(), 0));
+  if (comm_size_ == 1) {
+    if (X.n_cols > 0) FSPCHKERRQ(fspset_add_states(dset_, (int) X.n_rows, (long) X.n_cols, X.memptr(), 0));
+    return update_layout();
+  }
+  // Multi-GPU: each rank may pass its own (possibly overlapping) list (:176-178 of the reference); the replicated
+  // directory receives the union, concatenated in rank order, so that every rank builds the same index map.
+  const int S = num_species_;
+  std::vector<double> counts(comm_size_, 0.0);
+  counts[my_rank_] = (double) X.n_cols;
+  ierr = pacmensl_allreduce_sum(comm_, counts.data(), comm_size_);
+  PACMENSLCHKERRQ(ierr);
+  long pad = 0;
+  for (double c : counts) pad = std::max(pad, (long) c);
+  if (pad > 0) {
+    DeviceBuffer<int> loc((size_t) pad * S), all((size_t) pad * S * comm_size_);
+    if (!loc.get() || !all.get()) PACMENSLCHKERRQ(-1);
+    FSPCHKERRQ(fsp_memset(loc.get(), 0, sizeof(int) * pad * S, comm_->stream));
+    if (X.n_cols > 0) FSPCHKERRQ(fsp_memcpy_h2d(loc.get(), X.memptr(), sizeof(int) * X.n_elem, comm_->stream));
+    FSPCHKERRQ(fspcomm_allgather_int(comm_->nccl, loc.get(), all.get(), pad * S, comm_->stream));
+    for (int r = 0; r < comm_size_; ++r)
+      if (counts[r] > 0)
+        FSPCHKERRQ(fspset_add_states(dset_, S, (long) counts[r], all.get() + (size_t) r * pad * S, 1));
+  }
   return update_layout();
 }
 

@@ -1,6 +1,7 @@
 // petsc_shim.cpp -- device-resident Vec and the communicator shim (see petsc_shim.h).
 #include "petsc_shim.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -152,24 +153,61 @@ PetscErrorCode VecSetValue(Vec v, PetscInt row, PetscScalar value, InsertMode mo
   return VecSetValues(v, 1, &row, &value, mode);
 }
 PetscErrorCode VecAssemblyBegin(Vec) { return 0; }
+// Gather variable-length (index, value) lists from all ranks (rank order); identity when size == 1.
+static int gather_pairs(MPI_Comm comm, std::vector<int> &idx, std::vector<double> &val) {
+  if (!comm || comm->size == 1) return 0;
+  const int size = comm->size, rank = comm->rank;
+  std::vector<double> counts(size, 0.0);
+  counts[rank] = (double) idx.size();
+  int ierr = pacmensl_allreduce_sum(comm, counts.data(), size);
+  if (ierr) return ierr;
+  long pad = 0, total = 0;
+  for (double c : counts) { pad = std::max(pad, (long) c); total += (long) c; }
+  if (total == 0) return 0;
+  int    *d_is = nullptr, *d_ia = nullptr;
+  double *d_vs = nullptr, *d_va = nullptr;
+  if (fsp_malloc((void **) &d_is, sizeof(int) * pad) || fsp_malloc((void **) &d_ia, sizeof(int) * pad * size) ||
+      fsp_malloc((void **) &d_vs, sizeof(double) * pad) || fsp_malloc((void **) &d_va, sizeof(double) * pad * size)) return -1;
+  std::vector<int>    is((size_t) pad, -1), ia((size_t) pad * size);
+  std::vector<double> vs((size_t) pad, 0.0), va((size_t) pad * size);
+  std::copy(idx.begin(), idx.end(), is.begin());
+  std::copy(val.begin(), val.end(), vs.begin());
+  ierr = fsp_memcpy_h2d(d_is, is.data(), sizeof(int) * pad, comm->stream) || fsp_memcpy_h2d(d_vs, vs.data(), sizeof(double) * pad, comm->stream);
+  if (!ierr) ierr = fspcomm_allgather_int(comm->nccl, d_is, d_ia, pad, comm->stream);
+  if (!ierr) ierr = fspcomm_allgather_f64(comm->nccl, d_vs, d_va, pad, comm->stream);
+  if (!ierr) ierr = fsp_memcpy_d2h(ia.data(), d_ia, sizeof(int) * pad * size, comm->stream) || fsp_memcpy_d2h(va.data(), d_va, sizeof(double) * pad * size, comm->stream);
+  fsp_free(d_is); fsp_free(d_ia); fsp_free(d_vs); fsp_free(d_va);
+  if (ierr) return ierr;
+  idx.clear();
+  val.clear();
+  for (int r = 0; r < size; ++r)
+    for (long k = 0; k < (long) counts[r]; ++k) { idx.push_back(ia[(size_t) r * pad + k]); val.push_back(va[(size_t) r * pad + k]); }
+  return 0;
+}
+
 PetscErrorCode VecAssemblyEnd(Vec v) {
-  // Entries are given by GLOBAL index; every rank may set any entry (the reference's callers pass the
-  // same values on all ranks, FspSolverMultiSinks.cpp:628-636).  Only locally owned entries are applied.
-  if (v->pending.empty()) return 0;
-  for (auto &pr : v->pending) {
-    PetscInt loc = pr.first - v->own_start;
+  // Entries are given by GLOBAL index and may belong to another rank (PETSc communicates them at assembly time):
+  // the staged (index, value) pairs of all ranks are gathered in rank order and every rank applies the ones it owns.
+  // Collective when the communicator has more than one rank.
+  std::vector<int>    idx;
+  std::vector<double> val;
+  for (auto &pr : v->pending) { idx.push_back(pr.first); val.push_back(pr.second); }
+  v->pending.clear();
+  int ierr = gather_pairs(v->comm, idx, val);
+  if (ierr) return ierr;
+  for (size_t k = 0; k < idx.size(); ++k) {
+    PetscInt loc = idx[k] - v->own_start;
     if (loc < 0 || loc >= v->n_local) continue;
-    double val = pr.second;
+    double value = val[k];
     if (v->pending_mode == ADD_VALUES) {
       double cur;
-      int ierr = fsp_memcpy_d2h(&cur, v->d_data + loc, sizeof(double), S(v));
+      ierr = fsp_memcpy_d2h(&cur, v->d_data + loc, sizeof(double), S(v));
       if (ierr) return ierr;
-      val += cur;
+      value += cur;
     }
-    int ierr = fsp_memcpy_h2d(v->d_data + loc, &val, sizeof(double), S(v));
+    ierr = fsp_memcpy_h2d(v->d_data + loc, &value, sizeof(double), S(v));
     if (ierr) return ierr;
   }
-  v->pending.clear();
   return 0;
 }
 

@@ -1,0 +1,35 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped on a single-GPU box): launches tests/multirank_check.py under torchrun
+and the C++ host tests as N ranks (the counterpart of the reference's `mpirun -np N <gtest program>`)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu(cuda):
+    return cuda.cuda.device_count()
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_partitioned_action_and_solves(cuda, nranks):
+    if _ngpu(cuda) < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nranks), "--master-addr",
+           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "multirank_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    print(r.stdout[-4000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "MULTIRANK OK" in r.stdout
+
+
+@pytest.mark.parametrize("prog", ["test_mat", "test_fss", "test_ode", "test_fsp_solver"])
+def test_cpp_programs_two_ranks(cuda, prog):
+    if _ngpu(cuda) < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([os.path.join(ROOT, "tools", "launch_ranks.sh"), "2", os.path.join(ROOT, "build", "tests", prog)],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "0 failed" in r.stdout
