@@ -48,6 +48,7 @@ FSP_API int         fsp_device_sync(void);
 FSP_API int         fsp_event_create(void **event);
 FSP_API int         fsp_event_destroy(void *event);
 FSP_API int         fsp_event_record(void *event, void *stream);
+FSP_API int         fsp_stream_wait_event(void *stream, void *event);
 FSP_API int         fsp_event_elapsed_ms(void *start, void *stop, float *ms); /* syncs on stop */
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 FSP_API long long   fsp_launch_count(void);
@@ -223,6 +224,14 @@ FSP_API int fspmat_clear(fspmat_t h); /* Destroy(): frees values, object reusabl
  * (K doubles) instead of y; pass NULL to drop them. */
 FSP_API int fspmat_action(fspmat_t h, const double *coef_host, const double *x_dev, const double *ghost_dev,
                           double *y_dev, double *sink_out_dev, void *stream);
+/* Split action for overlapping the halo exchange with compute (multi-GPU):
+ *   phase 1  interior pass: all rows with ghost entries counted as 0, no sink rows (ghost_dev unused)
+ *   phase 2  boundary rows only (the rows that reference ghost slots; needs ghost_dev) -- run after phase 1
+ *   phase 3  sink partial sums only, written to sink_out_dev (K doubles)
+ *   phase 0  == fspmat_action (everything in one launch) */
+FSP_API int fspmat_action_phase(fspmat_t h, const double *coef_host, const double *x_dev, const double *ghost_dev,
+                                double *y_dev, double *sink_out_dev, int phase, void *stream);
+FSP_API int fspmat_num_boundary_rows(fspmat_t h, long *n);
 FSP_API int fspmat_flops(fspmat_t h, long *nflops);
 FSP_API int fspmat_num_rows(fspmat_t h, int *n_rows);
 /* algorithmic bytes of one Action: n*(16 + 12 P + 8 (n_tv + [n_ti>0])) + 12 nnz_sink + 8 K */

@@ -51,6 +51,7 @@ SIGNATURES = {
     "fsp_event_create": (ci, [vpp]),
     "fsp_event_destroy": (ci, [vp]),
     "fsp_event_record": (ci, [vp, vp]),
+    "fsp_stream_wait_event": (ci, [vp, vp]),
     "fsp_event_elapsed_ms": (ci, [vp, vp, C.POINTER(C.c_float)]),
     "fsp_launch_count": (C.c_longlong, []),
     "fspvec_set": (ci, [vp, cd, cl, vp]),
@@ -101,6 +102,8 @@ SIGNATURES = {
     "fspmat_generate": (ci, [vp, C.POINTER(FspMatDesc)]),
     "fspmat_clear": (ci, [vp]),
     "fspmat_action": (ci, [vp, dp, vp, vp, vp, vp, vp]),
+    "fspmat_action_phase": (ci, [vp, dp, vp, vp, vp, vp, ci, vp]),
+    "fspmat_num_boundary_rows": (ci, [vp, lp]),
     "fspmat_flops": (ci, [vp, lp]),
     "fspmat_num_rows": (ci, [vp, ip]),
     "fspmat_action_bytes": (ci, [vp, dp]),

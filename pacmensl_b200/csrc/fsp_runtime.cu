@@ -74,12 +74,16 @@ int fsp_stream_sync(void *s) { FSP_CUDA_CHECK(cudaStreamSynchronize(resolve_stre
 int fsp_device_sync(void) { FSP_CUDA_CHECK(cudaDeviceSynchronize()); return 0; }
 int fsp_event_create(void **e) {
   cudaEvent_t ev;
-  FSP_CUDA_CHECK(cudaEventCreate(&ev));
+  FSP_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDefault));
   *e = (void *) ev;
   return 0;
 }
 int fsp_event_destroy(void *e) { if (e) FSP_CUDA_CHECK(cudaEventDestroy((cudaEvent_t) e)); return 0; }
 int fsp_event_record(void *e, void *s) { FSP_CUDA_CHECK(cudaEventRecord((cudaEvent_t) e, resolve_stream(s))); return 0; }
+int fsp_stream_wait_event(void *s, void *e) {
+  FSP_CUDA_CHECK(cudaStreamWaitEvent(resolve_stream(s), (cudaEvent_t) e, 0));
+  return 0;
+}
 int fsp_event_elapsed_ms(void *a, void *b, float *ms) {
   FSP_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t) b));
   FSP_CUDA_CHECK(cudaEventElapsedTime(ms, (cudaEvent_t) a, (cudaEvent_t) b));

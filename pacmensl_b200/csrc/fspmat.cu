@@ -39,7 +39,8 @@ struct Coefs {
 };
 
 struct MatView {
-  int           n;       // local states (rows of the main block)
+  int           n;       // rows this launch processes (local states, or the boundary-list length)
+  int           n_rows_main;  // local states: the sink rows of y start here
   int           P, ND;
   long          ld;
   const int    *col;
@@ -57,12 +58,17 @@ struct MatView {
   double       *sink_partials; // [sink_blocks]
   unsigned     *sink_counter;
   int           owns_sinks;
+  // split (multi-GPU overlap) phases
+  int           ghost_zero;    // 1: ghost entries contribute 0 (interior pass, halo still in flight)
+  const int    *row_list;      // non-null: process only these rows (boundary pass); n = list length
+  int           write_y_sinks; // 0: sink role writes only sink_out (the owner copies the reduced values later)
 };
 
 __device__ __forceinline__ double fetch_x(const double *__restrict__ x, const double *__restrict__ ghost, int c) {
   // c >= 0: local entry; c == -1: absent neighbour (contributes 0); c <= -2: ghost slot
+  // (ghost == nullptr during the interior pass of the split multi-GPU action: contributes 0, the row is redone later)
   if (c >= 0) return __ldg(x + c);
-  if (c == -1) return 0.0;
+  if (c == -1 || ghost == nullptr) return 0.0;
   return __ldg(ghost + (-(c + 2)));
 }
 
@@ -99,7 +105,7 @@ __device__ __forceinline__ void sink_role(const MatView &m, const Coefs &cf, con
     }
     s = warp_sum(s);
     if (lane == 0) {
-      if (m.owns_sinks) y[m.n + k] = s;
+      if (m.owns_sinks && m.write_y_sinks) y[m.n_rows_main + k] = s;
       if (sink_out) sink_out[k] = s;
     }
   }
@@ -218,8 +224,11 @@ __global__ void __launch_bounds__(kThreads) fsp_action_rows1(MatView m, Coefs cf
     sink_role(m, cf, x, y, sink_out);
     return;
   }
-  const long i = (long) blockIdx.x * kThreads + threadIdx.x;
-  if (i < m.n) y[i] = row_scalar<P>(m, cf, x, ghost, i);
+  const long q = (long) blockIdx.x * kThreads + threadIdx.x;
+  if (q < m.n) {
+    const long i = m.row_list ? (long) m.row_list[q] : q;
+    y[i] = row_scalar<P>(m, cf, x, ghost, i);
+  }
 }
 
 // generic number of planes (P > 16): runtime loop
@@ -231,8 +240,9 @@ __global__ void __launch_bounds__(kThreads) fsp_action_generic(MatView m, Coefs 
     sink_role(m, cf, x, y, sink_out);
     return;
   }
-  const long i = (long) blockIdx.x * kThreads + threadIdx.x;
-  if (i >= m.n) return;
+  const long q = (long) blockIdx.x * kThreads + threadIdx.x;
+  if (q >= m.n) return;
+  const long   i = m.row_list ? (long) m.row_list[q] : q;
   const double xi = __ldg(x + i);
   double       d = 0.0;
   for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(m.diag + g * m.ld + i), d);
@@ -343,6 +353,14 @@ __global__ void remap_cols_kernel(int *col, long n, int lo, int hi, const int *g
   }
   col[q] = -((int) a + 2);
 }
+struct RowHasGhost {
+  const int *col; long ld; int P;
+  __host__ __device__ bool operator()(const int &i) const {
+    for (int p = 0; p < P; ++p)
+      if (col[p * ld + i] <= -2) return true;
+    return false;
+  }
+};
 __global__ void shift_idx_kernel(int *idx, long n, int delta) {
   long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) idx[q] += delta;
@@ -372,13 +390,15 @@ struct fspmat_s {
   long     flops = 0;
   double   bytes = 0.0;
   int      variant = 0;
+  int     *d_boundary_rows = nullptr;  // rows referencing ghost entries (multi-GPU)
+  long     n_boundary = 0;
 };
 
 static int free_values(fspmat_s *h) {
   cudaFree(h->d_col); cudaFree(h->d_off); cudaFree(h->d_diag);
   cudaFree(h->d_sink_idx); cudaFree(h->d_sink_val);
   cudaFree(h->d_sb_seg); cudaFree(h->d_sb_begin); cudaFree(h->d_sb_end);
-  cudaFree(h->d_sink_partials); cudaFree(h->d_sink_counter);
+  cudaFree(h->d_sink_partials); cudaFree(h->d_sink_counter); cudaFree(h->d_boundary_rows);
   int variant = h->variant;
   *h = fspmat_s();
   h->variant = variant;
@@ -448,6 +468,25 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
     FSP_LAUNCH_CHECK();
     FSP_CUDA_CHECK(cudaStreamSynchronize(st));
     cudaFree(t_col); cudaFree(t_off); cudaFree(t_diag);
+  }
+
+  // ---- multi-GPU: list of rows that reference ghost entries (redone after the halo exchange) ----------
+  if (h->n_ghost > 0 && P > 0 && n > 0) {
+    int   *d_num = nullptr;
+    void  *d_tmp = nullptr;
+    size_t need = 0;
+    FSP_CUDA_CHECK(cudaMalloc(&d_num, sizeof(int)));
+    FSP_CUDA_CHECK(cudaMalloc(&h->d_boundary_rows, sizeof(int) * n));
+    cub::CountingInputIterator<int> iota(0);
+    RowHasGhost pred{h->d_col, ld, P};
+    cub::DeviceSelect::If(nullptr, need, iota, h->d_boundary_rows, d_num, (int) n, pred);
+    FSP_CUDA_CHECK(cudaMalloc(&d_tmp, need));
+    FSP_CUDA_CHECK(cub::DeviceSelect::If(d_tmp, need, iota, h->d_boundary_rows, d_num, (int) n, pred));
+    count_launch();
+    int nb = 0;
+    FSP_CUDA_CHECK(cudaMemcpy(&nb, d_num, sizeof(int), cudaMemcpyDeviceToHost));
+    h->n_boundary = nb;
+    cudaFree(d_num); cudaFree(d_tmp);
   }
 
   // ---- flops: 2 nnz per matrix (+ rows per TV axpy); FspMatrixBase.cpp:429-444 -------------------
@@ -541,19 +580,18 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
   return 0;
 }
 
-int fspmat_action(fspmat_t h, const double *coef_host, const double *x, const double *ghost, double *y,
-                  double *sink_out, void *stream) {
-  cudaStream_t st = resolve_stream(stream);
-  if (!h->has_values) {  // FspMatrixBase.cpp:41 -- an operator without values acts as zero
-    return 0;
-  }
+// phase: 0 = everything in one launch; 1 = interior pass (all rows, ghost entries count as 0, no sink rows);
+//        2 = boundary rows only (needs the ghost buffer); 3 = sink partial sums only (written to sink_out)
+static int launch_action(fspmat_t h, const double *coef_host, const double *x, const double *ghost, double *y,
+                         double *sink_out, int phase, cudaStream_t st) {
+  if (!h->has_values) return 0;  // FspMatrixBase.cpp:41 -- an operator without values acts as zero
   Coefs cf;
   for (int g = 0; g < h->n_tv; ++g) { cf.c[g] = coef_host[h->tv[g]]; cf.cd[g] = cf.c[g]; }
   for (int q = 0; q < h->n_ti; ++q) cf.c[h->n_tv + q] = 1.0;
   if (h->n_ti > 0) cf.cd[h->n_tv] = 1.0;
 
   MatView m;
-  m.n = h->n; m.P = h->P; m.ND = h->ND; m.ld = h->ld;
+  m.n = h->n; m.n_rows_main = h->n; m.P = h->P; m.ND = h->ND; m.ld = h->ld;
   m.col = h->d_col; m.off = h->d_off; m.diag = h->d_diag;
   m.K = h->K; m.G = h->ND;
   m.sink_blocks = (h->K > 0 && (h->owns_sinks || sink_out)) ? h->sink_blocks : 0;
@@ -561,22 +599,39 @@ int fspmat_action(fspmat_t h, const double *coef_host, const double *x, const do
   m.sink_idx = h->d_sink_idx; m.sink_val = h->d_sink_val;
   m.sink_partials = h->d_sink_partials; m.sink_counter = h->d_sink_counter;
   m.owns_sinks = h->owns_sinks;
+  m.ghost_zero = 0; m.row_list = nullptr; m.write_y_sinks = 1;
 
   // variant 0 = default = 1 row per thread: 32 registers -> full occupancy, measured fastest on B200
   // (465^3 lattice: 7.0 TB/s vs 6.7 TB/s for 2 rows and 5.8 TB/s for 4 rows per thread, profiles/)
   int rows_per_thread = h->variant == 2 ? 2 : (h->variant == 4 ? 4 : 1);
   // vector paths need 16-byte aligned x and y
   if (((uintptr_t) x & 15u) || ((uintptr_t) y & 15u)) rows_per_thread = 1;
+  if (phase == 1) { ghost = nullptr; m.ghost_zero = 1; m.sink_blocks = 0; }
+  if (phase == 2) { m.row_list = h->d_boundary_rows; m.n = (int) h->n_boundary; m.sink_blocks = 0; rows_per_thread = 1; }
+  if (phase == 3) { m.n = 0; m.write_y_sinks = 0; rows_per_thread = 1; }
   action_fn fn = pick_kernel(h->P, rows_per_thread);
   if (!fn) { fn = fsp_action_generic; rows_per_thread = 1; }
   long per_block = (long) kThreads * rows_per_thread;
-  m.main_blocks = (int) ((h->n + per_block - 1) / per_block);
+  m.main_blocks = (int) ((m.n + per_block - 1) / per_block);
   int grid = m.main_blocks + m.sink_blocks;
   if (grid == 0) return 0;
   fn<<<grid, kThreads, 0, st>>>(m, cf, x, ghost, y, sink_out);
   FSP_LAUNCH_CHECK();
   return 0;
 }
+
+int fspmat_action(fspmat_t h, const double *coef_host, const double *x, const double *ghost, double *y,
+                  double *sink_out, void *stream) {
+  return launch_action(h, coef_host, x, ghost, y, sink_out, 0, resolve_stream(stream));
+}
+
+int fspmat_action_phase(fspmat_t h, const double *coef_host, const double *x, const double *ghost, double *y,
+                        double *sink_out, int phase, void *stream) {
+  if (phase < 0 || phase > 3) { set_error("fspmat_action_phase: bad phase %d", phase); return -1; }
+  return launch_action(h, coef_host, x, ghost, y, sink_out, phase, resolve_stream(stream));
+}
+
+int fspmat_num_boundary_rows(fspmat_t h, long *n) { *n = h->n_boundary; return 0; }
 
 int fspmat_build_ghosts(int *col, long n, int lo, int hi, int **ghost_out, long *n_ghost) {
   *ghost_out = nullptr;

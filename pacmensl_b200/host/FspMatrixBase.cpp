@@ -34,6 +34,12 @@ FspMatrixBase::FspMatrixBase(MPI_Comm comm) {
 
 FspMatrixBase::~FspMatrixBase() {
   Destroy();
+  if (comm_stream_) {
+    fsp_stream_sync(comm_stream_);
+    fsp_stream_destroy(comm_stream_);
+    fsp_event_destroy(ev_x_ready_);
+    fsp_event_destroy(ev_comm_done_);
+  }
   if (dmat_) fspmat_destroy(dmat_);
   dmat_ = nullptr;
   comm_ = MPI_COMM_NULL;
@@ -236,20 +242,38 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
     PACMENSLCHKERRQ(-1);
   }
   void *stream = comm_ ? comm_->stream : nullptr;
-  if (comm_size_ > 1 && (n_send_ > 0 || n_ghost_ > 0)) {
-    // halo exchange of the ghost entries of x (replaces the VecScatter inside MatMult on MATMPISELL)
-    if (n_send_ > 0) FSPCHKERRQ(fspvec_gather(send_buf_.get(), x->d_data, send_idx_.get(), n_send_, stream));
+  if (comm_size_ == 1) {
+    FSPCHKERRQ(fspmat_action(dmat_, coefs, x->d_data, nullptr, y->d_data, nullptr, stream));
+    return 0;
+  }
+  // Multi-GPU: overlap communication with the interior rows.
+  //   side stream : pack boundary entries of x -> NCCL halo exchange (replaces the VecScatter inside MatMult on
+  //                 MATMPISELL) -> K partial sink sums -> K-double all-reduce (FspMatrixConstrained.cpp:57-60)
+  //   main stream : interior pass over all rows (ghost entries counted as 0)
+  //   join        : rows that reference ghost entries are recomputed with the received halo; the owner of the sink
+  //                 rows copies the reduced sums into y.
+  if (!comm_stream_) {
+    FSPCHKERRQ(fsp_stream_create(&comm_stream_));
+    FSPCHKERRQ(fsp_event_create(&ev_x_ready_));
+    FSPCHKERRQ(fsp_event_create(&ev_comm_done_));
+  }
+  FSPCHKERRQ(fsp_event_record(ev_x_ready_, stream));
+  FSPCHKERRQ(fsp_stream_wait_event(comm_stream_, ev_x_ready_));
+  if (n_send_ > 0) FSPCHKERRQ(fspvec_gather(send_buf_.get(), x->d_data, send_idx_.get(), n_send_, comm_stream_));
+  if (n_send_ > 0 || n_ghost_ > 0)
     FSPCHKERRQ(fspcomm_halo_exchange(comm_->nccl, send_buf_.get(), send_counts_.data(), ghost_buf_.get(),
-                                     recv_counts_.data(), stream));
-  }
-  double *sink_out = (comm_size_ > 1 && num_constraints_ > 0) ? sink_buf_.get() : nullptr;
-  FSPCHKERRQ(fspmat_action(dmat_, coefs, x->d_data, ghost_buf_.get(), y->d_data, sink_out, stream));
+                                     recv_counts_.data(), comm_stream_));
+  double *sink_out = num_constraints_ > 0 ? sink_buf_.get() : nullptr;
   if (sink_out) {
-    // K partial sink sums -> owner of the sink rows (FspMatrixConstrained.cpp:57-60)
-    FSPCHKERRQ(fspcomm_allreduce_sum(comm_->nccl, sink_out, num_constraints_, stream));
-    if (owns_sinks_)
-      FSPCHKERRQ(fsp_memcpy_d2d(y->d_data + num_states_local_, sink_out, sizeof(double) * num_constraints_, stream));
+    FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, nullptr, y->d_data, sink_out, 3, comm_stream_));
+    FSPCHKERRQ(fspcomm_allreduce_sum(comm_->nccl, sink_out, num_constraints_, comm_stream_));
   }
+  FSPCHKERRQ(fsp_event_record(ev_comm_done_, comm_stream_));
+  FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, nullptr, y->d_data, nullptr, 1, stream));
+  FSPCHKERRQ(fsp_stream_wait_event(stream, ev_comm_done_));
+  if (n_ghost_ > 0) FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, ghost_buf_.get(), y->d_data, nullptr, 2, stream));
+  if (sink_out && owns_sinks_)
+    FSPCHKERRQ(fsp_memcpy_d2d(y->d_data + num_states_local_, sink_out, sizeof(double) * num_constraints_, stream));
   return 0;
 }
 

@@ -90,6 +90,8 @@ class PACMENSL_API FspMatrixBase {
   DeviceBuffer<int>    send_idx_;
   std::vector<long>    send_counts_, recv_counts_;
   long                 n_send_ = 0;
+  void                *comm_stream_ = nullptr;              ///< side stream carrying pack + halo + sink all-reduce
+  void                *ev_x_ready_ = nullptr, *ev_comm_done_ = nullptr;
 
   virtual int DetermineLayout_(const StateSetBase &fsp);
   /// Fill the sink segments for plane order `planes` (constrained subclass); default: none.
