@@ -28,6 +28,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lattice", type=int, default=465, help="states per species axis (L+1); N = lattice^3")
+    ap.add_argument("--lattice-dims", default=None, help="a,b,c states per axis (overrides --lattice; diagnostics)")
     ap.add_argument("--tv", action="store_true", help="time-varying births (R_tv = 3)")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = default = 1 row per thread; 2, 4 = rows per thread)")
     ap.add_argument("--cpu-lattice", type=int, default=200, help="lattice edge of the bounded CPU-baseline sample")
@@ -182,7 +183,8 @@ def main():
     # ---- build: state set (device hash directory) + operator through the host C++ classes -------------------
     Ledge = args.lattice
     t_build0 = time.perf_counter()
-    lat = Lattice([Ledge - 1] * 3, tv=args.tv, expand=not args.no_expand)
+    dims = [Ledge] * 3 if not args.lattice_dims else [int(v) for v in args.lattice_dims.split(",")]
+    lat = Lattice([d - 1 for d in dims], tv=args.tv, expand=not args.no_expand)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
     lat.mat.set_variant(args.variant)
@@ -287,8 +289,8 @@ def main():
             "metric": "FSP Action() GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (x ~ U(0,1) normalised, torch Philox seed 12345)",
-            "config": {"workload": "synthetic 3-D birth-death lattice %d^3 = %d states, S=3 R=6 K=3 sinks, %s, "
-                                   "FspMatrixConstrained::Action(t,x,y)" % (Ledge, N, "R_tv=3" if args.tv else "time-invariant"),
+            "config": {"workload": "synthetic 3-D birth-death lattice %s = %d states, S=3 R=6 K=3 sinks, %s, "
+                                   "FspMatrixConstrained::Action(t,x,y)" % ("x".join(str(d) for d in dims), N, "R_tv=3" if args.tv else "time-invariant"),
                        "states": N, "bytes_per_row": lattice_bytes_per_row(args.tv),
                        "l2": "inputs (%.2f GB per Action) exceed the 126 MB L2; no flush needed" % (bytes_total / 1e9),
                        "partition": "1 block" if world == 1 else "%d contiguous row blocks (BLOCK), NCCL halo exchange + K-double sink all-reduce per Action" % world,

@@ -64,8 +64,12 @@ int fsp_memset(void *d, int byte, size_t b, void *st) {
   return 0;
 }
 int fsp_stream_create(void **s) {
+  // non-blocking, highest priority: the library's side streams carry small communication kernels that must be
+  // scheduled ahead of the bulk kernel they overlap with
   cudaStream_t st;
-  FSP_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int lo = 0, hi = 0;
+  FSP_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  FSP_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi));
   *s = (void *) st;
   return 0;
 }

@@ -1,6 +1,7 @@
 #include "FspMatrixBase.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 PetscErrorCode MatMult(Mat A, Vec x, Vec y) {
   // dense host product for the small test matrices produced by ComputeRHSJacobian
@@ -252,28 +253,74 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
   //   main stream : interior pass over all rows (ghost entries counted as 0)
   //   join        : rows that reference ghost entries are recomputed with the received halo; the owner of the sink
   //                 rows copies the reduced sums into y.
+  static const int mode = [] {  // FSP_MULTIGPU_MODE: overlap (default) | sequential | nocomm (timing diagnostics only)
+    const char *e = std::getenv("FSP_MULTIGPU_MODE");
+    if (!e) return 0;
+    if (!std::strcmp(e, "sequential")) return 1;
+    if (!std::strcmp(e, "nocomm")) return 2;
+    return 0;
+  }();
+  if (mode == 2) {
+    FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, nullptr, y->d_data, nullptr, 1, stream));
+    return 0;
+  }
+  if (mode == 1) {
+    if (n_send_ > 0) FSPCHKERRQ(fspvec_gather(send_buf_.get(), x->d_data, send_idx_.get(), n_send_, stream));
+    if (n_send_ > 0 || n_ghost_ > 0)
+      FSPCHKERRQ(fspcomm_halo_exchange(comm_->nccl, send_buf_.get(), send_counts_.data(), ghost_buf_.get(),
+                                       recv_counts_.data(), stream));
+    double *so = num_constraints_ > 0 ? sink_buf_.get() : nullptr;
+    FSPCHKERRQ(fspmat_action(dmat_, coefs, x->d_data, ghost_buf_.get(), y->d_data, so, stream));
+    if (so) {
+      FSPCHKERRQ(fspcomm_allreduce_sum(comm_->nccl, so, num_constraints_, stream));
+      if (owns_sinks_) FSPCHKERRQ(fsp_memcpy_d2d(y->d_data + num_states_local_, so, sizeof(double) * num_constraints_, stream));
+    }
+    return 0;
+  }
   if (!comm_stream_) {
     FSPCHKERRQ(fsp_stream_create(&comm_stream_));
     FSPCHKERRQ(fsp_event_create(&ev_x_ready_));
     FSPCHKERRQ(fsp_event_create(&ev_comm_done_));
   }
+  // optional timeline (FSP_MULTIGPU_TRACE=n prints event timings of the first n Actions after 30 warm-up calls)
+  static const int trace_n = [] { const char *e = std::getenv("FSP_MULTIGPU_TRACE"); return e ? std::atoi(e) : 0; }();
+  static int   trace_calls = 0;
+  static void *tev[8] = {nullptr};
+  const bool   tracing = trace_n > 0 && trace_calls >= 30 && trace_calls < 30 + trace_n;
+  trace_calls++;
+  if (tracing && !tev[0]) for (auto &e : tev) fsp_event_create(&e);
+  if (tracing) fsp_event_record(tev[0], stream);
+
   FSPCHKERRQ(fsp_event_record(ev_x_ready_, stream));
   FSPCHKERRQ(fsp_stream_wait_event(comm_stream_, ev_x_ready_));
   if (n_send_ > 0) FSPCHKERRQ(fspvec_gather(send_buf_.get(), x->d_data, send_idx_.get(), n_send_, comm_stream_));
+  if (tracing) fsp_event_record(tev[1], comm_stream_);
   if (n_send_ > 0 || n_ghost_ > 0)
     FSPCHKERRQ(fspcomm_halo_exchange(comm_->nccl, send_buf_.get(), send_counts_.data(), ghost_buf_.get(),
                                      recv_counts_.data(), comm_stream_));
+  if (tracing) fsp_event_record(tev[2], comm_stream_);
   double *sink_out = num_constraints_ > 0 ? sink_buf_.get() : nullptr;
   if (sink_out) {
     FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, nullptr, y->d_data, sink_out, 3, comm_stream_));
+    if (tracing) fsp_event_record(tev[3], comm_stream_);
     FSPCHKERRQ(fspcomm_allreduce_sum(comm_->nccl, sink_out, num_constraints_, comm_stream_));
   }
+  if (tracing) fsp_event_record(tev[4], comm_stream_);
   FSPCHKERRQ(fsp_event_record(ev_comm_done_, comm_stream_));
   FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, nullptr, y->d_data, nullptr, 1, stream));
+  if (tracing) fsp_event_record(tev[5], stream);
   FSPCHKERRQ(fsp_stream_wait_event(stream, ev_comm_done_));
   if (n_ghost_ > 0) FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, ghost_buf_.get(), y->d_data, nullptr, 2, stream));
   if (sink_out && owns_sinks_)
     FSPCHKERRQ(fsp_memcpy_d2d(y->d_data + num_states_local_, sink_out, sizeof(double) * num_constraints_, stream));
+  if (tracing) {
+    fsp_event_record(tev[6], stream);
+    float t[7] = {0};
+    for (int k = 1; k <= 6; ++k) fsp_event_elapsed_ms(tev[0], tev[k], &t[k]);
+    if (rank_ == 0)
+      printf("[trace] pack %.3f | halo %.3f | sinks %.3f | allreduce %.3f || interior %.3f | end %.3f ms\n", t[1], t[2], t[3],
+             t[4], t[5], t[6]);
+  }
   return 0;
 }
 
