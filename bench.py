@@ -30,7 +30,7 @@ def parse():
     ap.add_argument("--lattice", type=int, default=465, help="states per species axis (L+1); N = lattice^3")
     ap.add_argument("--lattice-dims", default=None, help="a,b,c states per axis (overrides --lattice; diagnostics)")
     ap.add_argument("--tv", action="store_true", help="time-varying births (R_tv = 3)")
-    ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = default = 1 row per thread; 2, 4 = rows per thread)")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = default lean kernel; 1,2,3,4 = alternatives, see fspmat.cu)")
     ap.add_argument("--cpu-lattice", type=int, default=200, help="lattice edge of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -297,7 +297,7 @@ def main():
                        "kernel_variant": args.variant, "build_seconds": round(t_build, 2)},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "fsp_action_rows1<6> (pacmensl_b200/csrc/fspmat.cu)" + ("" if world == 1 else " + halo exchange (rank 0 share)"),
+                         "kernel": "fsp_action_lean<6,*> (pacmensl_b200/csrc/fspmat.cu)" + ("" if world == 1 else " + halo exchange (rank 0 share)"),
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_local},
             "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks,
         }

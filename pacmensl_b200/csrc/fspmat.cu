@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kThreads) fsp_action_rows4(MatView m, Coefs cf
 }
 
 // 1 row per thread (also the path for unaligned x / y)
-template <int P>
-__global__ void __launch_bounds__(kThreads) fsp_action_rows1(MatView m, Coefs cf, const double *__restrict__ x,
+template <int P, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) fsp_action_rows1(MatView m, Coefs cf, const double *__restrict__ x,
                                                              const double *__restrict__ ghost,
                                                              double *__restrict__ y, double *__restrict__ sink_out) {
   if ((int) blockIdx.x >= m.main_blocks) {
@@ -254,12 +254,67 @@ __global__ void __launch_bounds__(kThreads) fsp_action_generic(MatView m, Coefs 
   y[i] = fma(-d, xi, acc);
 }
 
+
+// Lean hot kernel: 1 row per thread, 32 registers -> 8 CTAs of 256 threads per SM (full occupancy), which matters
+// because every thread does TWO dependent memory round trips (column index, then the gathered x entry).
+// GHOST: 0 = no ghost columns exist (single GPU), 1 = ghost buffer valid, 2 = interior pass (ghost entries count 0).
+template <int P, int GHOST>
+__global__ void __launch_bounds__(kThreads, 8) fsp_action_lean(MatView m, Coefs cf, const double *__restrict__ x,
+                                                                const double *__restrict__ ghost,
+                                                                double *__restrict__ y, double *__restrict__ sink_out) {
+  if ((int) blockIdx.x >= m.main_blocks) {
+    sink_role(m, cf, x, y, sink_out);
+    return;
+  }
+  const int i = (int) blockIdx.x * kThreads + (int) threadIdx.x;
+  if (i >= m.n) return;
+  const int    *cp = m.col + i;
+  const double *op = m.off + i;
+  double acc = 0.0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int    c = ld_stream(cp + (size_t) p * m.ld);
+    const double o = ld_stream(op + (size_t) p * m.ld);
+    double xs;
+    if (GHOST == 0) xs = c >= 0 ? __ldg(x + c) : 0.0;
+    else if (GHOST == 2) xs = c >= 0 ? __ldg(x + c) : 0.0;
+    else xs = c >= 0 ? __ldg(x + c) : (c == -1 ? 0.0 : __ldg(ghost + (-(c + 2))));
+    acc = fma(cf.c[p] * o, xs, acc);
+  }
+  double d = 0.0;
+  const double *dp = m.diag + i;
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
+  y[i] = fma(-d, __ldg(x + i), acc);
+}
+
+// boundary rows of the split multi-GPU action (short list; runtime plane loop)
+__global__ void __launch_bounds__(kThreads) fsp_action_rowlist(MatView m, Coefs cf, const double *__restrict__ x,
+                                                               const double *__restrict__ ghost,
+                                                               double *__restrict__ y, double *__restrict__ sink_out) {
+  const long q = (long) blockIdx.x * kThreads + threadIdx.x;
+  if (q >= m.n) return;
+  const long   i = (long) m.row_list[q];
+  const double xi = __ldg(x + i);
+  double       d = 0.0;
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(m.diag + g * m.ld + i), d);
+  double acc = 0.0;
+  for (int p = 0; p < m.P; ++p) {
+    int c = ld_stream(m.col + p * m.ld + i);
+    acc = fma(cf.c[p] * ld_stream(m.off + p * m.ld + i), fetch_x(x, ghost, c), acc);
+  }
+  y[i] = fma(-d, xi, acc);
+}
+
 typedef void (*action_fn)(MatView, Coefs, const double *, const double *, double *, double *);
 
 template <int P>
 action_fn pick_variant(int rows_per_thread) {
   switch (rows_per_thread) {
-    case 1: return fsp_action_rows1<P>;
+    case 10: return fsp_action_lean<P, 0>;
+    case 11: return fsp_action_lean<P, 1>;
+    case 12: return fsp_action_lean<P, 2>;
+    case 1: return fsp_action_rows1<P, 1>;
+    case 3: return fsp_action_rows1<P, 8>;  // register-capped (32 regs, full occupancy, may spill for P >= 5)
     case 4: return fsp_action_rows4<P>;
     default: return fsp_action_rows2<P>;
   }
@@ -601,17 +656,29 @@ static int launch_action(fspmat_t h, const double *coef_host, const double *x, c
   m.owns_sinks = h->owns_sinks;
   m.ghost_zero = 0; m.row_list = nullptr; m.write_y_sinks = 1;
 
-  // variant 0 = default = 1 row per thread: 32 registers -> full occupancy, measured fastest on B200
-  // (465^3 lattice: 7.0 TB/s vs 6.7 TB/s for 2 rows and 5.8 TB/s for 4 rows per thread, profiles/)
-  int rows_per_thread = h->variant == 2 ? 2 : (h->variant == 4 ? 4 : 1);
-  // vector paths need 16-byte aligned x and y
-  if (((uintptr_t) x & 15u) || ((uintptr_t) y & 15u)) rows_per_thread = 1;
-  if (phase == 1) { ghost = nullptr; m.ghost_zero = 1; m.sink_blocks = 0; }
+  // Kernel selection.  variant 0 (default) = lean kernel: 1 row per thread, 32 registers, 8 CTAs/SM.  Measured on
+  // one B200 (465^3 lattice, same GPU, profiles/r01_variants.md): lean 6.77 TB/s, 2 rows/thread (64 regs) 6.15 TB/s,
+  // 1 row/thread capped at 32 regs with spills 5.59 TB/s, 4 rows/thread 5.8 TB/s.  Occupancy wins because each row
+  // needs two dependent memory round trips (column index -> gathered x).
+  // codes: 10/11/12 = lean (no ghosts / ghost buffer / interior pass), 1 = rows1, 2 = rows2, 3 = rows1 capped, 4 = rows4
+  int rows_per_thread;
+  switch (h->variant) {
+    case 1: rows_per_thread = 1; break;
+    case 2: rows_per_thread = 2; break;
+    case 3: rows_per_thread = 3; break;
+    case 4: rows_per_thread = 4; break;
+    default: rows_per_thread = h->n_ghost > 0 ? 11 : 10;
+  }
+  // the 128-bit vector paths need 16-byte aligned x and y
+  if ((rows_per_thread == 2 || rows_per_thread == 4) && (((uintptr_t) x & 15u) || ((uintptr_t) y & 15u)))
+    rows_per_thread = h->n_ghost > 0 ? 11 : 10;
+  if (phase == 1) { ghost = nullptr; m.ghost_zero = 1; m.sink_blocks = 0; if (rows_per_thread >= 10) rows_per_thread = 12; }
   if (phase == 2) { m.row_list = h->d_boundary_rows; m.n = (int) h->n_boundary; m.sink_blocks = 0; rows_per_thread = 1; }
   if (phase == 3) { m.n = 0; m.write_y_sinks = 0; rows_per_thread = 1; }
   action_fn fn = pick_kernel(h->P, rows_per_thread);
   if (!fn) { fn = fsp_action_generic; rows_per_thread = 1; }
-  long per_block = (long) kThreads * rows_per_thread;
+  if (phase == 2) fn = fsp_action_rowlist;
+  long per_block = (long) kThreads * ((rows_per_thread == 3 || rows_per_thread >= 10) ? 1 : rows_per_thread);
   m.main_blocks = (int) ((m.n + per_block - 1) / per_block);
   int grid = m.main_blocks + m.sink_blocks;
   if (grid == 0) return 0;

@@ -17,7 +17,7 @@ def _dev(torch, a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def _check(torch, O, A, R, name, times, variants=(0, 2, 4), seed=3):
+def _check(torch, O, A, R, name, times, variants=(0, 1, 2, 4), seed=3):
     M = device_matrix_from_oracle(A, R)
     rng = np.random.default_rng(seed)
     for t in times:
@@ -104,7 +104,7 @@ def test_enabled_subset_and_ragged_sizes(cuda, oracle):
         for t in (0.0, 2.0):
             ierr, yref = A.action(t, x)
             coef = 1.0 + t * np.arange(6)
-            for v in (0, 2, 4):
+            for v in (0, 1, 2, 4):
                 M.set_variant(v)
                 yd = torch.empty(A.nrows, dtype=torch.float64, device="cuda")
                 M.action(coef, _dev(torch, x), yd)
