@@ -37,7 +37,7 @@ EXAMPLES := $(patsubst examples/%.cpp,$(BUILD)/examples/%,$(wildcard examples/*.
 $(BUILD)/tests/%: tests/cpp/%.cpp tests/cpp/mini_gtest.h tests/cpp/pacmensl_test_env.h $(LIB)
 	@mkdir -p $(BUILD)/tests
 	$(CXX_HOST) -O1 -g -std=c++17 -Wall -Wno-unused-function -Iinclude -Ipacmensl_b200/host -Ipacmensl_b200/fixtures -Itests/cpp $< -o $@ -Lpacmensl_b200/lib -lpacmensl_b200 -Wl,-rpath,'$$ORIGIN/../../pacmensl_b200/lib'
-$(BUILD)/examples/%: examples/%.cpp $(LIB)
+$(BUILD)/examples/%: examples/%.cpp examples/example_common.h $(LIB)
 	@mkdir -p $(BUILD)/examples
 	$(CXX_HOST) -O2 -g -std=c++17 -Wall -Wno-unused-function -Iinclude -Ipacmensl_b200/host -Ipacmensl_b200/fixtures $< -o $@ -Lpacmensl_b200/lib -lpacmensl_b200 -Wl,-rpath,'$$ORIGIN/../../pacmensl_b200/lib'
 cpptests: $(CPP_TESTS)

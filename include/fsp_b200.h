@@ -160,6 +160,8 @@ FSP_API int fspset_check_constraints_shifted(fspset_t h, const int *nu_host, lon
  * after k into idx_out_dev (capacity `cap`); counts_host[k] = list lengths. */
 FSP_API int fspset_sink_lists(fspset_t h, const int *nu_host, long first, long count, int *idx_out_dev, long cap,
                               long *counts_host);
+/* upper bound on the number of states in [first, first+count) that can have sink entries (status != 0 after Expand) */
+FSP_API int fspset_num_boundary_states(fspset_t h, long first, long count, long *n);
 FSP_API int fspset_states_dev(fspset_t h, const int **states_dev); /* borrowed, valid until next mutation */
 FSP_API int fspset_copy_states(fspset_t h, long first, long count, int *out_host);
 FSP_API int fspset_copy_status(fspset_t h, long first, long count, signed char *out_host);

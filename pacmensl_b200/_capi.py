@@ -92,6 +92,7 @@ SIGNATURES = {
     "fspset_lookup_shifted": (ci, [vp, ip, ci, cl, cl, vp]),
     "fspset_check_constraints_shifted": (ci, [vp, ip, cl, cl, vp]),
     "fspset_sink_lists": (ci, [vp, ip, cl, cl, vp, cl, lp]),
+    "fspset_num_boundary_states": (ci, [vp, cl, cl, lp]),
     "fspset_states_dev": (ci, [vp, vpp]),
     "fspset_copy_states": (ci, [vp, cl, cl, ip]),
     "fspset_copy_status": (ci, [vp, cl, cl, C.POINTER(C.c_byte)]),

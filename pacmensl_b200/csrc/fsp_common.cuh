@@ -9,6 +9,13 @@
 namespace fspb {
 
 void        set_error(const char *fmt, ...);
+// Stream-ordered pooled allocation (cudaMallocAsync on the legacy stream with an unbounded release threshold): the
+// set-up paths allocate many short-lived temporaries and plain cudaMalloc/cudaFree synchronise the device each time.
+cudaError_t pool_malloc_bytes(void **p, size_t bytes);
+cudaError_t pool_free(void *p);
+template <typename T>
+inline cudaError_t pmalloc(T **p, size_t bytes) { return pool_malloc_bytes(reinterpret_cast<void **>(p), bytes); }
+inline cudaError_t pfree(void *p) { return pool_free(p); }
 cudaStream_t resolve_stream(void *stream);
 void        count_launch(int n = 1);
 int         sm_count();

@@ -30,6 +30,25 @@ int sm_count() {
   }
   return cached;
 }
+static void pool_init_once() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_dev = dev;
+}
+cudaError_t pool_malloc_bytes(void **p, size_t bytes) {
+  pool_init_once();
+  return cudaMallocAsync(p, bytes ? bytes : 8, (cudaStream_t) 0);
+}
+cudaError_t pool_free(void *p) {
+  if (!p) return cudaSuccess;
+  return cudaFreeAsync(p, (cudaStream_t) 0);
+}
 }  // namespace fspb
 
 using namespace fspb;
@@ -41,8 +60,8 @@ int fsp_device_set(int device) { FSP_CUDA_CHECK(cudaSetDevice(device)); return 0
 int fsp_device_get(int *device) { FSP_CUDA_CHECK(cudaGetDevice(device)); return 0; }
 int fsp_device_sm_count(int *count) { *count = sm_count(); return 0; }
 const char *fsp_last_error(void) { return g_err; }
-int fsp_malloc(void **p, size_t bytes) { FSP_CUDA_CHECK(cudaMalloc(p, bytes ? bytes : 8)); return 0; }
-int fsp_free(void *p) { if (p) FSP_CUDA_CHECK(cudaFree(p)); return 0; }
+int fsp_malloc(void **p, size_t bytes) { FSP_CUDA_CHECK(pool_malloc_bytes(p, bytes)); return 0; }
+int fsp_free(void *p) { if (p) FSP_CUDA_CHECK(pool_free(p)); return 0; }
 int fsp_malloc_host(void **p, size_t bytes) { FSP_CUDA_CHECK(cudaMallocHost(p, bytes ? bytes : 8)); return 0; }
 int fsp_free_host(void *p) { if (p) FSP_CUDA_CHECK(cudaFreeHost(p)); return 0; }
 int fsp_memcpy_h2d(void *d, const void *s, size_t b, void *st) {

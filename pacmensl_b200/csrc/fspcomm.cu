@@ -168,8 +168,8 @@ int fspcomm_alltoall_counts(fspcomm_t c, const long *send_host, long *recv_host,
   const int    P = c->size;
   cudaStream_t st = resolve_stream(stream);
   double      *d_send = nullptr, *d_all = nullptr;
-  FSP_CUDA_CHECK(cudaMalloc(&d_send, sizeof(double) * P));
-  FSP_CUDA_CHECK(cudaMalloc(&d_all, sizeof(double) * P * P));
+  FSP_CUDA_CHECK(pmalloc(&d_send, sizeof(double) * P));
+  FSP_CUDA_CHECK(pmalloc(&d_all, sizeof(double) * P * P));
   double hs[256], hall[256 * 8];
   if (P > 256 || P * P > 2048) { set_error("fspcomm_alltoall_counts: too many ranks"); return -1; }
   for (int p = 0; p < P; ++p) hs[p] = (double) send_host[p];
@@ -178,7 +178,7 @@ int fspcomm_alltoall_counts(fspcomm_t c, const long *send_host, long *recv_host,
   FSP_CUDA_CHECK(cudaMemcpyAsync(hall, d_all, sizeof(double) * P * P, cudaMemcpyDeviceToHost, st));
   FSP_CUDA_CHECK(cudaStreamSynchronize(st));
   for (int p = 0; p < P; ++p) recv_host[p] = (long) hall[p * P + c->rank];
-  cudaFree(d_send); cudaFree(d_all);
+  pfree(d_send); pfree(d_all);
   return 0;
 }
 

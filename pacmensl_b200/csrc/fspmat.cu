@@ -450,10 +450,10 @@ struct fspmat_s {
 };
 
 static int free_values(fspmat_s *h) {
-  cudaFree(h->d_col); cudaFree(h->d_off); cudaFree(h->d_diag);
-  cudaFree(h->d_sink_idx); cudaFree(h->d_sink_val);
-  cudaFree(h->d_sb_seg); cudaFree(h->d_sb_begin); cudaFree(h->d_sb_end);
-  cudaFree(h->d_sink_partials); cudaFree(h->d_sink_counter); cudaFree(h->d_boundary_rows);
+  pfree(h->d_col); pfree(h->d_off); pfree(h->d_diag);
+  pfree(h->d_sink_idx); pfree(h->d_sink_val);
+  pfree(h->d_sb_seg); pfree(h->d_sb_begin); pfree(h->d_sb_end);
+  pfree(h->d_sink_partials); pfree(h->d_sink_counter); pfree(h->d_boundary_rows);
   int variant = h->variant;
   *h = fspmat_s();
   h->variant = variant;
@@ -498,17 +498,17 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
   cudaStream_t st = 0;
 
   if (P > 0) {
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_col, sizeof(int) * P * ld));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_off, sizeof(double) * P * ld));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_diag, sizeof(double) * std::max(h->ND, 1) * ld));
+    FSP_CUDA_CHECK(pmalloc(&h->d_col, sizeof(int) * P * ld));
+    FSP_CUDA_CHECK(pmalloc(&h->d_off, sizeof(double) * P * ld));
+    FSP_CUDA_CHECK(pmalloc(&h->d_diag, sizeof(double) * std::max(h->ND, 1) * ld));
     const int *col_in = d->col; const double *off_in = d->off, *diag_in = d->diag;
     int *t_col = nullptr; double *t_off = nullptr, *t_diag = nullptr;
     long ld_in = d->ld;
     if (!d->arrays_on_device) {
       // stage through the device with a dense leading dimension
-      FSP_CUDA_CHECK(cudaMalloc(&t_col, sizeof(int) * P * std::max(n, 1L)));
-      FSP_CUDA_CHECK(cudaMalloc(&t_off, sizeof(double) * P * std::max(n, 1L)));
-      FSP_CUDA_CHECK(cudaMalloc(&t_diag, sizeof(double) * P * std::max(n, 1L)));
+      FSP_CUDA_CHECK(pmalloc(&t_col, sizeof(int) * P * std::max(n, 1L)));
+      FSP_CUDA_CHECK(pmalloc(&t_off, sizeof(double) * P * std::max(n, 1L)));
+      FSP_CUDA_CHECK(pmalloc(&t_diag, sizeof(double) * P * std::max(n, 1L)));
       if (n > 0) {
         FSP_CUDA_CHECK(cudaMemcpy2D(t_col, sizeof(int) * n, d->col, sizeof(int) * d->ld, sizeof(int) * n, P, cudaMemcpyHostToDevice));
         FSP_CUDA_CHECK(cudaMemcpy2D(t_off, sizeof(double) * n, d->off, sizeof(double) * d->ld, sizeof(double) * n, P, cudaMemcpyHostToDevice));
@@ -522,7 +522,7 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
     pack_diag_kernel<<<(unsigned) ((ld + 255) / 256), 256, 0, st>>>((int) n, h->n_tv, h->n_ti, ld_in, ld, diag_in, h->d_diag);
     FSP_LAUNCH_CHECK();
     FSP_CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFree(t_col); cudaFree(t_off); cudaFree(t_diag);
+    pfree(t_col); pfree(t_off); pfree(t_diag);
   }
 
   // ---- multi-GPU: list of rows that reference ghost entries (redone after the halo exchange) ----------
@@ -530,30 +530,30 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
     int   *d_num = nullptr;
     void  *d_tmp = nullptr;
     size_t need = 0;
-    FSP_CUDA_CHECK(cudaMalloc(&d_num, sizeof(int)));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_boundary_rows, sizeof(int) * n));
+    FSP_CUDA_CHECK(pmalloc(&d_num, sizeof(int)));
+    FSP_CUDA_CHECK(pmalloc(&h->d_boundary_rows, sizeof(int) * n));
     cub::CountingInputIterator<int> iota(0);
     RowHasGhost pred{h->d_col, ld, P};
     cub::DeviceSelect::If(nullptr, need, iota, h->d_boundary_rows, d_num, (int) n, pred);
-    FSP_CUDA_CHECK(cudaMalloc(&d_tmp, need));
+    FSP_CUDA_CHECK(pmalloc(&d_tmp, need));
     FSP_CUDA_CHECK(cub::DeviceSelect::If(d_tmp, need, iota, h->d_boundary_rows, d_num, (int) n, pred));
     count_launch();
     int nb = 0;
     FSP_CUDA_CHECK(cudaMemcpy(&nb, d_num, sizeof(int), cudaMemcpyDeviceToHost));
     h->n_boundary = nb;
-    cudaFree(d_num); cudaFree(d_tmp);
+    pfree(d_num); pfree(d_tmp);
   }
 
   // ---- flops: 2 nnz per matrix (+ rows per TV axpy); FspMatrixBase.cpp:429-444 -------------------
   std::vector<unsigned long long> counts(h->n_tv + 1, 0ull);
   if (P > 0 && n > 0) {
     unsigned long long *d_counts;
-    FSP_CUDA_CHECK(cudaMalloc(&d_counts, sizeof(unsigned long long) * (h->n_tv + 1)));
+    FSP_CUDA_CHECK(pmalloc(&d_counts, sizeof(unsigned long long) * (h->n_tv + 1)));
     FSP_CUDA_CHECK(cudaMemset(d_counts, 0, sizeof(unsigned long long) * (h->n_tv + 1)));
     count_nnz_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>((int) n, h->n_tv, h->n_ti, ld, h->d_col, d_counts);
     FSP_LAUNCH_CHECK();
     FSP_CUDA_CHECK(cudaMemcpy(counts.data(), d_counts, sizeof(unsigned long long) * (h->n_tv + 1), cudaMemcpyDeviceToHost));
-    cudaFree(d_counts);
+    pfree(d_counts);
   }
   long flops = 0;
   if (h->n_ti > 0) flops += 2 * ((long) counts[h->n_tv] + n);
@@ -613,13 +613,13 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
     }
     if (sb_seg.empty()) { sb_seg.push_back(-1); sb_b.push_back(0); sb_e.push_back(0); }
     h->sink_blocks = (int) sb_seg.size();
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_sink_idx, sizeof(int) * std::max(total_sink, 1L)));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_sink_val, sizeof(double) * std::max(total_sink, 1L)));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_sb_seg, sizeof(int) * h->sink_blocks));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_sb_begin, sizeof(long) * h->sink_blocks));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_sb_end, sizeof(long) * h->sink_blocks));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_sink_partials, sizeof(double) * h->sink_blocks));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_sink_counter, sizeof(unsigned)));
+    FSP_CUDA_CHECK(pmalloc(&h->d_sink_idx, sizeof(int) * std::max(total_sink, 1L)));
+    FSP_CUDA_CHECK(pmalloc(&h->d_sink_val, sizeof(double) * std::max(total_sink, 1L)));
+    FSP_CUDA_CHECK(pmalloc(&h->d_sb_seg, sizeof(int) * h->sink_blocks));
+    FSP_CUDA_CHECK(pmalloc(&h->d_sb_begin, sizeof(long) * h->sink_blocks));
+    FSP_CUDA_CHECK(pmalloc(&h->d_sb_end, sizeof(long) * h->sink_blocks));
+    FSP_CUDA_CHECK(pmalloc(&h->d_sink_partials, sizeof(double) * h->sink_blocks));
+    FSP_CUDA_CHECK(pmalloc(&h->d_sink_counter, sizeof(unsigned)));
     FSP_CUDA_CHECK(cudaMemset(h->d_sink_counter, 0, sizeof(unsigned)));
     if (total_sink > 0) {
       FSP_CUDA_CHECK(cudaMemcpy(h->d_sink_idx, idx.data(), sizeof(int) * total_sink, cudaMemcpyHostToDevice));
@@ -707,25 +707,25 @@ int fspmat_build_ghosts(int *col, long n, int lo, int hi, int **ghost_out, long 
   int *d_sel = nullptr, *d_sorted = nullptr, *d_uniq = nullptr, *d_num = nullptr;
   void *d_tmp = nullptr;
   size_t need = 0, cap = 0;
-  FSP_CUDA_CHECK(cudaMalloc(&d_num, sizeof(int)));
-  FSP_CUDA_CHECK(cudaMalloc(&d_sel, sizeof(int) * n));
+  FSP_CUDA_CHECK(pmalloc(&d_num, sizeof(int)));
+  FSP_CUDA_CHECK(pmalloc(&d_sel, sizeof(int) * n));
   OutOfRange pred{lo, hi};
   cub::DeviceSelect::If(nullptr, need, col, d_sel, d_num, (int) n, pred);
-  FSP_CUDA_CHECK(cudaMalloc(&d_tmp, need)); cap = need;
+  FSP_CUDA_CHECK(pmalloc(&d_tmp, need)); cap = need;
   FSP_CUDA_CHECK(cub::DeviceSelect::If(d_tmp, need, col, d_sel, d_num, (int) n, pred));
   count_launch();
   int n_sel = 0;
   FSP_CUDA_CHECK(cudaMemcpy(&n_sel, d_num, sizeof(int), cudaMemcpyDeviceToHost));
   int n_u = 0;
   if (n_sel > 0) {
-    FSP_CUDA_CHECK(cudaMalloc(&d_sorted, sizeof(int) * n_sel));
-    FSP_CUDA_CHECK(cudaMalloc(&d_uniq, sizeof(int) * n_sel));
+    FSP_CUDA_CHECK(pmalloc(&d_sorted, sizeof(int) * n_sel));
+    FSP_CUDA_CHECK(pmalloc(&d_uniq, sizeof(int) * n_sel));
     cub::DeviceRadixSort::SortKeys(nullptr, need, d_sel, d_sorted, n_sel);
-    if (need > cap) { cudaFree(d_tmp); FSP_CUDA_CHECK(cudaMalloc(&d_tmp, need)); cap = need; }
+    if (need > cap) { pfree(d_tmp); FSP_CUDA_CHECK(pmalloc(&d_tmp, need)); cap = need; }
     FSP_CUDA_CHECK(cub::DeviceRadixSort::SortKeys(d_tmp, need, d_sel, d_sorted, n_sel));
     count_launch();
     cub::DeviceSelect::Unique(nullptr, need, d_sorted, d_uniq, d_num, n_sel);
-    if (need > cap) { cudaFree(d_tmp); FSP_CUDA_CHECK(cudaMalloc(&d_tmp, need)); cap = need; }
+    if (need > cap) { pfree(d_tmp); FSP_CUDA_CHECK(pmalloc(&d_tmp, need)); cap = need; }
     FSP_CUDA_CHECK(cub::DeviceSelect::Unique(d_tmp, need, d_sorted, d_uniq, d_num, n_sel));
     count_launch();
     FSP_CUDA_CHECK(cudaMemcpy(&n_u, d_num, sizeof(int), cudaMemcpyDeviceToHost));
@@ -733,7 +733,7 @@ int fspmat_build_ghosts(int *col, long n, int lo, int hi, int **ghost_out, long 
   remap_cols_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(col, n, lo, hi, d_uniq, n_u);
   FSP_LAUNCH_CHECK();
   FSP_CUDA_CHECK(cudaDeviceSynchronize());
-  cudaFree(d_sel); cudaFree(d_sorted); cudaFree(d_tmp); cudaFree(d_num);
+  pfree(d_sel); pfree(d_sorted); pfree(d_tmp); pfree(d_num);
   *ghost_out = d_uniq;
   *n_ghost = n_u;
   return 0;

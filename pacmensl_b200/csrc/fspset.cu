@@ -249,6 +249,33 @@ __global__ void mass_action_kernel(const int *states, long first, long count, in
 }
 
 
+struct StatusNonZero {
+  const signed char *status; int use;
+  __host__ __device__ bool operator()(const int &i) const { return !use || status[i] != 0; }
+};
+__global__ void status_nonzero_flag_kernel(const signed char *status, long n, int *flag) {
+  long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = status[i] != 0 ? 1 : 0;
+}
+__global__ void check_list_default_kernel(const int *states, long first, const int *list, long m, int S, int K,
+                                          SmallVec nu, Bounds bd, int *satisfied) {
+  long j = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const long i = first + list[j];
+  int  key[kMaxS];
+  bool neg = false;
+  for (int s = 0; s < S; ++s) {
+    key[s] = states[(size_t) i * S + s] + nu.v[s];
+    neg |= key[s] < 0;
+  }
+  for (int k = 0; k < K; ++k) satisfied[(size_t) k * m + j] = (neg || key[k] <= bd.b[k]) ? 1 : 0;
+}
+__global__ void shift_list_kernel(const int *states, long first, const int *list, long m, int S, SmallVec nu, int *out) {
+  long j = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const long i = first + list[j];
+  for (int s = 0; s < S; ++s) out[(size_t) j * S + s] = states[(size_t) i * S + s] + nu.v[s];
+}
 struct NotFlag {
   const int *sat;
   __host__ __device__ int operator()(int i) const { return sat[i] == 0 ? 1 : 0; }
@@ -275,6 +302,8 @@ struct fspset_s {
   int         *d_flag = nullptr, *d_pos = nullptr; long flag_cap = 0;
   unsigned long long *d_slot = nullptr;
   void        *d_cub = nullptr;        size_t cub_bytes = 0;
+  bool             expanded = false;   // Expand() has run: status 0 <=> all children inside the set
+  std::vector<int> expanded_bounds;    // bounds at the last Expand()
 };
 
 namespace {
@@ -283,8 +312,8 @@ int ensure_table(fspset_s *h, long need) {
   unsigned long long want = h->tsize ? h->tsize : 1024;
   while ((unsigned long long) need * 2 > want) want *= 2;
   if (want == h->tsize) return 0;
-  cudaFree(h->d_table);
-  FSP_CUDA_CHECK(cudaMalloc(&h->d_table, sizeof(unsigned) * want));
+  pfree(h->d_table);
+  FSP_CUDA_CHECK(pmalloc(&h->d_table, sizeof(unsigned) * want));
   FSP_CUDA_CHECK(cudaMemset(h->d_table, 0xFF, sizeof(unsigned) * want));
   h->tsize = want;
   if (h->n > 0) {
@@ -300,24 +329,24 @@ int ensure_states(fspset_s *h, long need) {
   while (cap < need) cap = cap + cap / 2 + 1024;
   int         *ns;
   signed char *nst;
-  FSP_CUDA_CHECK(cudaMalloc(&ns, sizeof(int) * cap * h->S));
-  FSP_CUDA_CHECK(cudaMalloc(&nst, cap));
+  FSP_CUDA_CHECK(pmalloc(&ns, sizeof(int) * cap * h->S));
+  FSP_CUDA_CHECK(pmalloc(&nst, cap));
   if (h->n > 0) {
     FSP_CUDA_CHECK(cudaMemcpy(ns, h->d_states, sizeof(int) * h->n * h->S, cudaMemcpyDeviceToDevice));
     FSP_CUDA_CHECK(cudaMemcpy(nst, h->d_status, h->n, cudaMemcpyDeviceToDevice));
   }
-  cudaFree(h->d_states); cudaFree(h->d_status);
+  pfree(h->d_states); pfree(h->d_status);
   h->d_states = ns; h->d_status = nst; h->cap = cap;
   return 0;
 }
 
 int ensure_cand(fspset_s *h, long m) {
   if (m > h->cand_cap) {
-    cudaFree(h->d_cand); cudaFree(h->d_valid); cudaFree(h->d_slot);
+    pfree(h->d_cand); pfree(h->d_valid); pfree(h->d_slot);
     long cap = std::max(m, 4096L);
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_cand, sizeof(int) * cap * h->S));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_valid, cap));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_slot, sizeof(unsigned long long) * cap));
+    FSP_CUDA_CHECK(pmalloc(&h->d_cand, sizeof(int) * cap * h->S));
+    FSP_CUDA_CHECK(pmalloc(&h->d_valid, cap));
+    FSP_CUDA_CHECK(pmalloc(&h->d_slot, sizeof(unsigned long long) * cap));
     h->cand_cap = cap;
   }
   return 0;
@@ -325,10 +354,10 @@ int ensure_cand(fspset_s *h, long m) {
 
 int ensure_flags(fspset_s *h, long m) {
   if (m > h->flag_cap) {
-    cudaFree(h->d_flag); cudaFree(h->d_pos);
+    pfree(h->d_flag); pfree(h->d_pos);
     long cap = std::max(m, 4096L);
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_flag, sizeof(int) * cap));
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_pos, sizeof(int) * cap));
+    FSP_CUDA_CHECK(pmalloc(&h->d_flag, sizeof(int) * cap));
+    FSP_CUDA_CHECK(pmalloc(&h->d_pos, sizeof(int) * cap));
     h->flag_cap = cap;
   }
   return 0;
@@ -339,8 +368,8 @@ int scan_flags(fspset_s *h, long m, long *total) {
   size_t need = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, need, h->d_flag, h->d_pos, (int) m);
   if (need > h->cub_bytes) {
-    cudaFree(h->d_cub);
-    FSP_CUDA_CHECK(cudaMalloc(&h->d_cub, need));
+    pfree(h->d_cub);
+    FSP_CUDA_CHECK(pmalloc(&h->d_cub, need));
     h->cub_bytes = need;
   }
   FSP_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(h->d_cub, need, h->d_flag, h->d_pos, (int) m));
@@ -423,8 +452,8 @@ int fspset_create(fspset_t *out, int S, int R, const int *SM) {
 
 int fspset_destroy(fspset_t h) {
   if (!h) return 0;
-  cudaFree(h->d_states); cudaFree(h->d_status); cudaFree(h->d_table); cudaFree(h->d_cand); cudaFree(h->d_valid);
-  cudaFree(h->d_flag); cudaFree(h->d_pos); cudaFree(h->d_slot); cudaFree(h->d_cub);
+  pfree(h->d_states); pfree(h->d_status); pfree(h->d_table); pfree(h->d_cand); pfree(h->d_valid);
+  pfree(h->d_flag); pfree(h->d_pos); pfree(h->d_slot); pfree(h->d_cub);
   delete h;
   return 0;
 }
@@ -500,10 +529,10 @@ int fspset_expand(fspset_t h) {
     if (scan_flags(h, n, &nF)) { rc = -1; break; }
     if (nF == 0) break;
     if (nF > fcap) {
-      cudaFree(d_frontier); cudaFree(d_fstatus);
+      pfree(d_frontier); pfree(d_fstatus);
       fcap = nF + nF / 2;
-      FSP_CUDA_CHECK(cudaMalloc(&d_frontier, sizeof(int) * fcap));
-      FSP_CUDA_CHECK(cudaMalloc(&d_fstatus, fcap));
+      FSP_CUDA_CHECK(pmalloc(&d_frontier, sizeof(int) * fcap));
+      FSP_CUDA_CHECK(pmalloc(&d_fstatus, fcap));
     }
     frontier_fill_kernel<<<blocks_for(n), 256>>>(h->d_flag, h->d_pos, n, d_frontier);
     FSP_LAUNCH_CHECK();
@@ -530,7 +559,8 @@ int fspset_expand(fspset_t h) {
     set_frontier_status_kernel<<<blocks_for(nF), 256>>>(h->d_status, d_frontier, d_fstatus, nF);  // :198
     FSP_LAUNCH_CHECK();
   }
-  cudaFree(d_frontier); cudaFree(d_fstatus);
+  pfree(d_frontier); pfree(d_fstatus);
+  if (rc == 0) { h->expanded = true; h->expanded_bounds = h->bounds; }
   return rc;
 }
 
@@ -541,12 +571,12 @@ int fspset_state2index(fspset_t h, long m, const int *X, int x_on_device, int *i
   const int *dX = X;
   int       *tX = nullptr, *dI = idx, *tI = nullptr;
   if (!x_on_device) {
-    FSP_CUDA_CHECK(cudaMalloc(&tX, sizeof(int) * m * h->S));
+    FSP_CUDA_CHECK(pmalloc(&tX, sizeof(int) * m * h->S));
     FSP_CUDA_CHECK(cudaMemcpy(tX, X, sizeof(int) * m * h->S, cudaMemcpyHostToDevice));
     dX = tX;
   }
   if (!idx_on_device) {
-    FSP_CUDA_CHECK(cudaMalloc(&tI, sizeof(int) * m));
+    FSP_CUDA_CHECK(pmalloc(&tI, sizeof(int) * m));
     dI = tI;
   }
   if (h->n == 0 || !h->d_table) {
@@ -556,7 +586,7 @@ int fspset_state2index(fspset_t h, long m, const int *X, int x_on_device, int *i
     FSP_LAUNCH_CHECK();
   }
   if (!idx_on_device) FSP_CUDA_CHECK(cudaMemcpy(idx, dI, sizeof(int) * m, cudaMemcpyDeviceToHost));
-  cudaFree(tX); cudaFree(tI);
+  pfree(tX); pfree(tI);
   return 0;
 }
 
@@ -583,11 +613,11 @@ int fspset_check_constraints_shifted(fspset_t h, const int *nu_host, long first,
   // custom lhs: evaluate on the host (API contract: user std::function), StateSetConstrained.cpp:63-82
   std::vector<int> X((size_t) count * h->S), fval((size_t) count * h->K), sat((size_t) count * h->K);
   int             *d_tmp;
-  FSP_CUDA_CHECK(cudaMalloc(&d_tmp, sizeof(int) * count * h->S));
+  FSP_CUDA_CHECK(pmalloc(&d_tmp, sizeof(int) * count * h->S));
   shift_states_kernel<<<blocks_for(count), 256>>>(h->d_states, first, count, h->S, nu, 1, d_tmp);
   FSP_LAUNCH_CHECK();
   FSP_CUDA_CHECK(cudaMemcpy(X.data(), d_tmp, sizeof(int) * count * h->S, cudaMemcpyDeviceToHost));
-  cudaFree(d_tmp);
+  pfree(d_tmp);
   int ierr = h->lhs(h->S, h->K, (int) count, X.data(), fval.data(), h->lhs_args);
   if (ierr) { set_error("fspset: constraint callback returned %d", ierr); return ierr; }
   for (int k = 0; k < h->K; ++k)
@@ -630,46 +660,98 @@ int fspset_eval_mass_action(fspset_t h, double rate, const int *order_host, cons
 // Sink column lists (FspMatrixConstrained.cpp:170-194): for each constraint k the ascending local indices
 // i - first of stored states whose destination state_i + nu violates constraint k.  Lists are written
 // k after k into idx_out_dev (capacity cap entries); counts_host[k] receives their lengths.
+// Only states whose status is not 0 can contribute: status 0 means every child of the state is inside the set
+// (StateSetConstrained.cpp:184-198), hence satisfies all constraints -- so the constraint evaluation (a HOST callback
+// for custom shapes) runs on the O(surface) subset only.  That shortcut needs the bounds to be no smaller than at
+// the last Expand(); otherwise all states are examined.
 int fspset_sink_lists(fspset_t h, const int *nu_host, long first, long count, int *idx_out_dev, long cap,
                       long *counts_host) {
   for (int k = 0; k < h->K; ++k) counts_host[k] = 0;
   if (count <= 0) return 0;
-  int *d_sat = nullptr;
-  FSP_CUDA_CHECK(cudaMalloc(&d_sat, sizeof(int) * count * h->K));
-  if (fspset_check_constraints_shifted(h, nu_host, first, count, d_sat)) { cudaFree(d_sat); return -1; }
-  int *d_num = nullptr;
-  FSP_CUDA_CHECK(cudaMalloc(&d_num, sizeof(int)));
-  long written = 0;
-  int  rc = 0;
-  for (int k = 0; k < h->K && !rc; ++k) {
-    // select indices with satisfied == 0
+  SmallVec nu;
+  for (int s = 0; s < kMaxS; ++s) nu.v[s] = s < h->S ? nu_host[s] : 0;
+  bool use_status = h->expanded && (int) h->expanded_bounds.size() == h->K;
+  for (int k = 0; k < h->K && use_status; ++k) use_status = h->bounds[k] >= h->expanded_bounds[k];
+  // candidate list (ascending positions relative to `first`)
+  int *d_cand = nullptr, *d_num = nullptr;
+  FSP_CUDA_CHECK(pmalloc(&d_cand, sizeof(int) * count));
+  FSP_CUDA_CHECK(pmalloc(&d_num, sizeof(int)));
+  long m = count;
+  {
     cub::CountingInputIterator<int> iota(0);
-    NotFlag                         flags{d_sat + (size_t) k * count};
-    cub::TransformInputIterator<int, NotFlag, cub::CountingInputIterator<int>> fl(iota, flags);
+    StatusNonZero pred{h->d_status + first, use_status ? 1 : 0};
     size_t need = 0;
-    int   *d_out = nullptr;
-    // worst case output = count entries: select into a scratch then copy what fits
-    if (cudaMalloc(&d_out, sizeof(int) * count) != cudaSuccess) { set_error("fspset_sink_lists: out of memory"); rc = -1; break; }
-    cub::DeviceSelect::Flagged(nullptr, need, iota, fl, d_out, d_num, (int) count);
-    if (need > h->cub_bytes) {
-      cudaFree(h->d_cub);
-      if (cudaMalloc(&h->d_cub, need) != cudaSuccess) { set_error("fspset_sink_lists: out of memory"); cudaFree(d_out); rc = -1; break; }
-      h->cub_bytes = need;
-    }
-    if (cub::DeviceSelect::Flagged(h->d_cub, need, iota, fl, d_out, d_num, (int) count) != cudaSuccess) {
-      set_error("fspset_sink_lists: select failed"); cudaFree(d_out); rc = -1; break;
-    }
+    cub::DeviceSelect::If(nullptr, need, iota, d_cand, d_num, (int) count, pred);
+    if (need > h->cub_bytes) { pfree(h->d_cub); FSP_CUDA_CHECK(pmalloc(&h->d_cub, need)); h->cub_bytes = need; }
+    FSP_CUDA_CHECK(cub::DeviceSelect::If(h->d_cub, need, iota, d_cand, d_num, (int) count, pred));
     count_launch();
     int num = 0;
-    cudaMemcpy(&num, d_num, sizeof(int), cudaMemcpyDeviceToHost);
-    if (written + num > cap) { set_error("fspset_sink_lists: capacity %ld too small", cap); cudaFree(d_out); rc = -1; break; }
-    if (num > 0) cudaMemcpy(idx_out_dev + written, d_out, sizeof(int) * num, cudaMemcpyDeviceToDevice);
-    cudaFree(d_out);
-    counts_host[k] = num;
-    written += num;
+    FSP_CUDA_CHECK(cudaMemcpy(&num, d_num, sizeof(int), cudaMemcpyDeviceToHost));
+    m = num;
   }
-  cudaFree(d_sat); cudaFree(d_num);
+  int rc = 0;
+  if (m > 0) {
+    int *d_sat = nullptr, *d_out = nullptr;
+    FSP_CUDA_CHECK(pmalloc(&d_sat, sizeof(int) * m * h->K));
+    FSP_CUDA_CHECK(pmalloc(&d_out, sizeof(int) * m));
+    if (!h->lhs) {
+      check_list_default_kernel<<<blocks_for(m), 256>>>(h->d_states, first, d_cand, m, h->S, h->K, nu, bounds_of(h), d_sat);
+      FSP_LAUNCH_CHECK();
+    } else {
+      // custom lhs: the user's host callback on the candidate destinations only
+      int *d_tmp = nullptr;
+      FSP_CUDA_CHECK(pmalloc(&d_tmp, sizeof(int) * m * h->S));
+      shift_list_kernel<<<blocks_for(m), 256>>>(h->d_states, first, d_cand, m, h->S, nu, d_tmp);
+      FSP_LAUNCH_CHECK();
+      std::vector<int> X((size_t) m * h->S), fval((size_t) m * h->K), sat((size_t) m * h->K);
+      FSP_CUDA_CHECK(cudaMemcpy(X.data(), d_tmp, sizeof(int) * m * h->S, cudaMemcpyDeviceToHost));
+      pfree(d_tmp);
+      int ierr = h->lhs(h->S, h->K, (int) m, X.data(), fval.data(), h->lhs_args);
+      if (ierr) { set_error("fspset: constraint callback returned %d", ierr); pfree(d_sat); pfree(d_out); pfree(d_cand); pfree(d_num); return ierr; }
+      for (int k = 0; k < h->K; ++k)
+        for (long i = 0; i < m; ++i) {
+          int ok = fval[(size_t) h->K * i + k] <= h->bounds[k] ? 1 : 0;
+          for (int s = 0; s < h->S; ++s)
+            if (X[(size_t) h->S * i + s] < 0) ok = 1;
+          sat[(size_t) k * m + i] = ok;
+        }
+      FSP_CUDA_CHECK(cudaMemcpy(d_sat, sat.data(), sizeof(int) * m * h->K, cudaMemcpyHostToDevice));
+    }
+    long written = 0;
+    for (int k = 0; k < h->K && !rc; ++k) {
+      NotFlag flags{d_sat + (size_t) k * m};
+      cub::TransformInputIterator<int, NotFlag, cub::CountingInputIterator<int>> fl(cub::CountingInputIterator<int>(0), flags);
+      size_t need = 0;
+      cub::DeviceSelect::Flagged(nullptr, need, d_cand, fl, d_out, d_num, (int) m);
+      if (need > h->cub_bytes) { pfree(h->d_cub); if (pmalloc(&h->d_cub, need) != cudaSuccess) { rc = -1; break; } h->cub_bytes = need; }
+      if (cub::DeviceSelect::Flagged(h->d_cub, need, d_cand, fl, d_out, d_num, (int) m) != cudaSuccess) {
+        set_error("fspset_sink_lists: select failed"); rc = -1; break;
+      }
+      count_launch();
+      int num = 0;
+      cudaMemcpy(&num, d_num, sizeof(int), cudaMemcpyDeviceToHost);
+      if (written + num > cap) { set_error("fspset_sink_lists: capacity %ld too small", cap); rc = -1; break; }
+      if (num > 0) cudaMemcpyAsync(idx_out_dev + written, d_out, sizeof(int) * num, cudaMemcpyDeviceToDevice, 0);
+      counts_host[k] = num;
+      written += num;
+    }
+    pfree(d_sat); pfree(d_out);
+  }
+  pfree(d_cand); pfree(d_num);
   return rc;
+}
+
+/* number of stored states in [first, first+count) that can contribute sink entries (status != 0) */
+int fspset_num_boundary_states(fspset_t h, long first, long count, long *n) {
+  *n = count;
+  if (count <= 0 || !h->expanded) return 0;
+  if (ensure_flags(h, count)) return -1;
+  status_nonzero_flag_kernel<<<blocks_for(count), 256>>>(h->d_status + first, count, h->d_flag);
+  FSP_LAUNCH_CHECK();
+  long tot = 0;
+  if (scan_flags(h, count, &tot)) return -1;
+  *n = tot;
+  return 0;
 }
 
 }  // extern "C"

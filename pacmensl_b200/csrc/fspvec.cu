@@ -29,8 +29,8 @@ int get_scratch(double **partials, unsigned **counter) {
   FSP_CUDA_CHECK(cudaGetDevice(&dev));
   RedScratch &s = g_scratch[dev & 15];
   if (!s.partials) {
-    FSP_CUDA_CHECK(cudaMalloc(&s.partials, sizeof(double) * kSlots * kMaxRed * kMaxBlocks));
-    FSP_CUDA_CHECK(cudaMalloc(&s.counters, sizeof(unsigned) * kSlots));
+    FSP_CUDA_CHECK(pmalloc(&s.partials, sizeof(double) * kSlots * kMaxRed * kMaxBlocks));
+    FSP_CUDA_CHECK(pmalloc(&s.counters, sizeof(unsigned) * kSlots));
     FSP_CUDA_CHECK(cudaMemset(s.counters, 0, sizeof(unsigned) * kSlots));
     s.device = dev;
   }
@@ -337,7 +337,7 @@ thread_local double *g_tmp[16] = {nullptr};
 int tmp_scalar(double **p) {
   int dev = 0;
   FSP_CUDA_CHECK(cudaGetDevice(&dev));
-  if (!g_tmp[dev & 15]) FSP_CUDA_CHECK(cudaMalloc(&g_tmp[dev & 15], sizeof(double) * 16));
+  if (!g_tmp[dev & 15]) FSP_CUDA_CHECK(pmalloc(&g_tmp[dev & 15], sizeof(double) * 16));
   *p = g_tmp[dev & 15];
   return 0;
 }

@@ -51,6 +51,7 @@ int FspMatrixBase::Destroy() {
   enable_reactions_.clear();
   tv_reactions_.clear();
   ti_reactions_.clear();
+  if (comm_stream_) fsp_stream_sync(comm_stream_);  // side-stream kernels may still read the halo buffers
   if (dmat_) fspmat_clear(dmat_);
   ghost_buf_.release();
   send_buf_.release();
@@ -137,27 +138,68 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
   std::vector<int>    shifted;
   std::vector<double> vals;
   const bool          on_device = (bool) mass_action_;
-  const arma::Mat<int> *states = nullptr;
-  if (!on_device && n > 0) {
-    states = &fsp.GetStatesRef();
-    shifted.resize((size_t) n * n_species);
-    vals.resize((size_t) n);
-  }
-  std::vector<int> zero_nu(n_species, 0);
-  for (int p = 0; p < P && n > 0; ++p) {
-    const int  r = planes[p];
-    const int *nu = SM.colptr(r);
-    // column indices: State2Index(x - nu) for all local states, in one batched device lookup (:133-134)
-    FSPCHKERRQ(fspset_lookup_shifted(dset, nu, -1, fsp.GetLocalStart(), n, col.get() + (size_t) p * ld));
-    if (on_device) {
+  std::vector<int>    zero_nu(n_species, 0);
+  const long          first = fsp.GetLocalStart();
+
+  if (on_device) {
+    // device-evaluable (mass-action) propensities: everything stays on the GPU
+    for (int p = 0; p < P && n > 0; ++p) {
+      const int  r = planes[p];
+      const int *nu = SM.colptr(r);
+      FSPCHKERRQ(fspset_lookup_shifted(dset, nu, -1, first, n, col.get() + (size_t) p * ld));  // State2Index(x - nu), :133-134
       std::vector<int> ord(n_species);
       for (int s = 0; s < n_species; ++s) ord[s] = mass_action_->order(s, r);
-      FSPCHKERRQ(fspset_eval_mass_action(dset, mass_action_->rate[r], ord.data(), nu, -1, fsp.GetLocalStart(), n,
-                                         off.get() + (size_t) p * ld));
-      FSPCHKERRQ(fspset_eval_mass_action(dset, mass_action_->rate[r], ord.data(), zero_nu.data(), 0,
-                                         fsp.GetLocalStart(), n, diag.get() + (size_t) p * ld));
-    } else {
-      // host callbacks (API contract): prop_x on x - nu (:135-136) and on x (:180, :232)
+      FSPCHKERRQ(fspset_eval_mass_action(dset, mass_action_->rate[r], ord.data(), nu, -1, first, n, off.get() + (size_t) p * ld));
+      FSPCHKERRQ(fspset_eval_mass_action(dset, mass_action_->rate[r], ord.data(), zero_nu.data(), 0, first, n,
+                                         diag.get() + (size_t) p * ld));
+    }
+  } else if (comm_size_ == 1) {
+    // Single rank, host callbacks (API contract).  d_r(x_i) is evaluated on the host once per state -- with the
+    // incremental cache only for states added since the previous generation -- and the off-diagonal values
+    // d_r(x_i - nu_r) are gathered on the device from the source state's entry (off(i, r) == diag(col(i, r), r):
+    // prop_x is a function of (reaction, state)); the reference instead calls prop_x a second time on every shifted
+    // state (:135-136), including absent ones whose value it then drops.
+    const bool reuse = incremental_ && cache_R_ == num_reactions_ && cache_enabled_ == enable_reactions_ && cache_n_ <= n;
+    if (!reuse) { cache_n_ = 0; cache_R_ = num_reactions_; cache_enabled_ = enable_reactions_; }
+    if (n > cache_ld_ || !diag_cache_.get()) {
+      long new_ld = std::max<long>(n + n / 2 + 1024, 1);
+      DeviceBuffer<double> bigger;
+      if (bigger.resize((size_t) num_reactions_ * new_ld)) PACMENSLCHKERRQ(-1);
+      for (int r = 0; r < num_reactions_ && cache_n_ > 0; ++r)
+        FSPCHKERRQ(fsp_memcpy_d2d(bigger.get() + (size_t) r * new_ld, diag_cache_.get() + (size_t) r * cache_ld_,
+                                  sizeof(double) * cache_n_, nullptr));
+      FSPCHKERRQ(fsp_device_sync());
+      diag_cache_.swap(bigger);
+      cache_ld_ = new_ld;
+    }
+    const long n_new = n - cache_n_;
+    if (n_new > 0) {
+      shifted.resize((size_t) n_new * n_species);  // host copy of the NEW states only
+      vals.resize((size_t) n_new);
+      FSPCHKERRQ(fspset_copy_states(dset, cache_n_, n_new, shifted.data()));
+      for (int r : enable_reactions_) {
+        ierr = new_prop_x(r, n_species, (int) n_new, shifted.data(), vals.data(), prop_x_args);
+        PACMENSLCHKERRQ(ierr);
+        FSPCHKERRQ(fsp_memcpy_h2d(diag_cache_.get() + (size_t) r * cache_ld_ + cache_n_, vals.data(), sizeof(double) * n_new, nullptr));
+      }
+      cache_n_ = n;
+    }
+    for (int p = 0; p < P && n > 0; ++p) {
+      const int r = planes[p];
+      FSPCHKERRQ(fspset_lookup_shifted(dset, SM.colptr(r), -1, first, n, col.get() + (size_t) p * ld));
+      FSPCHKERRQ(fsp_memcpy_d2d(diag.get() + (size_t) p * ld, diag_cache_.get() + (size_t) r * cache_ld_, sizeof(double) * n, nullptr));
+      FSPCHKERRQ(fspvec_gather(off.get() + (size_t) p * ld, diag_cache_.get() + (size_t) r * cache_ld_,
+                               col.get() + (size_t) p * ld, n, nullptr));
+    }
+    if (!incremental_) ResetGenerationCache();
+  } else {
+    // Multi-GPU, host callbacks: as the reference, prop_x on x - nu (:135-136) and on x (:180, :232) for the local rows
+    const arma::Mat<int> *states = n > 0 ? &fsp.GetStatesRef() : nullptr;
+    if (n > 0) { shifted.resize((size_t) n * n_species); vals.resize((size_t) n); }
+    for (int p = 0; p < P && n > 0; ++p) {
+      const int  r = planes[p];
+      const int *nu = SM.colptr(r);
+      FSPCHKERRQ(fspset_lookup_shifted(dset, nu, -1, first, n, col.get() + (size_t) p * ld));
       const int *X = states->memptr();
       for (long i = 0; i < n; ++i)
         for (int s = 0; s < n_species; ++s) shifted[(size_t) i * n_species + s] = X[(size_t) i * n_species + s] - nu[s];
@@ -359,6 +401,13 @@ double FspMatrixBase::GetActionBytes() const {
   double b = 0.0;
   if (dmat_) fspmat_action_bytes(dmat_, &b);
   return b;
+}
+
+void FspMatrixBase::ResetGenerationCache() {
+  diag_cache_.release();
+  cache_n_ = cache_ld_ = 0;
+  cache_R_ = 0;
+  cache_enabled_.clear();
 }
 
 void FspMatrixBase::SetKernelVariant(int v) {

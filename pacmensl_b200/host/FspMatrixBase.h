@@ -54,6 +54,12 @@ class PACMENSL_API FspMatrixBase {
   double GetActionBytes() const;
   /// select a kernel variant (tuning / benchmarks)
   void SetKernelVariant(int v);
+  /// Extension: keep the per-state propensities d_r(x_i) on the device across Destroy()/GenerateValues() cycles so
+  /// that a regeneration after a state-set expansion evaluates the host callback only on the NEW states (indices of
+  /// existing states never change).  The caller promises that the same model and the same, only-growing state set are
+  /// used until ResetGenerationCache() / destruction.  FspSolverMultiSinks turns this on.  Single-rank only.
+  void SetIncrementalGeneration(bool on) { incremental_ = on; if (!on) ResetGenerationCache(); }
+  void ResetGenerationCache();
 
   virtual ~FspMatrixBase();
 
@@ -76,6 +82,12 @@ class PACMENSL_API FspMatrixBase {
   fspmat_t  dmat_ = nullptr;
   PetscBool has_values_ = PETSC_FALSE;
   int       kernel_variant_ = 0;
+
+  bool                 incremental_ = false;
+  DeviceBuffer<double> diag_cache_;  ///< [num_reactions][cache_ld_] propensities d_r(x_i) by reaction id
+  long                 cache_n_ = 0, cache_ld_ = 0;
+  int                  cache_R_ = 0;
+  std::vector<int>     cache_enabled_;
 
   // set when GenerateValues(fsp, model) is used with a model that has a mass-action description
   std::shared_ptr<MassActionPropensity> mass_action_;

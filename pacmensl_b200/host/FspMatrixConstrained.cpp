@@ -1,5 +1,7 @@
 #include "FspMatrixConstrained.h"
 
+#include <algorithm>
+
 namespace pacmensl {
 
 FspMatrixConstrained::FspMatrixConstrained(MPI_Comm comm) : FspMatrixBase(comm) {}
@@ -60,33 +62,30 @@ int FspMatrixConstrained::CollectSinks_(const StateSetBase &fsp, const arma::Mat
     int   ierr = cfss ? cfss->SyncShapeToDevice() : -1;
     PACMENSLCHKERRQ(ierr);
   }
-  // per plane: K ascending index lists; capacity grows on demand (boundary entries are O(surface))
+  // per plane: K ascending index lists over the boundary states (status != 0): O(surface) work and memory
+  long n_bnd = n;
+  FSPCHKERRQ(fspset_num_boundary_states(dset, fsp.GetLocalStart(), n, &n_bnd));
+  const long cap = std::max<long>(n_bnd * K, 1);
   std::vector<DeviceBuffer<int>>    idx_parts(P);
   std::vector<DeviceBuffer<double>> val_parts(P);
   std::vector<long>                 counts((size_t) K);
+  DeviceBuffer<int>                 scratch;
+  if (scratch.resize((size_t) cap)) return -1;
   long total = 0;
   for (int p = 0; p < P; ++p) {
     const int r = planes[p];
-    if (idx_parts[p].resize((size_t) n * K)) return -1;  // upper bound; freed right after compaction below
-    FSPCHKERRQ(fspset_sink_lists(dset, SM.colptr(r), fsp.GetLocalStart(), n, idx_parts[p].get(), (long) n * K,
-                                 counts.data()));
+    FSPCHKERRQ(fspset_sink_lists(dset, SM.colptr(r), fsp.GetLocalStart(), n, scratch.get(), cap, counts.data()));
     long tot_p = 0;
     for (int k = 0; k < K; ++k) {
       sink_ptr[(size_t) p * K + k + 1] = sink_ptr[(size_t) p * K + k] + counts[k];
       tot_p += counts[k];
     }
-    // values d_r(x_i): gather from this plane's diagonal (the reference calls prop() per entry, :188)
-    if (val_parts[p].resize((size_t) (tot_p > 0 ? tot_p : 1))) return -1;
-    if (tot_p > 0)
+    if (idx_parts[p].resize((size_t) (tot_p > 0 ? tot_p : 1)) || val_parts[p].resize((size_t) (tot_p > 0 ? tot_p : 1))) return -1;
+    if (tot_p > 0) {
+      FSPCHKERRQ(fsp_memcpy_d2d(idx_parts[p].get(), scratch.get(), sizeof(int) * tot_p, nullptr));
+      // values d_r(x_i): gather from this plane's diagonal (the reference calls prop() per entry, :188)
       FSPCHKERRQ(fspvec_gather(val_parts[p].get(), diag_planes_dev + (size_t) p * ld, idx_parts[p].get(), tot_p, nullptr));
-    // shrink the index list to its real size
-    DeviceBuffer<int> small;
-    if (small.resize((size_t) (tot_p > 0 ? tot_p : 1))) return -1;
-    if (tot_p > 0) FSPCHKERRQ(fsp_memcpy_d2d(small.get(), idx_parts[p].get(), sizeof(int) * tot_p, nullptr));
-    FSPCHKERRQ(fsp_device_sync());
-    idx_parts[p].release();
-    idx_parts[p].resize((size_t) (tot_p > 0 ? tot_p : 1));
-    if (tot_p > 0) FSPCHKERRQ(fsp_memcpy_d2d(idx_parts[p].get(), small.get(), sizeof(int) * tot_p, nullptr));
+    }
     total += tot_p;
   }
   if (sink_idx.resize((size_t) (total > 0 ? total : 1))) return -1;

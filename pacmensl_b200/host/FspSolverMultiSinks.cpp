@@ -184,6 +184,7 @@ PacmenslErrorCode FspSolverMultiSinks::SetUp() {
   if (!A_) {
     double t0 = now_s();
     A_ = std::make_shared<FspMatrixConstrained>(comm_);
+    A_->SetIncrementalGeneration(true);  // the driver owns model and state set: regenerate only for new states
     ierr = A_->GenerateValues(*state_set_, model_);
     PACMENSLCHKERRQ(ierr);
     t_matgen_ += now_s() - t0;

@@ -102,6 +102,7 @@ class DeviceBuffer {
   void release() { if (ptr_) fsp_free(ptr_); ptr_ = nullptr; n_ = cap_ = 0; }
   T *get() const { return ptr_; }
   size_t size() const { return n_; }
+  void swap(DeviceBuffer &o) { std::swap(ptr_, o.ptr_); std::swap(n_, o.n_); std::swap(cap_, o.cap_); }
   int upload(const T *host, size_t n) { int e = resize(n); if (e) return e; return n ? fsp_memcpy_h2d(ptr_, host, sizeof(T) * n, nullptr) : 0; }
   int download(T *host, size_t n) const { return n ? fsp_memcpy_d2h(host, ptr_, sizeof(T) * n, nullptr) : 0; }
 
