@@ -107,8 +107,9 @@ def lattice_bytes_per_row(tv):
     return 16 + 12 * R + 8 * (ntv + (1 if R - ntv > 0 else 0))
 
 
-def cpu_baseline(args, all_threads=True):
+def cpu_baseline(args, steps=None, warmup=3):
     """Reference-shaped multi-pass Action (oracle port) on a bounded sample of the same workload."""
+    steps = steps or args.cpu_steps
     import numpy as np
     from oracle import oracle as O
     L = args.cpu_lattice
@@ -123,10 +124,10 @@ def cpu_baseline(args, all_threads=True):
     x[n:] = 0.0
     x /= x.sum()
     y = np.empty_like(x)
-    for _ in range(3):
+    for _ in range(max(warmup, 1)):
         A.action_into(0.0, x, y)
     ts = []
-    for _ in range(args.cpu_steps):
+    for _ in range(steps):
         t0 = time.perf_counter()
         A.action_into(0.0, x, y)
         ts.append(time.perf_counter() - t0)
@@ -135,7 +136,7 @@ def cpu_baseline(args, all_threads=True):
     nbytes = n * lattice_bytes_per_row(args.tv) + 12 * 3 * L * L + 8 * 3
     return {"value": nbytes / med / 1e9, "unit": "GB/s", "cores": O.num_threads(), "kind": "port",
             "sample": "%d^3 = %d-state lattice, median of %d reference-shaped (SpMV+AXPY per matrix) OpenMP Actions; "
-                      "oracle/fsp_oracle.c (the PETSc reference cannot be built in this image)" % (L, n, args.cpu_steps),
+                      "oracle/fsp_oracle.c (the PETSc reference cannot be built in this image)" % (L, n, steps),
             "ms_per_step": med * 1e3}
 
 
@@ -143,10 +144,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args)
+    # K steps / W warm-ups as asked, each step one Action on the bounded CPU sample (a few ms to a few 100 ms per step)
+    steps, warmup = max(1, min(args.steps, 2000)), max(args.warmup, 3)
+    cb = cpu_baseline(args, steps=steps, warmup=warmup)
     line = {
         "metric": "FSP Action() GB/s", "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.cpu_steps, "warmup": 3, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
         "config": {"workload": "synthetic 3-D birth-death lattice Action() (CPU sample %d^3)" % args.cpu_lattice,
                    "tv": bool(args.tv)},

@@ -234,6 +234,14 @@ FSP_API int fspmat_action(fspmat_t h, const double *coef_host, const double *x_d
 FSP_API int fspmat_action_phase(fspmat_t h, const double *coef_host, const double *x_dev, const double *ghost_dev,
                                 double *y_dev, double *sink_out_dev, int phase, void *stream);
 FSP_API int fspmat_num_boundary_rows(fspmat_t h, long *n);
+/* Peer-memory variants (see fsphalo_* below).  sinks: the K partial sink sums go straight into the sink owner's slot
+ * row (e->sink_slot_remote) followed by the flag; boundary: waits in device code for every peer's halo flag, redoes
+ * the rows that reference ghost entries and, on the sink owner, adds the slots in rank order into y[n..n+K). */
+struct fsphalo_epoch;
+FSP_API int fspmat_action_sinks_p2p(fspmat_t h, const double *coef_host, const double *x_dev,
+                                    const struct fsphalo_epoch *e, void *stream);
+FSP_API int fspmat_action_boundary_p2p(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev,
+                                       const struct fsphalo_epoch *e, void *stream);
 FSP_API int fspmat_flops(fspmat_t h, long *nflops);
 FSP_API int fspmat_num_rows(fspmat_t h, int *n_rows);
 /* algorithmic bytes of one Action: n*(16 + 12 P + 8 (n_tv + [n_ti>0])) + 12 nnz_sink + 8 K */
@@ -277,6 +285,38 @@ FSP_API int fspcomm_alltoall_counts(fspcomm_t c, const long *send_host, long *re
 FSP_API int fspcomm_exchange_int(fspcomm_t c, const int *send_dev, const long *send_counts_host, int *recv_dev,
                                  const long *recv_counts_host, void *stream);
 /* pack: out[i] = x[idx[i]] is fspvec_gather */
+
+/* ---- peer-memory fast path (one node, NVLink / NVSwitch; CUDA IPC windows mapped at fspcomm_create) ----------
+ * When enabled (all ranks can map all peers; FSP_P2P=0 disables), fspcomm_allreduce_{sum,max} of n <=
+ * FSP_P2P_MAX_REDUCE doubles is ONE kernel (store to every peer's slot, flag, wait, sum in rank order: deterministic
+ * and bit-identical on all ranks), and the halo exchange of an Action is ONE kernel (fsphalo_begin: pack boundary
+ * entries of x, store them into the peers' ghost buffers over NVLink, publish an epoch flag) whose consumers
+ * (fspmat_action_boundary_p2p, fspmat_action_sinks_p2p) wait on the flags in device code.  These replace the
+ * VecScatter of MatMult(MATMPISELL), the sink VecScatter ADD (FspMatrixConstrained.cpp:57-60) and the
+ * MPI_Allreduce of VecDot/VecNorm without any host synchronisation or library call on the hot path. */
+#define FSP_P2P_MAX_RANKS 16
+#define FSP_P2P_MAX_REDUCE 64
+#define FSP_P2P_MAX_SINKS 64
+FSP_API int fspcomm_p2p_enabled(fspcomm_t c);
+typedef struct fsphalo_s *fsphalo_t;
+typedef struct fsphalo_epoch {
+  unsigned long long        epoch;
+  int                       n_ranks, self_rank;
+  const double             *ghost;            /* this epoch's local ghost buffer (filled by the peers) */
+  const unsigned long long *halo_flags;       /* local [n_ranks]: peer p has delivered when flags[p] >= epoch */
+  const unsigned long long *sink_flags;       /* local [n_ranks] (meaningful on the sink owner = last rank) */
+  const double             *sink_slots;       /* local [n_ranks][FSP_P2P_MAX_SINKS] partial sink sums */
+  double                   *sink_slot_remote; /* the owner's slot row of THIS rank (peer memory) */
+  unsigned long long       *sink_flag_remote; /* the owner's sink flag of THIS rank (peer memory) */
+  unsigned int             *error_flag;       /* set by device code when a wait times out */
+} fsphalo_epoch;
+/* collective.  send_idx_dev: local indices of the x entries the peers need, packed per destination in rank order
+ * (borrowed, must outlive the halo); ghost slots are laid out per source in rank order. */
+FSP_API int fsphalo_create(fspcomm_t c, fsphalo_t *out, const int *send_idx_dev, const long *send_counts_host,
+                           const long *recv_counts_host, int n_sink);
+FSP_API int fsphalo_destroy(fsphalo_t h);
+/* start of an Action: launches the fused pack + store + signal kernel on `stream` and describes the epoch */
+FSP_API int fsphalo_begin(fsphalo_t h, const double *x_dev, void *stream, fsphalo_epoch *out);
 
 #ifdef __cplusplus
 }

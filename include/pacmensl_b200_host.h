@@ -30,6 +30,8 @@ typedef int (*pfsp_constr_fn)(int num_species, int num_constr, int num_states, i
 /* process set-up: select the device and (size > 1) join the NCCL world with the id made by fspcomm_unique_id on rank 0 */
 FSP_API int         pfsp_init(int device, const char *nccl_id, int rank, int size);
 FSP_API int         pfsp_finalize(void);
+/* 1 when the world communicator uses the peer-memory (CUDA IPC over NVLink) fast path, 0 = NCCL path / single rank */
+FSP_API int         pfsp_p2p_enabled(void);
 FSP_API const char *pfsp_last_error(void);
 
 /* ---- state set ---- */
@@ -53,6 +55,8 @@ FSP_API int pfsp_model_from_fixture(void **model, const char *name, int *S, int 
                                     int *x0, double *t_final, double *fsp_tol, double *rtol, double *atol,
                                     pfsp_constr_fn *lhs);
 FSP_API int pfsp_model_set_mass_action(void *model, const double *rates, const int *orders_colmajor);
+/* copies the S x R stoichiometry matrix (column major: SM[r*S + s]) */
+FSP_API int pfsp_model_get_stoichiometry(void *model, int *SM_colmajor);
 FSP_API int pfsp_model_destroy(void *model);
 
 /* ---- operator ---- */

@@ -105,6 +105,8 @@ SIGNATURES = {
     "fspmat_action": (ci, [vp, dp, vp, vp, vp, vp, vp]),
     "fspmat_action_phase": (ci, [vp, dp, vp, vp, vp, vp, ci, vp]),
     "fspmat_num_boundary_rows": (ci, [vp, lp]),
+    "fspmat_action_sinks_p2p": (ci, [vp, dp, vp, vp, vp]),
+    "fspmat_action_boundary_p2p": (ci, [vp, dp, vp, vp, vp, vp]),
     "fspmat_flops": (ci, [vp, lp]),
     "fspmat_num_rows": (ci, [vp, ip]),
     "fspmat_action_bytes": (ci, [vp, dp]),
@@ -124,6 +126,10 @@ SIGNATURES = {
     "fspcomm_halo_exchange": (ci, [vp, vp, lp, vp, lp, vp]),
     "fspcomm_alltoall_counts": (ci, [vp, lp, lp, vp]),
     "fspcomm_exchange_int": (ci, [vp, vp, lp, vp, lp, vp]),
+    "fspcomm_p2p_enabled": (ci, [vp]),
+    "fsphalo_create": (ci, [vp, vpp, vp, lp, lp, ci]),
+    "fsphalo_destroy": (ci, [vp]),
+    "fsphalo_begin": (ci, [vp, vp, vp, vp]),
 }
 
 _LIB = None

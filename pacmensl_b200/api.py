@@ -20,6 +20,7 @@ PROP_FN, TCOEF_FN, CONSTR_FN = _capi.PROP_FN, _capi.TCOEF_FN, _capi.CONSTR_FN
 HOST_SIGNATURES = {
     "pfsp_init": (ci, [ci, C.c_char_p, ci, ci]),
     "pfsp_finalize": (ci, []),
+    "pfsp_p2p_enabled": (ci, []),
     "pfsp_last_error": (C.c_char_p, []),
     "pfsp_set_create": (ci, [vpp]),
     "pfsp_set_destroy": (ci, [vp]),
@@ -35,6 +36,7 @@ HOST_SIGNATURES = {
     "pfsp_model_create": (ci, [vpp, ci, ci, ip, vp, vp, vp, vp, ci, ip]),
     "pfsp_model_from_fixture": (ci, [vpp, C.c_char_p, ip, ip, ip, ip, dp, ip, dp, dp, dp, dp, vpp]),
     "pfsp_model_set_mass_action": (ci, [vp, dp, ip]),
+    "pfsp_model_get_stoichiometry": (ci, [vp, ip]),
     "pfsp_model_destroy": (ci, [vp]),
     "pfsp_mat_create": (ci, [vpp, ci]),
     "pfsp_mat_destroy": (ci, [vp]),
@@ -113,6 +115,11 @@ def init(device=0, dist=None):
 
 def finalize():
     lib().pfsp_finalize()
+
+
+def p2p_enabled():
+    """True when halo exchange / small all-reduces run as fused peer-memory kernels (CUDA IPC over NVLink)."""
+    return bool(lib().pfsp_p2p_enabled())
 
 
 class StateSet:
@@ -235,6 +242,12 @@ class Model:
                                       C.cast(pt, vp) if pt else None, None, len(tvv), _ip(tvv)), "pfsp_model_create")
         self.h = h
 
+    def stoichiometry(self):
+        """S x R matrix as written in the reference (one column per reaction)."""
+        sm = np.zeros((self.R, self.S), dtype=np.int32)
+        check(lib().pfsp_model_get_stoichiometry(self.h, _ip(sm)), "stoichiometry")
+        return np.ascontiguousarray(sm.T)
+
     def set_mass_action(self, rates, orders):
         r = np.ascontiguousarray(rates, dtype=np.float64)
         o = np.ascontiguousarray(np.asarray(orders, dtype=np.int32).T)  # S x R -> column major
@@ -352,6 +365,24 @@ class FspSolver:
 
     def clear(self):
         return lib().pfsp_solver_clear(self.h)
+
+
+def fixture_set_and_matrix(name, bounds=None, model=None, constrained=True):
+    """StateSetConstrained (x0 added, Expand()ed within `bounds`) + generated FspMatrix of a named workload."""
+    m = model or Model(fixture=name)
+    fx = m.fixture
+    st = StateSet(m.stoichiometry())
+    b = fx["bounds"] if bounds is None else bounds
+    ierr = st.set_shape(b, lhs_c=fx["lhs"])
+    assert ierr == 0, ierr
+    assert st.add_states(fx["x0"].reshape(1, -1)) == 0
+    assert st.expand() == 0
+    mat = FspMatrix(constrained=constrained)
+    ierr = mat.generate(st, m)
+    if ierr:
+        raise FspError("GenerateValues failed: %d" % ierr)
+    mat._model = m
+    return st, mat
 
 
 def fixture_solver(name, ode_type=CVODE, custom_constraints=True):

@@ -80,4 +80,33 @@ __device__ __forceinline__ double block_sum(double v, double *smem) {
   return r;
 }
 
+// ---- peer-memory signalling (multi-GPU fast path, fspcomm.cu / fspmat.cu) --------------------------
+constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= epoch; false (and *err = 1) after kSpinTimeoutNs so that a lost peer cannot hang the GPU
+__device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long epoch, unsigned int *err) {
+  if (ld_acquire_sys(flag) >= epoch) return true;
+  const unsigned long long t0 = global_ns();
+  while (ld_acquire_sys(flag) < epoch) {
+    __nanosleep(64);
+    if (global_ns() - t0 > kSpinTimeoutNs) {
+      if (err) *(volatile unsigned int *) err = 1u;
+      return false;
+    }
+  }
+  return true;
+}
+
 }  // namespace fspb

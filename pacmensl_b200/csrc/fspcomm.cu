@@ -5,8 +5,20 @@
 // MPI_Allreduce behind every VecDot/VecNorm (src/OdeSolver/KrylovFsp.cpp:280-309).
 // NCCL is bound at run time with dlopen so that a process which already loaded a libnccl.so.2 (e.g.
 // PyTorch's bundled copy) shares it instead of pulling in a second, different NCCL.
+//
+// Peer-memory fast path (one node, NVLink 5 / NVSwitch): every rank maps a window of every peer's HBM through
+// CUDA IPC.  The halo exchange is then ONE kernel (pack the boundary entries of x and store them straight into the
+// peers' ghost buffers, then publish an epoch flag with release semantics at system scope) and the consumer kernels
+// wait on the flags in device code; small all-reduces (Krylov/GMRES inner products) are ONE kernel that writes
+// this rank's values into every peer's slot and sums the slots in rank order (deterministic, bit-identical on all
+// ranks).  No NCCL call, no host synchronisation, on the per-Action / per-inner-product path.  NCCL remains the
+// bootstrap (handle exchange) and the path for FSP_P2P=0 or GPUs without peer access.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "fsp_common.cuh"
 
@@ -73,10 +85,220 @@ int load_nccl() {
 
 }  // namespace
 
+// ---- peer-memory windows ---------------------------------------------------------------------------
+constexpr int kMaxRanks = FSP_P2P_MAX_RANKS;
+constexpr int kMaxRedVals = FSP_P2P_MAX_REDUCE;
+constexpr int kRedDepth = 4;  // ring of reduction slots (calls are stream-ordered; 2 would do)
+
+struct PeerWindow {
+  size_t bytes = 0;
+  void  *local = nullptr;
+  void  *peer[kMaxRanks] = {nullptr};  // peer[rank] == local
+};
+
+// control window of a communicator: flags + slots of the fused small all-reduce
+struct CtrlLayout {
+  unsigned long long flags[kRedDepth][kMaxRanks];
+  double             slots[kRedDepth][kMaxRanks][kMaxRedVals];
+};
+
+// halo window of one operator: epoch flags, sink slots, double-buffered ghost entries
+struct HaloHeader {
+  unsigned long long halo_flags[2][kMaxRanks];
+  unsigned long long sink_flags[2][kMaxRanks];
+  double             sink_slots[2][kMaxRanks][FSP_P2P_MAX_SINKS];
+};
+
 struct fspcomm_s {
   ncclComm_t comm = nullptr;
   int        rank = 0, size = 1;
+  // peer-memory state
+  bool               p2p = false;
+  PeerWindow         ctrl;
+  unsigned long long red_epoch = 0;
+  unsigned int      *err_host = nullptr;  // pinned + mapped: device code sets it when a flag wait times out
+  unsigned int      *err_dev = nullptr;
+  struct PooledHalo { PeerWindow win; size_t cap = 0; unsigned long long epoch = 0; };
+  std::vector<PooledHalo> halo_pool;  // windows returned by fsphalo_destroy, identical order/capacity on all ranks
 };
+
+struct fsphalo_s {
+  fspcomm_s         *c = nullptr;
+  fspcomm_s::PooledHalo w;
+  long               n_send = 0, n_ghost = 0;
+  int                n_sink = 0;
+  int               *send_idx = nullptr;  // borrowed device pointer
+  long               send_off[kMaxRanks + 1] = {0};
+  long               remote_off[kMaxRanks] = {0};  // where my segment starts in peer p's ghost buffer
+  unsigned          *block_counter = nullptr;
+};
+
+namespace {
+
+struct PushArgs {
+  int                 size, rank, parity;
+  long                n_send;
+  unsigned long long  epoch;
+  long                send_off[kMaxRanks + 1];
+  double             *dst[kMaxRanks];    // peer p's ghost buffer of this parity, already offset to my segment
+  unsigned long long *flag[kMaxRanks];   // peer p's halo flag of this parity for my rank
+};
+
+// ONE kernel = pack + all-to-all over NVLink + signal: thread q stores x[send_idx[q]] into the ghost buffer of the
+// peer that needs it; the last CTA to finish publishes epoch on every peer (release at system scope orders it after
+// all the data stores, which each CTA made visible with a system-scope fence before taking its ticket).
+__global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a, const double *__restrict__ x,
+                                                        const int *__restrict__ send_idx, unsigned *block_counter) {
+  const long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < a.n_send) {
+    int p = 0;
+    while (q >= a.send_off[p + 1]) ++p;
+    a.dst[p][q - a.send_off[p]] = x[send_idx[q]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(block_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x < a.size) st_release_sys(a.flag[threadIdx.x], a.epoch);
+  if (threadIdx.x == 0) *block_counter = 0u;
+}
+
+struct ReduceArgs {
+  int                 size, rank, n, slot;
+  unsigned long long  epoch;
+  double             *slots[kMaxRanks];  // peer p's slot row [slot][rank][*] for my rank
+  unsigned long long *flag[kMaxRanks];   // peer p's flag [slot][rank]
+  const double             *my_slots;    // local [slot][0][0]
+  const unsigned long long *my_flags;    // local [slot][0]
+  unsigned int       *err;
+};
+
+// Fused small all-reduce (n <= kMaxRedVals): write my values into every peer's slot, publish, wait for all peers,
+// sum (or max) in rank order.  One CTA.
+template <bool IS_MAX>
+__global__ void __launch_bounds__(128) p2p_allreduce_kernel(ReduceArgs a, double *__restrict__ buf) {
+  const int t = threadIdx.x;
+  if (t < a.n) {
+    const double v = buf[t];
+    for (int p = 0; p < a.size; ++p) a.slots[p][t] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < a.size) {
+    st_release_sys(a.flag[t], a.epoch);
+    wait_flag(a.my_flags + t, a.epoch, a.err);
+  }
+  __syncthreads();
+  if (t < a.n) {
+    double s = __ldcg(a.my_slots + t);
+    for (int p = 1; p < a.size; ++p) {
+      const double v = __ldcg(a.my_slots + (size_t) p * kMaxRedVals + t);
+      s = IS_MAX ? fmax(s, v) : s + v;
+    }
+    buf[t] = s;
+  }
+}
+
+int window_create(fspcomm_s *c, size_t bytes, PeerWindow *w) {
+  // collective: allocate + zero the local part, all-gather the IPC handles over NCCL, map every peer
+  w->bytes = bytes;
+  FSP_CUDA_CHECK(cudaMalloc(&w->local, bytes));
+  FSP_CUDA_CHECK(cudaMemset(w->local, 0, bytes));
+  FSP_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t mine;
+  FSP_CUDA_CHECK(cudaIpcGetMemHandle(&mine, w->local));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  double *d_send = nullptr, *d_all = nullptr;
+  FSP_CUDA_CHECK(cudaMalloc(&d_send, 64));
+  FSP_CUDA_CHECK(cudaMalloc(&d_all, 64 * (size_t) c->size));
+  FSP_CUDA_CHECK(cudaMemcpy(d_send, &mine, 64, cudaMemcpyHostToDevice));
+  FSP_NCCL_CHECK(g_nccl.AllGather(d_send, d_all, 8, ncclFloat64, c->comm, (cudaStream_t) 0));
+  std::vector<cudaIpcMemHandle_t> all((size_t) c->size);
+  FSP_CUDA_CHECK(cudaMemcpy(all.data(), d_all, 64 * (size_t) c->size, cudaMemcpyDeviceToHost));
+  cudaFree(d_send);
+  cudaFree(d_all);
+  for (int p = 0; p < c->size; ++p) {
+    if (p == c->rank) { w->peer[p] = w->local; continue; }
+    cudaError_t e = cudaIpcOpenMemHandle(&w->peer[p], all[(size_t) p], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("cudaIpcOpenMemHandle(peer %d) failed: %s", p, cudaGetErrorString(e));
+      cudaGetLastError();
+      return -1;
+    }
+  }
+  return 0;
+}
+
+void window_destroy(fspcomm_s *c, PeerWindow *w) {
+  for (int p = 0; p < c->size; ++p)
+    if (p != c->rank && w->peer[p]) cudaIpcCloseMemHandle(w->peer[p]);
+  if (w->local) cudaFree(w->local);
+  *w = PeerWindow();
+}
+
+int check_peer_error(fspcomm_s *c, const char *where) {
+  if (c->err_host && *(volatile unsigned int *) c->err_host) {
+    set_error("%s: a peer-memory flag wait timed out (a rank is missing or failed)", where);
+    return -1;
+  }
+  return 0;
+}
+
+
+int p2p_allreduce(fspcomm_s *c, double *buf, int n, bool is_max, cudaStream_t st) {
+  if (check_peer_error(c, "fspcomm_allreduce")) return -1;
+  const unsigned long long epoch = ++c->red_epoch;
+  const int slot = (int) (epoch % kRedDepth);
+  ReduceArgs a;
+  a.size = c->size; a.rank = c->rank; a.n = n; a.slot = slot; a.epoch = epoch;
+  for (int p = 0; p < c->size; ++p) {
+    CtrlLayout *L = reinterpret_cast<CtrlLayout *>(c->ctrl.peer[p]);
+    a.slots[p] = &L->slots[slot][c->rank][0];
+    a.flag[p] = &L->flags[slot][c->rank];
+  }
+  CtrlLayout *me = reinterpret_cast<CtrlLayout *>(c->ctrl.local);
+  a.my_slots = &me->slots[slot][0][0];
+  a.my_flags = &me->flags[slot][0];
+  a.err = c->err_dev;
+  if (is_max) p2p_allreduce_kernel<true><<<1, 128, 0, st>>>(a, buf);
+  else p2p_allreduce_kernel<false><<<1, 128, 0, st>>>(a, buf);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+// collective; leaves c->p2p == false (NCCL path) if any rank cannot map any peer or FSP_P2P=0
+int p2p_setup(fspcomm_s *c) {
+  const char *env = getenv("FSP_P2P");
+  int want = (env && !strcmp(env, "0")) ? 0 : 1;
+  if (c->size > kMaxRanks) want = 0;
+  int ok = want;
+  if (want) {
+    if (window_create(c, sizeof(CtrlLayout), &c->ctrl)) ok = 0;
+  }
+  // agree: minimum over ranks
+  double *d = nullptr;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
+  double v = ok ? 0.0 : 1.0;
+  cudaMemcpy(d, &v, 8, cudaMemcpyHostToDevice);
+  int r = g_nccl.AllReduce(d, d, 1, ncclFloat64, ncclSum, c->comm, (cudaStream_t) 0);
+  cudaMemcpy(&v, d, 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (r != ncclSuccess || v != 0.0) {
+    if (c->ctrl.local) window_destroy(c, &c->ctrl);
+    c->p2p = false;
+    return 0;
+  }
+  if (cudaHostAlloc((void **) &c->err_host, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) { window_destroy(c, &c->ctrl); return 0; }
+  *c->err_host = 0u;
+  if (cudaHostGetDevicePointer((void **) &c->err_dev, c->err_host, 0) != cudaSuccess) { window_destroy(c, &c->ctrl); return 0; }
+  c->p2p = true;
+  return 0;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -97,6 +319,7 @@ int fspcomm_create(fspcomm_t *out, const char id[FSPCOMM_ID_BYTES], int rank, in
     memcpy(uid.internal, id, FSPCOMM_ID_BYTES);
     int r = g_nccl.CommInitRank(&c->comm, size, uid, rank);
     if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); delete c; return -1; }
+    p2p_setup(c);  // peer-memory fast path when every rank can map every peer; NCCL path otherwise
   }
   *out = c;
   return 0;
@@ -104,6 +327,22 @@ int fspcomm_create(fspcomm_t *out, const char id[FSPCOMM_ID_BYTES], int rank, in
 
 int fspcomm_destroy(fspcomm_t c) {
   if (!c) return 0;
+  if (c->p2p) {
+    // every rank must be past its last peer store before any window is unmapped
+    cudaDeviceSynchronize();
+    double *d = nullptr;
+    if (cudaMalloc(&d, 8) == cudaSuccess) {
+      cudaMemset(d, 0, 8);
+      g_nccl.AllReduce(d, d, 1, ncclFloat64, ncclSum, c->comm, (cudaStream_t) 0);
+      cudaDeviceSynchronize();
+      cudaFree(d);
+    }
+    for (auto &w : c->halo_pool) window_destroy(c, &w.win);
+    c->halo_pool.clear();
+    window_destroy(c, &c->ctrl);
+    if (c->err_host) cudaFreeHost(c->err_host);
+    c->p2p = false;
+  }
   if (c->comm) g_nccl.CommDestroy(c->comm);
   delete c;
   return 0;
@@ -115,13 +354,17 @@ int fspcomm_rank(fspcomm_t c, int *rank, int *size) {
   return 0;
 }
 
+int fspcomm_p2p_enabled(fspcomm_t c) { return (c && c->p2p) ? 1 : 0; }
+
 int fspcomm_allreduce_sum(fspcomm_t c, double *buf, long n, void *stream) {
   if (!c || c->size == 1 || n <= 0) return 0;
+  if (c->p2p && n <= kMaxRedVals) return p2p_allreduce(c, buf, (int) n, false, resolve_stream(stream));
   FSP_NCCL_CHECK(g_nccl.AllReduce(buf, buf, (size_t) n, ncclFloat64, ncclSum, c->comm, resolve_stream(stream)));
   return 0;
 }
 int fspcomm_allreduce_max(fspcomm_t c, double *buf, long n, void *stream) {
   if (!c || c->size == 1 || n <= 0) return 0;
+  if (c->p2p && n <= kMaxRedVals) return p2p_allreduce(c, buf, (int) n, true, resolve_stream(stream));
   FSP_NCCL_CHECK(g_nccl.AllReduce(buf, buf, (size_t) n, ncclFloat64, ncclMax, c->comm, resolve_stream(stream)));
   return 0;
 }
@@ -196,6 +439,99 @@ int fspcomm_exchange_int(fspcomm_t c, const int *send, const long *send_counts, 
   }
   FSP_NCCL_CHECK(g_nccl.GroupEnd());
   FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+
+// ---- fused halo exchange over peer memory ----------------------------------------------------------
+int fsphalo_create(fspcomm_t c, fsphalo_t *out, const int *send_idx_dev, const long *send_counts,
+                   const long *recv_counts, int n_sink) {
+  *out = nullptr;
+  if (!c || !c->p2p) { set_error("fsphalo_create: peer memory is not enabled on this communicator"); return -1; }
+  if (n_sink > FSP_P2P_MAX_SINKS) { set_error("fsphalo_create: %d sink rows exceed %d", n_sink, FSP_P2P_MAX_SINKS); return -1; }
+  fsphalo_s *h = new fsphalo_s();
+  h->c = c; h->n_sink = n_sink; h->send_idx = const_cast<int *>(send_idx_dev);
+  long recv_off[kMaxRanks + 1] = {0};
+  for (int p = 0; p < c->size; ++p) {
+    h->send_off[p + 1] = h->send_off[p] + send_counts[p];
+    recv_off[p + 1] = recv_off[p] + recv_counts[p];
+  }
+  h->n_send = h->send_off[c->size];
+  h->n_ghost = recv_off[c->size];
+  // every peer learns where its segment starts in my ghost buffer
+  if (fspcomm_alltoall_counts(c, recv_off, h->remote_off, nullptr)) { delete h; return -1; }
+  // window capacity: the maximum ghost count over ranks (all ranks must take the same pool decision)
+  double *d = nullptr;
+  FSP_CUDA_CHECK(cudaMalloc(&d, 8));
+  double need = (double) h->n_ghost;
+  FSP_CUDA_CHECK(cudaMemcpy(d, &need, 8, cudaMemcpyHostToDevice));
+  FSP_NCCL_CHECK(g_nccl.AllReduce(d, d, 1, ncclFloat64, ncclMax, c->comm, (cudaStream_t) 0));
+  FSP_CUDA_CHECK(cudaMemcpy(&need, d, 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  const size_t cap_need = (size_t) need;
+  bool found = false;
+  for (size_t q = 0; q < c->halo_pool.size(); ++q) {
+    if (c->halo_pool[q].cap >= cap_need) {
+      h->w = c->halo_pool[q];
+      c->halo_pool.erase(c->halo_pool.begin() + (long) q);
+      found = true;
+      break;
+    }
+  }
+  if (!found) {
+    size_t cap = ((cap_need + cap_need / 4 + 1024) + 31) / 32 * 32;
+    if (window_create(c, sizeof(HaloHeader) + 2 * cap * sizeof(double), &h->w.win)) { delete h; return -1; }
+    h->w.cap = cap;
+    h->w.epoch = 0;
+  }
+  FSP_CUDA_CHECK(cudaMalloc(&h->block_counter, sizeof(unsigned)));
+  FSP_CUDA_CHECK(cudaMemset(h->block_counter, 0, sizeof(unsigned)));
+  *out = h;
+  return 0;
+}
+
+int fsphalo_destroy(fsphalo_t h) {
+  if (!h) return 0;
+  // the window (with its epoch counter: the flags stay monotone) goes back to the pool; the kernels in flight keep
+  // using it safely because every later user continues the same epoch sequence
+  h->c->halo_pool.push_back(h->w);
+  if (h->block_counter) { cudaDeviceSynchronize(); cudaFree(h->block_counter); }
+  delete h;
+  return 0;
+}
+
+int fsphalo_begin(fsphalo_t h, const double *x_dev, void *stream, fsphalo_epoch *out) {
+  fspcomm_s *c = h->c;
+  if (check_peer_error(c, "fsphalo_begin")) return -1;
+  const unsigned long long epoch = ++h->w.epoch;
+  const int par = (int) (epoch & 1ull);
+  PushArgs a;
+  a.size = c->size; a.rank = c->rank; a.parity = par; a.n_send = h->n_send; a.epoch = epoch;
+  for (int p = 0; p <= c->size; ++p) a.send_off[p] = h->send_off[p];
+  for (int p = 0; p < c->size; ++p) {
+    char       *base = reinterpret_cast<char *>(h->w.win.peer[p]);
+    HaloHeader *H = reinterpret_cast<HaloHeader *>(base);
+    double     *ghost = reinterpret_cast<double *>(base + sizeof(HaloHeader)) + (size_t) par * h->w.cap;
+    a.dst[p] = ghost + h->remote_off[p];
+    a.flag[p] = &H->halo_flags[par][c->rank];
+  }
+  const unsigned grid = (unsigned) std::max<long>(1, (h->n_send + 255) / 256);
+  halo_push_kernel<<<grid, 256, 0, resolve_stream(stream)>>>(a, x_dev, h->send_idx, h->block_counter);
+  FSP_LAUNCH_CHECK();
+  char       *mine = reinterpret_cast<char *>(h->w.win.local);
+  HaloHeader *M = reinterpret_cast<HaloHeader *>(mine);
+  const int   owner = c->size - 1;
+  HaloHeader *O = reinterpret_cast<HaloHeader *>(h->w.win.peer[owner]);
+  out->epoch = epoch;
+  out->n_ranks = c->size;
+  out->self_rank = c->rank;
+  out->ghost = reinterpret_cast<double *>(mine + sizeof(HaloHeader)) + (size_t) par * h->w.cap;
+  out->halo_flags = &M->halo_flags[par][0];
+  out->sink_flags = &M->sink_flags[par][0];
+  out->sink_slots = &M->sink_slots[par][0][0];
+  out->sink_slot_remote = &O->sink_slots[par][c->rank][0];
+  out->sink_flag_remote = &O->sink_flags[par][c->rank];
+  out->error_flag = c->err_dev;
   return 0;
 }
 

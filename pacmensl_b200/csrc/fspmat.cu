@@ -62,6 +62,18 @@ struct MatView {
   int           ghost_zero;    // 1: ghost entries contribute 0 (interior pass, halo still in flight)
   const int    *row_list;      // non-null: process only these rows (boundary pass); n = list length
   int           write_y_sinks; // 0: sink role writes only sink_out (the owner copies the reduced values later)
+  // peer-memory mode: sink_out is the sink owner's slot row of this rank; publish this flag after writing it
+  unsigned long long *sink_flag_remote;
+  unsigned long long  sink_epoch;
+};
+
+struct P2PWait {
+  const unsigned long long *halo_flags;
+  const unsigned long long *sink_flags;  // null: this rank does not finish the sink rows
+  const double             *sink_slots;
+  unsigned long long        epoch;
+  int                       n_ranks, rank;
+  unsigned int             *err;
 };
 
 __device__ __forceinline__ double fetch_x(const double *__restrict__ x, const double *__restrict__ ghost, int c) {
@@ -110,6 +122,11 @@ __device__ __forceinline__ void sink_role(const MatView &m, const Coefs &cf, con
     }
   }
   if (threadIdx.x == 0) *m.sink_counter = 0u;
+  if (m.sink_flag_remote) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(m.sink_flag_remote, m.sink_epoch);
+  }
 }
 
 // ---- main rows: V rows per thread, P planes unrolled at compile time ------------------------------
@@ -301,6 +318,41 @@ __global__ void __launch_bounds__(kThreads) fsp_action_rowlist(MatView m, Coefs 
   for (int p = 0; p < m.P; ++p) {
     int c = ld_stream(m.col + p * m.ld + i);
     acc = fma(cf.c[p] * ld_stream(m.off + p * m.ld + i), fetch_x(x, ghost, c), acc);
+  }
+  y[i] = fma(-d, xi, acc);
+}
+
+// Boundary pass of the peer-memory multi-GPU action, fused with the arrival wait: every CTA first waits (device code,
+// acquire at system scope) until every peer's push kernel has published this epoch, then recomputes its rows with the
+// ghost entries the peers stored into this GPU's window.  One extra CTA on the sink owner adds the K x n_ranks partial
+// sink sums in rank order (deterministic) into y[n..n+K).
+__global__ void __launch_bounds__(kThreads) fsp_action_boundary_p2p_kernel(MatView m, Coefs cf, P2PWait w,
+                                                                           const double *__restrict__ x,
+                                                                           const double *ghost, double *__restrict__ y) {
+  if ((int) blockIdx.x >= m.main_blocks) {
+    if ((int) threadIdx.x < w.n_ranks) wait_flag(w.sink_flags + threadIdx.x, w.epoch, w.err);
+    __syncthreads();
+    if ((int) threadIdx.x < m.K) {
+      double s = 0.0;
+      for (int p = 0; p < w.n_ranks; ++p) s += __ldcg(w.sink_slots + (size_t) p * FSP_P2P_MAX_SINKS + threadIdx.x);
+      y[m.n_rows_main + threadIdx.x] = s;
+    }
+    return;
+  }
+  if ((int) threadIdx.x < w.n_ranks && (int) threadIdx.x != w.rank) wait_flag(w.halo_flags + threadIdx.x, w.epoch, w.err);
+  __syncthreads();
+  const long q = (long) blockIdx.x * kThreads + threadIdx.x;
+  if (q >= m.n) return;
+  const long   i = (long) m.row_list[q];
+  const double xi = __ldg(x + i);
+  double       d = 0.0;
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(m.diag + g * m.ld + i), d);
+  double acc = 0.0;
+  for (int p = 0; p < m.P; ++p) {
+    const int c = ld_stream(m.col + p * m.ld + i);
+    // ghost entries were written by other GPUs during this kernel's lifetime: read them at L2 (ld.cg), never L1
+    const double xs = c >= 0 ? __ldg(x + c) : (c == -1 ? 0.0 : __ldcg(ghost + (-(c + 2))));
+    acc = fma(cf.c[p] * ld_stream(m.off + p * m.ld + i), xs, acc);
   }
   y[i] = fma(-d, xi, acc);
 }
@@ -655,6 +707,7 @@ static int launch_action(fspmat_t h, const double *coef_host, const double *x, c
   m.sink_partials = h->d_sink_partials; m.sink_counter = h->d_sink_counter;
   m.owns_sinks = h->owns_sinks;
   m.ghost_zero = 0; m.row_list = nullptr; m.write_y_sinks = 1;
+  m.sink_flag_remote = nullptr; m.sink_epoch = 0;
 
   // Kernel selection.  variant 0 (default) = lean kernel: 1 row per thread, 32 registers, 8 CTAs/SM.  Measured on
   // one B200 (465^3 lattice, same GPU, profiles/r01_variants.md): lean 6.77 TB/s, 2 rows/thread (64 regs) 6.15 TB/s,
@@ -699,6 +752,58 @@ int fspmat_action_phase(fspmat_t h, const double *coef_host, const double *x, co
 }
 
 int fspmat_num_boundary_rows(fspmat_t h, long *n) { *n = h->n_boundary; return 0; }
+
+static void fill_coefs_view(fspmat_t h, const double *coef_host, Coefs &cf, MatView &m) {
+  for (int g = 0; g < h->n_tv; ++g) { cf.c[g] = coef_host[h->tv[g]]; cf.cd[g] = cf.c[g]; }
+  for (int q = 0; q < h->n_ti; ++q) cf.c[h->n_tv + q] = 1.0;
+  if (h->n_ti > 0) cf.cd[h->n_tv] = 1.0;
+  m.n = h->n; m.n_rows_main = h->n; m.P = h->P; m.ND = h->ND; m.ld = h->ld;
+  m.col = h->d_col; m.off = h->d_off; m.diag = h->d_diag;
+  m.K = h->K; m.G = h->ND;
+  m.sink_blocks = h->K > 0 ? h->sink_blocks : 0;
+  m.sb_seg = h->d_sb_seg; m.sb_begin = h->d_sb_begin; m.sb_end = h->d_sb_end;
+  m.sink_idx = h->d_sink_idx; m.sink_val = h->d_sink_val;
+  m.sink_partials = h->d_sink_partials; m.sink_counter = h->d_sink_counter;
+  m.owns_sinks = h->owns_sinks;
+  m.ghost_zero = 0; m.row_list = nullptr; m.write_y_sinks = 0;
+  m.sink_flag_remote = nullptr; m.sink_epoch = 0;
+  m.main_blocks = 0;
+}
+
+int fspmat_action_sinks_p2p(fspmat_t h, const double *coef_host, const double *x, const fsphalo_epoch *e, void *stream) {
+  if (!h->has_values || h->K <= 0) return 0;
+  Coefs cf; MatView m;
+  fill_coefs_view(h, coef_host, cf, m);
+  m.n = 0;
+  m.sink_flag_remote = e->sink_flag_remote;
+  m.sink_epoch = e->epoch;
+  action_fn fn = pick_kernel(h->P, 1);
+  if (!fn) fn = fsp_action_generic;
+  fn<<<m.sink_blocks, kThreads, 0, resolve_stream(stream)>>>(m, cf, x, nullptr, nullptr, e->sink_slot_remote);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fspmat_action_boundary_p2p(fspmat_t h, const double *coef_host, const double *x, double *y, const fsphalo_epoch *e,
+                               void *stream) {
+  if (!h->has_values) return 0;
+  Coefs cf; MatView m;
+  fill_coefs_view(h, coef_host, cf, m);
+  m.row_list = h->d_boundary_rows;
+  m.n = (int) h->n_boundary;
+  m.main_blocks = std::max(1, (int) ((h->n_boundary + kThreads - 1) / kThreads));  // >= 1: every rank waits (pacing)
+  P2PWait w;
+  w.halo_flags = e->halo_flags;
+  const bool finish_sinks = h->K > 0 && h->owns_sinks;
+  w.sink_flags = finish_sinks ? e->sink_flags : nullptr;
+  w.sink_slots = e->sink_slots;
+  w.epoch = e->epoch; w.n_ranks = e->n_ranks; w.err = e->error_flag;
+  w.rank = e->self_rank;
+  const int grid = m.main_blocks + (finish_sinks ? 1 : 0);
+  fsp_action_boundary_p2p_kernel<<<grid, kThreads, 0, resolve_stream(stream)>>>(m, cf, w, x, e->ghost, y);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
 
 int fspmat_build_ghosts(int *col, long n, int lo, int hi, int **ghost_out, long *n_ghost) {
   *ghost_out = nullptr;

@@ -53,6 +53,7 @@ int FspMatrixBase::Destroy() {
   ti_reactions_.clear();
   if (comm_stream_) fsp_stream_sync(comm_stream_);  // side-stream kernels may still read the halo buffers
   if (dmat_) fspmat_clear(dmat_);
+  if (halo_) { fsphalo_destroy(halo_); halo_ = nullptr; }
   ghost_buf_.release();
   send_buf_.release();
   send_idx_.release();
@@ -324,6 +325,25 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
     FSPCHKERRQ(fsp_event_create(&ev_x_ready_));
     FSPCHKERRQ(fsp_event_create(&ev_comm_done_));
   }
+  if (halo_) {
+    // Peer-memory path (NVLink/NVSwitch, no NCCL call, no host synchronisation):
+    //   side stream : ONE kernel packs the boundary entries of x, stores them into the peers' ghost windows and
+    //                 publishes the epoch flag; the sink kernel stores the K partial sums into the owner's slots
+    //   main stream : interior pass; then the boundary kernel waits for the peers' flags in device code, redoes the
+    //                 rows with ghost entries and (sink owner) adds the slots in rank order into y[n..n+K)
+    fsphalo_epoch ep;
+    FSPCHKERRQ(fsp_event_record(ev_x_ready_, stream));
+    FSPCHKERRQ(fsp_stream_wait_event(comm_stream_, ev_x_ready_));
+    FSPCHKERRQ(fsphalo_begin(halo_, x->d_data, comm_stream_, &ep));
+    if (num_constraints_ > 0) FSPCHKERRQ(fspmat_action_sinks_p2p(dmat_, coefs, x->d_data, &ep, comm_stream_));
+    FSPCHKERRQ(fsp_event_record(ev_comm_done_, comm_stream_));
+    FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, nullptr, y->d_data, nullptr, 1, stream));
+    // own push/sink kernels are complete before the boundary kernel may start waiting (no scheduling dependence
+    // between a spinning kernel and a not-yet-scheduled one on this GPU)
+    FSPCHKERRQ(fsp_stream_wait_event(stream, ev_comm_done_));
+    FSPCHKERRQ(fspmat_action_boundary_p2p(dmat_, coefs, x->d_data, y->d_data, &ep, stream));
+    return 0;
+  }
   // optional timeline (FSP_MULTIGPU_TRACE=n prints event timings of the first n Actions after 30 warm-up calls)
   static const int trace_n = [] { const char *e = std::getenv("FSP_MULTIGPU_TRACE"); return e ? std::atoi(e) : 0; }();
   static int   trace_calls = 0;
@@ -447,6 +467,11 @@ int FspMatrixBase::SetupGhosts_(const StateSetBase &fsp, int *col_planes_dev, lo
   FSPCHKERRQ(fspmat_shift_indices(send_idx_.get(), n_send_, -own_start));  // global -> local
   if (ghost_buf_.resize((size_t) (n_ghost > 0 ? n_ghost : 1))) return -1;
   if (send_buf_.resize((size_t) (n_send_ > 0 ? n_send_ : 1))) return -1;
+  // peer-memory halo (CUDA IPC windows over NVLink) when the communicator has it and the default overlap mode is on
+  const char *mode = std::getenv("FSP_MULTIGPU_MODE");
+  if (fspcomm_p2p_enabled(comm_->nccl) && (!mode || !std::strcmp(mode, "overlap")) && num_constraints_ <= FSP_P2P_MAX_SINKS) {
+    FSPCHKERRQ(fsphalo_create(comm_->nccl, &halo_, send_idx_.get(), send_counts_.data(), recv_counts_.data(), num_constraints_));
+  }
   return 0;
 }
 

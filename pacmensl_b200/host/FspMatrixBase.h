@@ -99,6 +99,7 @@ class PACMENSL_API FspMatrixBase {
   // multi-GPU halo exchange (ghost entries of x) and sink reduction
   long                 n_ghost_ = 0;
   DeviceBuffer<double> ghost_buf_, send_buf_, sink_buf_;
+  fsphalo_t            halo_ = nullptr;                      ///< peer-memory halo (fused pack+store+signal kernel); null => NCCL path
   DeviceBuffer<int>    send_idx_;
   std::vector<long>    send_counts_, recv_counts_;
   long                 n_send_ = 0;

@@ -49,6 +49,7 @@ int pfsp_init(int device, const char *nccl_id, int rank, int size) {
   return 0;
 }
 int pfsp_finalize(void) { return pacmensl_comm_world_finalize(); }
+int pfsp_p2p_enabled(void) { MPI_Comm w = MPI_COMM_WORLD; return (w && w->nccl) ? fspcomm_p2p_enabled(w->nccl) : 0; }
 
 // ---- state set ----
 int pfsp_set_create(void **set) {
@@ -143,6 +144,11 @@ int pfsp_model_set_mass_action(void *model, const double *rates, const int *orde
   auto *b = static_cast<ModelBox *>(model);
   const int S = (int) b->model.stoichiometry_matrix_.n_rows, R = (int) b->model.stoichiometry_matrix_.n_cols;
   b->model.SetMassAction(std::vector<double>(rates, rates + R), colmajor(orders, S, R));
+  return 0;
+}
+int pfsp_model_get_stoichiometry(void *model, int *SM_colmajor) {
+  const arma::Mat<int> &SM = static_cast<ModelBox *>(model)->model.stoichiometry_matrix_;
+  std::memcpy(SM_colmajor, SM.memptr(), sizeof(int) * SM.n_elem);
   return 0;
 }
 int pfsp_model_destroy(void *model) { delete static_cast<ModelBox *>(model); return 0; }

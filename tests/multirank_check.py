@@ -41,6 +41,8 @@ def main():
     api.init(local_rank, dist)
     dev = torch.device("cuda", local_rank)
     ok = True
+    if rank == 0:
+        print("peer-memory fast path: %s" % ("on" if api.p2p_enabled() else "off (NCCL)"))
 
     # ---- 1. partitioned Action vs oracle ----
     from helpers import rel_err
@@ -62,7 +64,9 @@ def main():
         for t in (0.0, 4.0):
             xd = torch.from_numpy(xl).to(dev)
             yd = torch.empty_like(xd)
-            lat.action(t, xd, yd)
+            for rep in range(5):  # repeated calls walk through both parities of the double-buffered ghost windows
+                yd.fill_(float("nan"))
+                lat.action(t, xd if rep == 4 else xd * (rep + 2.0), yd)
             torch.cuda.synchronize()
             yg = gather_blocks(yd, sizes_rows, dev)   # states of rank 0.., then the K sinks of the last rank
             if rank == 0:
