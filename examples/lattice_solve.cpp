@@ -56,7 +56,7 @@ int main(int argc, char *argv[]) {
   const double t_build = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
   auto AV = [&](PetscReal t, Vec x, Vec y) { return A.Action(t, x, y); };
-  double wall_best = 1e300, psum = 0.0, l1err = -1.0;
+  double wall_best = 1e300, setup_best = 1e300, psum = 0.0, l1err = -1.0;
   long   nrhs = 0;
   int    stat = 0;
   for (int rep = 0; rep < repeat; ++rep) {
@@ -70,11 +70,14 @@ int main(int argc, char *argv[]) {
     fsp_device_sync();
     MPI_Barrier(PETSC_COMM_WORLD);
     auto   t1 = std::chrono::steady_clock::now();
+    double t_setup = 0.0;
     if (solver == "cvode") {
       CvodeFsp ode(PETSC_COMM_WORLD, CV_BDF);
       ode.SetFinalTime(t_final); ode.SetInitialSolution(&P); ode.SetRhs(AV); ode.SetTolerances(rtol, atol);
       ode.SetStatusOutput(0);
       if (ode.SetUp()) return 1;
+      fsp_device_sync();
+      t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
       stat = ode.Solve();
       nrhs = ode.GetNumRhsEvals();
       ode.FreeWorkspace();
@@ -84,6 +87,8 @@ int main(int argc, char *argv[]) {
       ode.SetTolerances(rtol, atol);
       ode.SetStatusOutput(0);
       if (ode.SetUp()) return 1;
+      fsp_device_sync();
+      t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
       stat = ode.Solve();
       nrhs = ode.GetNumRhsEvals();
       ode.FreeWorkspace();
@@ -91,7 +96,7 @@ int main(int argc, char *argv[]) {
     fsp_device_sync();
     MPI_Barrier(PETSC_COMM_WORLD);
     double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
-    if (wall < wall_best) wall_best = wall;
+    if (wall < wall_best) { wall_best = wall; setup_best = t_setup; }
     VecSum(P, &psum);
     if (rep == repeat - 1 && fsp.GetNumGlobalStates() <= 30000000) {
       // 1-norm error against the product of Poisson pmfs (local block, then summed over ranks)
@@ -121,9 +126,9 @@ int main(int argc, char *argv[]) {
   pacmensl_allreduce_sum(PETSC_COMM_WORLD, &bytes_tot, 1);
   if (rank == 0) {
     std::printf("{\"example\": \"lattice_solve\", \"solver\": \"%s\", \"ranks\": %d, \"edge\": %d, \"states\": %d, \"t_final\": %g, "
-                "\"rtol\": %g, \"atol\": %g, \"status\": %d, \"wall_s\": %.4f, \"build_s\": %.3f, \"action_calls\": %ld, "
+                "\"rtol\": %g, \"atol\": %g, \"status\": %d, \"wall_s\": %.4f, \"of_which_solver_setup_s\": %.4f, \"build_s\": %.3f, \"action_calls\": %ld, "
                 "\"us_per_action_incl_vector_ops\": %.2f, \"action_GBps_equiv\": %.1f, \"sum_p\": %.12f, \"l1_err_vs_poisson\": %.3e}\n",
-                solver.c_str(), size, edge, fsp.GetNumGlobalStates(), t_final, rtol, atol, stat, wall_best, t_build, nrhs,
+                solver.c_str(), size, edge, fsp.GetNumGlobalStates(), t_final, rtol, atol, stat, wall_best, setup_best, t_build, nrhs,
                 1e6 * wall_best / (double) std::max(1L, nrhs), bytes_tot * (double) nrhs / wall_best / 1e9, psum, l1err);
   }
   return stat == 0 ? 0 : 1;

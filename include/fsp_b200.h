@@ -52,6 +52,16 @@ FSP_API int         fsp_stream_wait_event(void *stream, void *event);
 FSP_API int         fsp_event_elapsed_ms(void *start, void *stop, float *ms); /* syncs on stop */
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 FSP_API long long   fsp_launch_count(void);
+/* CUDA graphs for launch-bound inner loops (the Arnoldi/IOP basis generation of KrylovFsp on small state sets):
+ * capture everything the library submits to `stream` (a stream from fsp_stream_create, not NULL) between begin and
+ * end, instantiate once, replay with one launch.  Kernels launched while capturing are not executed. */
+typedef struct fsp_graph_s *fsp_graph_t;
+FSP_API int         fsp_graph_begin_capture(void *stream);
+FSP_API int         fsp_graph_end_capture(void *stream, fsp_graph_t *out);
+FSP_API int         fsp_graph_abort_capture(void *stream);
+FSP_API int         fsp_graph_launch(fsp_graph_t g, void *stream);
+FSP_API int         fsp_graph_num_kernels(fsp_graph_t g, long *n);
+FSP_API int         fsp_graph_destroy(fsp_graph_t g);
 
 /* ------------------------------------------------------------------------------------------------
  * Device vectors (fp64).  Replaces the PETSc Vec BLAS-1 calls on the hot path:
@@ -105,6 +115,26 @@ FSP_API int fspvec_axpy_dot(double *w_dev, const double *h_dev, double sign, con
                             const double *u_dev, double *out_dev, long n, void *stream);
 /* w *= 1/sqrt(*normsq_dev)  (VecScale with a device-resident scalar; KrylovFsp.cpp:308) */
 FSP_API int fspvec_scale_rsqrt(double *w_dev, const double *normsq_dev, long n, void *stream);
+/* ---- fused passes of the BDF/Newton/GMRES integrator (replace chains of N_VLinearSum/N_VProd/N_VDiv/N_VWrmsNorm/
+ * N_VScale calls CVODE makes per step; src/OdeSolver/CvodeFsp.cpp:41-58 hands these to SUNDIALS) ------------------- */
+/* b = c0 x0 + c1 x1 + c2 x2 ; v = b .* w ; out = sum v_i^2   (Newton residual, scaled GMRES start vector, its norm and
+ * the WRMS norm of b in one pass) */
+FSP_API int fspvec_lincomb3_wprod_sqsum(double *b_dev, double *v_dev, double c0, const double *x0_dev, double c1,
+                                        const double *x1_dev, double c2, const double *x2_dev, const double *w_dev,
+                                        double *out_dev, long n, void *stream);
+/* v *= a ; t = v ./ w */
+FSP_API int fspvec_scale_div(double *v_dev, double a, double *t_dev, const double *w_dev, long n, void *stream);
+/* d = dw ? x ./ dw : x ; acor += d ; ycur = zn0 + acor ; out = sum (d_i ewt_i)^2   (end of a Newton iteration) */
+FSP_API int fspvec_newton_update(const double *x_dev, const double *dw_dev, const double *ewt_dev, double *acor_dev,
+                                 const double *zn0_dev, double *ycur_dev, double *out_dev, long n, void *stream);
+/* Nordsieck history array Z[0..L) (L <= 8, Z_dev_ptrs is a HOST array of device pointers): optional rescale
+ * Z[j] *= scale_host[j] for j >= 1 (scale_host == NULL: none), then the Pascal-triangle prediction (pascal = +1:
+ * for k = 1..L-1, j = L-1..k: Z[j-1] += Z[j]), its inverse (pascal = -1) or nothing (0) -- one pass, bit-identical to
+ * the sequence of separate scale/axpy calls (cvRescale, cvPredict, cvRestore of CVODE). */
+FSP_API int fspvec_nordsieck(double *const *Z_dev_ptrs, int L, const double *scale_host, int pascal, long n, void *stream);
+/* Z[j] += coef_host[j] * x for j < L  (history update after an accepted step, cvCompleteStep) */
+FSP_API int fspvec_multi_axpy(double *const *Z_dev_ptrs, int L, const double *coef_host, const double *x_dev, long n,
+                              void *stream);
 /* host-result conveniences (synchronise `stream`) */
 FSP_API int fspvec_dot_h(double *out_host, const double *x_dev, const double *y_dev, long n, void *stream);
 FSP_API int fspvec_norm2_h(double *out_host, const double *x_dev, long n, void *stream);

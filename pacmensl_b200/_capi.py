@@ -53,6 +53,12 @@ SIGNATURES = {
     "fsp_event_record": (ci, [vp, vp]),
     "fsp_stream_wait_event": (ci, [vp, vp]),
     "fsp_event_elapsed_ms": (ci, [vp, vp, C.POINTER(C.c_float)]),
+    "fsp_graph_begin_capture": (ci, [vp]),
+    "fsp_graph_end_capture": (ci, [vp, vpp]),
+    "fsp_graph_abort_capture": (ci, [vp]),
+    "fsp_graph_launch": (ci, [vp, vp]),
+    "fsp_graph_num_kernels": (ci, [vp, lp]),
+    "fsp_graph_destroy": (ci, [vp]),
     "fsp_launch_count": (C.c_longlong, []),
     "fspvec_set": (ci, [vp, cd, cl, vp]),
     "fspvec_copy": (ci, [vp, vp, cl, vp]),
@@ -74,6 +80,11 @@ SIGNATURES = {
     "fspvec_ratio_absmax": (ci, [vp, vp, vp, cd, cd, cl, vp]),
     "fspvec_axpy_dot": (ci, [vp, vp, cd, vp, vp, vp, cl, vp]),
     "fspvec_scale_rsqrt": (ci, [vp, vp, cl, vp]),
+    "fspvec_lincomb3_wprod_sqsum": (ci, [vp, vp, cd, vp, cd, vp, cd, vp, vp, vp, cl, vp]),
+    "fspvec_scale_div": (ci, [vp, cd, vp, vp, cl, vp]),
+    "fspvec_newton_update": (ci, [vp, vp, vp, vp, vp, vp, vp, cl, vp]),
+    "fspvec_nordsieck": (ci, [vp, ci, vp, ci, cl, vp]),
+    "fspvec_multi_axpy": (ci, [vp, ci, vp, vp, cl, vp]),
     "fspvec_dot_h": (ci, [dp, vp, vp, cl, vp]),
     "fspvec_norm2_h": (ci, [dp, vp, cl, vp]),
     "fspvec_sum_h": (ci, [dp, vp, cl, vp]),

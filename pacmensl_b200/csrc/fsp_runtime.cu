@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <vector>
 
 #include "fsp_common.cuh"
 
@@ -113,5 +114,76 @@ int fsp_event_elapsed_ms(void *a, void *b, float *ms) {
   return 0;
 }
 long long fsp_launch_count(void) { return g_launches.load(); }
+
+// ---- CUDA graphs for launch-bound inner loops -----------------------------------------------------
+struct fsp_graph_s {
+  cudaGraphExec_t exec = nullptr;
+  size_t          n_kernels = 0;
+};
+
+int fsp_graph_begin_capture(void *stream) {
+  if (!stream) { set_error("fsp_graph_begin_capture: the legacy default stream cannot be captured"); return -1; }
+  // relaxed: only work submitted to `stream` is captured; other streams/threads of the process are unaffected
+  FSP_CUDA_CHECK(cudaStreamBeginCapture((cudaStream_t) stream, cudaStreamCaptureModeRelaxed));
+  return 0;
+}
+
+int fsp_graph_end_capture(void *stream, fsp_graph_t *out) {
+  *out = nullptr;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture((cudaStream_t) stream, &g);
+  if (e != cudaSuccess || !g) {
+    cudaGetLastError();
+    set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    if (g) cudaGraphDestroy(g);
+    return -1;
+  }
+  fsp_graph_s *h = new fsp_graph_s();
+  size_t n_nodes = 0;
+  cudaGraphGetNodes(g, nullptr, &n_nodes);
+  if (n_nodes > 0) {
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    cudaGraphGetNodes(g, nodes.data(), &n_nodes);
+    for (size_t i = 0; i < n_nodes; ++i) {
+      cudaGraphNodeType t;
+      if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) h->n_kernels += 1;
+    }
+  }
+  e = cudaGraphInstantiate(&h->exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    delete h;
+    return -1;
+  }
+  count_launch(-(int) h->n_kernels);  // launches seen while capturing did not execute
+  *out = h;
+  return 0;
+}
+
+int fsp_graph_abort_capture(void *stream) {
+  cudaGraph_t g = nullptr;
+  cudaStreamEndCapture((cudaStream_t) stream, &g);
+  if (g) cudaGraphDestroy(g);
+  cudaGetLastError();
+  return 0;
+}
+
+int fsp_graph_launch(fsp_graph_t h, void *stream) {
+  FSP_CUDA_CHECK(cudaGraphLaunch(h->exec, resolve_stream(stream)));
+  // the kernels a replay launches were counted when they were captured, not now: count them per replay
+  count_launch((int) h->n_kernels);
+  return 0;
+}
+
+int fsp_graph_num_kernels(fsp_graph_t h, long *n) { *n = (long) h->n_kernels; return 0; }
+
+int fsp_graph_destroy(fsp_graph_t h) {
+  if (!h) return 0;
+  if (h->exec) cudaGraphExecDestroy(h->exec);
+  delete h;
+  return 0;
+}
 
 }  // extern "C"

@@ -304,6 +304,88 @@ struct AxpyDotF {
   }
 };
 
+// ---- fused passes of the BDF integrator (host/BdfCore.cpp) -------------------------------------------------------
+// b = c0 x0 + c1 x1 + c2 x2 ; v = b .* w ; acc = sum v^2     (Newton residual + GMRES start vector + both norms)
+struct Lc3WprodSqF {
+  double *b, *v; double c0; const double *x0; double c1; const double *x1; double c2; const double *x2; const double *w;
+  __device__ void operator()(long i, double (&acc)[1]) const {
+    const double bi = c0 * x0[i] + c1 * x1[i] + c2 * x2[i];
+    const double vi = bi * w[i];
+    b[i] = bi;
+    v[i] = vi;
+    acc[0] = fma(vi, vi, acc[0]);
+  }
+};
+// v *= a ; t = v ./ w      (normalise a Krylov vector and form the unscaled operand of the next J*v in one pass)
+struct ScaleDivF {
+  double *v; double a; double *t; const double *w;
+  __device__ void operator()(long i) const {
+    const double vi = v[i] * a;
+    v[i] = vi;
+    t[i] = vi / w[i];
+  }
+};
+// d = dw ? x ./ dw : x ; acor += d ; ycur = zn0 + acor ; acc = sum (d .* ewt)^2     (end of a Newton iteration)
+struct NewtonUpdateF {
+  const double *x, *dw, *ewt; double *acor; const double *zn0; double *ycur;
+  __device__ void operator()(long i, double (&acc)[1]) const {
+    const double e = ewt[i];
+    const double d = dw ? x[i] / dw[i] : x[i];
+    const double a = acor[i] + d;
+    acor[i] = a;
+    ycur[i] = zn0[i] + a;
+    const double de = d * e;
+    acc[0] = fma(de, de, acc[0]);
+  }
+};
+
+// Nordsieck history array Z[0..L) of the BDF integrator: optional rescale Z[j] *= f[j] (j >= 1), then the Pascal
+// triangle product (prediction, sign +1) or its inverse (restore, sign -1), all in registers: 16 L bytes per row
+// instead of 24 bytes per row for each of the L(L-1)/2 separate axpys.  Uses the same operation order and un-fused
+// roundings as the axpy sequence, so the result is bit-identical to it.
+constexpr int kMaxNord = 8;
+struct NordArgs {
+  double *Z[kMaxNord];
+  double  f[kMaxNord];
+};
+template <int L>
+__global__ void __launch_bounds__(kThreads) nordsieck_kernel(NordArgs a, int has_scale, int pascal, long n) {
+  const long stride = (long) gridDim.x * blockDim.x;
+  for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double z[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) z[j] = a.Z[j][i];
+    if (has_scale) {
+#pragma unroll
+      for (int j = 1; j < L; ++j) z[j] = __dmul_rn(z[j], a.f[j]);
+    }
+    if (pascal > 0) {
+#pragma unroll
+      for (int k = 1; k < L; ++k)
+#pragma unroll
+        for (int j = L - 1; j >= k; --j) z[j - 1] = __dadd_rn(z[j - 1], z[j]);
+    } else if (pascal < 0) {
+#pragma unroll
+      for (int k = 1; k < L; ++k)
+#pragma unroll
+        for (int j = L - 1; j >= k; --j) z[j - 1] = __dsub_rn(z[j - 1], z[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < L; ++j)
+      if (j < L - 1 ? (pascal != 0 || (has_scale && j >= 1)) : has_scale) a.Z[j][i] = z[j];
+  }
+}
+// Z[j] += c[j] x  for j < L   (BDF history update after an accepted step): 8 + 16 L bytes per row
+template <int L>
+__global__ void __launch_bounds__(kThreads) multi_axpy_kernel(NordArgs a, const double *__restrict__ x, long n) {
+  const long stride = (long) gridDim.x * blockDim.x;
+  for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double xi = x[i];
+#pragma unroll
+    for (int j = 0; j < L; ++j) a.Z[j][i] = __fma_rn(a.f[j], xi, a.Z[j][i]);
+  }
+}
+
 template <class F>
 int launch_map(F f, long n, void *stream) {
   if (n <= 0) return 0;
@@ -433,6 +515,51 @@ int fspvec_axpy_dot(double *w, const double *h, double sign, const double *v, co
   return launch_reduce<1, RED_SUM>(AxpyDotF{w, h, sign, v, u}, n, out, s);
 }
 int fspvec_scale_rsqrt(double *w, const double *nsq, long n, void *s) { return launch_map(ScaleRsqrtF{w, nsq}, n, s); }
+
+int fspvec_lincomb3_wprod_sqsum(double *b, double *v, double c0, const double *x0, double c1, const double *x1, double c2,
+                                const double *x2, const double *w, double *out, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(Lc3WprodSqF{b, v, c0, x0, c1, x1, c2, x2, w}, n, out, s);
+}
+int fspvec_scale_div(double *v, double a, double *t, const double *w, long n, void *s) {
+  return launch_map(ScaleDivF{v, a, t, w}, n, s);
+}
+int fspvec_newton_update(const double *x, const double *dw, const double *ewt, double *acor, const double *zn0,
+                         double *ycur, double *out, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(NewtonUpdateF{x, dw, ewt, acor, zn0, ycur}, n, out, s);
+}
+
+int fspvec_nordsieck(double *const *Z, int L, const double *scale, int pascal, long n, void *s) {
+  if (L < 1 || L > kMaxNord) { set_error("fspvec_nordsieck: L=%d out of range (1..%d)", L, kMaxNord); return -1; }
+  if (n <= 0 || (!scale && pascal == 0)) return 0;
+  NordArgs a;
+  for (int j = 0; j < L; ++j) { a.Z[j] = Z[j]; a.f[j] = scale ? scale[j] : 1.0; }
+  const int    hs = scale ? 1 : 0;
+  const int    grid = grid_for(n, 1);
+  cudaStream_t st = resolve_stream(s);
+  switch (L) {
+#define FSP_NORD(N) case N: nordsieck_kernel<N><<<grid, kThreads, 0, st>>>(a, hs, pascal, n); break;
+    FSP_NORD(1) FSP_NORD(2) FSP_NORD(3) FSP_NORD(4) FSP_NORD(5) FSP_NORD(6) FSP_NORD(7) FSP_NORD(8)
+#undef FSP_NORD
+  }
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fspvec_multi_axpy(double *const *Z, int L, const double *coef, const double *x, long n, void *s) {
+  if (L < 1 || L > kMaxNord) { set_error("fspvec_multi_axpy: L=%d out of range (1..%d)", L, kMaxNord); return -1; }
+  if (n <= 0) return 0;
+  NordArgs a;
+  for (int j = 0; j < L; ++j) { a.Z[j] = Z[j]; a.f[j] = coef[j]; }
+  const int    grid = grid_for(n, 1);
+  cudaStream_t st = resolve_stream(s);
+  switch (L) {
+#define FSP_MAX(N) case N: multi_axpy_kernel<N><<<grid, kThreads, 0, st>>>(a, x, n); break;
+    FSP_MAX(1) FSP_MAX(2) FSP_MAX(3) FSP_MAX(4) FSP_MAX(5) FSP_MAX(6) FSP_MAX(7) FSP_MAX(8)
+#undef FSP_MAX
+  }
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
 
 int fspvec_dot_h(double *out, const double *x, const double *y, long n, void *s) {
   double *tmp;

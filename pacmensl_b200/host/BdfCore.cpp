@@ -176,13 +176,35 @@ int BdfCore::initial_step(double tout) {
 }
 
 // ---- order / step adjustments ----------------------------------------------------------------------------------
+// History arrays zn_[0..q] (and the sensitivity histories) are transformed by ONE fused pass per call: optional
+// rescale, then prediction / restore (fspvec_nordsieck), bit-identical to CVODE's sequence of separate vector calls.
+void BdfCore::history_pass(const double *scale, int pascal, int q) {
+  double *Z[LMAX + 1];
+  for (int j = 0; j <= q; ++j) Z[j] = zn_[j]->d_data;
+  vec_status_ |= fspvec_nordsieck(Z, q + 1, scale, pascal, n_local_, stream_);
+  for (int is = 0; is < ns_; ++is) {
+    for (int j = 0; j <= q; ++j) Z[j] = znS_[is][j]->d_data;
+    vec_status_ |= fspvec_nordsieck(Z, q + 1, scale, pascal, n_local_, stream_);
+  }
+}
+
+void BdfCore::flush_scale() {
+  if (!scale_pending_) return;
+  history_pass(pending_scale_, 0, pending_q_);
+  scale_pending_ = false;
+}
+
 void BdfCore::rescale() {
+  // zn_[j] *= eta^j, j = 1..q (cvRescale): recorded here, applied inside the next prediction pass
+  flush_scale();
   double factor = eta_;
+  pending_scale_[0] = 1.0;
   for (int j = 1; j <= q_; ++j) {
-    vec_status_ |= fspvec_scale(zn_[j]->d_data, factor, n_local_, stream_);
-    for (int is = 0; is < ns_; ++is) vec_status_ |= fspvec_scale(znS_[is][j]->d_data, factor, n_local_, stream_);
+    pending_scale_[j] = factor;
     factor *= eta_;
   }
+  scale_pending_ = true;
+  pending_q_ = q_;
   h_ = hscale_ * eta_;
   next_h_ = h_;
   hscale_ = h_;
@@ -190,6 +212,7 @@ void BdfCore::rescale() {
 }
 
 void BdfCore::increase_bdf() {
+  flush_scale();
   for (int i = 0; i <= QMAX; ++i) l_[i] = 0.0;
   l_[2] = 1.0;
   double alpha1 = 1.0, prod = 1.0, xiold = 1.0, alpha0 = -1.0, hsum = hscale_;
@@ -215,6 +238,7 @@ void BdfCore::increase_bdf() {
 }
 
 void BdfCore::decrease_bdf() {
+  flush_scale();
   for (int i = 0; i <= QMAX; ++i) l_[i] = 0.0;
   l_[2] = 1.0;
   double hsum = 0.0;
@@ -247,23 +271,18 @@ void BdfCore::adjust_params() {
 }
 
 void BdfCore::predict() {
+  // cvPredict: for k = 1..q, j = q..k: zn[j-1] += zn[j]  -- with the pending rescale, one pass over the history
   tn_ += h_;
-  for (int k = 1; k <= q_; ++k)
-    for (int j = q_; j >= k; --j) {
-      vec_status_ |= fspvec_axpy(zn_[j - 1]->d_data, 1.0, zn_[j]->d_data, n_local_, stream_);
-      for (int is = 0; is < ns_; ++is)
-        vec_status_ |= fspvec_axpy(znS_[is][j - 1]->d_data, 1.0, znS_[is][j]->d_data, n_local_, stream_);
-    }
+  if (scale_pending_ && pending_q_ != q_) flush_scale();
+  history_pass(scale_pending_ ? pending_scale_ : nullptr, +1, q_);
+  scale_pending_ = false;
 }
 
 void BdfCore::restore(double saved_t) {
+  // cvRestore: the inverse Pascal product, one pass
   tn_ = saved_t;
-  for (int k = 1; k <= q_; ++k)
-    for (int j = q_; j >= k; --j) {
-      vec_status_ |= fspvec_axpy(zn_[j - 1]->d_data, -1.0, zn_[j]->d_data, n_local_, stream_);
-      for (int is = 0; is < ns_; ++is)
-        vec_status_ |= fspvec_axpy(znS_[is][j - 1]->d_data, -1.0, znS_[is][j]->d_data, n_local_, stream_);
-    }
+  flush_scale();
+  history_pass(nullptr, -1, q_);
 }
 
 void BdfCore::set_tq(double hsum, double alpha0, double alpha0_hat, double xi_inv, double xistar_inv) {
@@ -318,38 +337,37 @@ void BdfCore::set_coeffs() {
 }
 
 // ---- linear solver: scaled GMRES on (I - gamma J) x = b, x0 = 0 -----------------------------------------------------
-int BdfCore::atimes(Vec v, Vec z, double tn) {
-  njtv_ += 1;
-  int r = jtv_(tn, v, z);  // z = J v
-  if (r != 0) return r;
-  VCHK(fspvec_linear_sum(z->d_data, 1.0, v->d_data, -gamma_, z->d_data, n_local_, stream_));
+// sum over ranks of a device-resident partial sum
+int BdfCore::global_sum(const double *dev_scalar, double *out) {
+  double s = 0.0;
+  VCHK(fsp_memcpy_d2h(&s, dev_scalar, sizeof(double), stream_));
+  if (pacmensl_allreduce_sum(comm_, &s, 1)) return BDF_MEM_FAIL;
+  *out = s;
   return 0;
 }
 
-int BdfCore::lin_solve(Vec b, Vec ewt, Vec x, double tn, bool first_newton, int *converged) {
+// On entry V_[0] = s1 .* b (s1 = s2 = ewt) and ss_b = ||V_[0]||_2^2 (global), both produced by the fused residual pass of
+// nls().  On success the correction is  x = *xsrc ./ ewt  when *divide, else x = *xsrc; *xsrc == nullptr means x = 0.
+int BdfCore::lin_solve(Vec b, Vec ewt, double ss_b, double tn, bool first_newton, int *converged, Vec *xsrc, bool *divide) {
   *converged = 0;
+  *xsrc = nullptr;
+  *divide = false;
   const double deltar = EPLIFAC * tq_[4];
-  double       bnorm = 0.0;
-  if (wrms(b, ewt, &bnorm)) return BDF_MEM_FAIL;
+  const double bnorm = std::sqrt(ss_b / n_global_);  // WRMS norm of b with weights ewt
   if (bnorm <= deltar) {
     // right-hand side already below the tolerance: the correction is b itself on the first Newton iteration
     // and zero afterwards (CVODE's linear-solver interface returns b unchanged / zeroed in these two cases)
-    if (first_newton) VCHK(VecCopy(b, x));
-    else VCHK(fspvec_set(x->d_data, 0.0, n_local_, stream_));
+    if (first_newton) *xsrc = b;
     *converged = 1;
     return 0;
   }
   const double delta = deltar * std::sqrt(n_global_);
   const bool   multi = comm_ && comm_->size > 1;
-  VCHK(fspvec_set(x->d_data, 0.0, n_local_, stream_));
-  if (V_.empty()) { V_.push_back(nullptr); if (alloc_like(b, &V_[0])) return BDF_MEM_FAIL; }
-  // V0 = s1 .* b ; beta = ||V0||_2
-  VCHK(fspvec_prod(V_[0]->d_data, b->d_data, ewt->d_data, n_local_, stream_));
-  double beta = 0.0;
-  if (VecNorm(V_[0], NORM_2, &beta)) return BDF_MEM_FAIL;
-  double rho = beta;
+  const double beta = std::sqrt(ss_b);
+  double       rho = beta;
   if (rho <= delta) { *converged = 1; return 0; }
-  VCHK(fspvec_scale(V_[0]->d_data, 1.0 / beta, n_local_, stream_));
+  // V0 /= beta and vtemp = V0 ./ s2 in one pass
+  VCHK(fspvec_scale_div(V_[0]->d_data, 1.0 / beta, vtemp_->d_data, ewt->d_data, n_local_, stream_));
 
   const int lmax = maxl_;
   std::vector<std::vector<double>> Hes((size_t) lmax + 1, std::vector<double>((size_t) lmax, 0.0));
@@ -360,11 +378,11 @@ int BdfCore::lin_solve(Vec b, Vec ewt, Vec x, double tn, bool first_newton, int 
   for (int l = 0; l < lmax; ++l) {
     l_used = l + 1;
     if ((int) V_.size() < l + 2) { V_.push_back(nullptr); if (alloc_like(b, &V_[l + 1])) return BDF_MEM_FAIL; }
-    // vtemp = V_l ./ s2 ; w = A vtemp ; V_{l+1} = s1 .* w
-    VCHK(fspvec_div(vtemp_->d_data, V_[l]->d_data, ewt->d_data, n_local_, stream_));
-    int r = atimes(vtemp_, V_[l + 1], tn);
+    // w = J vtemp ; V_{l+1} = s1 .* (vtemp - gamma w)   (vtemp = V_l ./ s2 was formed by the previous fused pass)
+    njtv_ += 1;
+    int r = jtv_(tn, vtemp_, V_[l + 1]);
     if (r != 0) return r < 0 ? BDF_LSOLVE_FAIL : r;
-    VCHK(fspvec_prod(V_[l + 1]->d_data, V_[l + 1]->d_data, ewt->d_data, n_local_, stream_));
+    VCHK(fspvec_wlincomb(V_[l + 1]->d_data, ewt->d_data, 1.0, vtemp_->d_data, -gamma_, V_[l + 1]->d_data, n_local_, stream_));
     nli_ += 1;
     // modified Gram-Schmidt against V_0..V_l with device-resident coefficients:
     //   hd[0] = <w, V_0>, hd[l+2] = <w, w> (norm before orthogonalisation); then fused axpy+dot chain
@@ -409,7 +427,6 @@ int BdfCore::lin_solve(Vec b, Vec ewt, Vec x, double tn, bool first_newton, int 
       }
     }
     Hes[l + 1][l] = new_norm;
-    if (new_norm > 0.0) VCHK(fspvec_scale(w, 1.0 / new_norm, n_local_, stream_));
     // Givens QR update of column l
     {
       // apply previous rotations
@@ -432,6 +449,12 @@ int BdfCore::lin_solve(Vec b, Vec ewt, Vec x, double tn, bool first_newton, int 
       rho = std::fabs(rotation_product * beta);
     }
     if (rho <= delta) { conv = true; break; }
+    // another iteration follows: normalise V_{l+1} and form its unscaled copy vtemp = V_{l+1} ./ s2 in one pass (the
+    // last basis vector of a finished solve is never read, so it is neither normalised nor divided)
+    if (l + 1 < lmax && new_norm > 0.0)
+      VCHK(fspvec_scale_div(w, 1.0 / new_norm, vtemp_->d_data, ewt->d_data, n_local_, stream_));
+    else if (l + 1 < lmax)
+      VCHK(fspvec_div(vtemp_->d_data, w, ewt->d_data, n_local_, stream_));
   }
   // least-squares solution: yg = beta * Q e1 ; solve R yg = .
   const int lp1 = l_used + 1;
@@ -447,7 +470,7 @@ int BdfCore::lin_solve(Vec b, Vec ewt, Vec x, double tn, bool first_newton, int 
     yg[k] /= Hes[k][k];
     for (int i = k - 1; i >= 0; --i) yg[i] -= yg[k] * Hes[i][k];
   }
-  // x = (sum_k yg_k V_k) ./ s2
+  // xcor = sum_k yg_k V_k ; the unscaling x = xcor ./ s2 is fused into the Newton update of the caller
   {
     std::vector<const double *> ptrs((size_t) l_used);
     for (int k = 0; k < l_used; ++k) ptrs[k] = V_[k]->d_data;
@@ -457,8 +480,9 @@ int BdfCore::lin_solve(Vec b, Vec ewt, Vec x, double tn, bool first_newton, int 
       VCHK(fspvec_maxpy(xcor_->d_data, beta_y, mm, yg.data() + k0, ptrs.data() + k0, n_local_, stream_));
       beta_y = 1.0;
     }
-    VCHK(fspvec_div(x->d_data, xcor_->d_data, ewt->d_data, n_local_, stream_));
   }
+  *xsrc = xcor_;
+  *divide = true;
   // not converged within maxl iterations: accept if the residual was reduced (SUNLS_RES_REDUCED on the first
   // Newton iteration), otherwise a recoverable convergence failure
   if (!conv) {
@@ -479,20 +503,30 @@ int BdfCore::nls(Vec zn0, Vec zn1, Vec ewt, Vec acor, Vec ycur, Vec ftemp, int s
   else { r = fs_(sens_index, tn_, y_, ftemp_, zn0, ftemp); nfe_ += 0; }
   if (r < 0) return BDF_RHS_FAIL;
   if (r > 0) return CONV_FAIL;
-  VCHK(VecCopy(zn0, ycur));
+  if (V_.empty()) { V_.push_back(nullptr); if (alloc_like(zn0, &V_[0])) return BDF_MEM_FAIL; }
   double del = 0.0, delp = 0.0;
   int    m = 0;
   while (true) {
     nni_ += 1;
-    // b = gamma f(y) - rl1 zn1 - acor
-    VCHK(fspvec_lincomb3(tempv_->d_data, gamma_, ftemp->d_data, -rl1_, zn1->d_data, -1.0, acor->d_data, n_local_, stream_));
-    int conv = 0;
-    r = lin_solve(tempv_, ewt, delta_, tn_, m == 0, &conv);
+    // b = gamma f(y) - rl1 zn1 - acor ; V0 = s1 .* b ; ss = ||V0||^2 -- one pass (was lincomb3 + wrms + prod + norm)
+    double *red = hdev_.get() + maxl_ + 6;
+    VCHK(fspvec_lincomb3_wprod_sqsum(tempv_->d_data, V_[0]->d_data, gamma_, ftemp->d_data, -rl1_, zn1->d_data, -1.0,
+                                     acor->d_data, ewt->d_data, red, n_local_, stream_));
+    double ss_b = 0.0;
+    if (global_sum(red, &ss_b)) return BDF_MEM_FAIL;
+    int  conv = 0;
+    Vec  xsrc = nullptr;
+    bool divide = false;
+    r = lin_solve(tempv_, ewt, ss_b, tn_, m == 0, &conv, &xsrc, &divide);
     if (r < 0) return r;
     if (r > 0 || !conv) return CONV_FAIL;
-    if (wrms(delta_, ewt, &del)) return BDF_MEM_FAIL;
-    VCHK(fspvec_axpy(acor->d_data, 1.0, delta_->d_data, n_local_, stream_));
-    VCHK(fspvec_linear_sum(ycur->d_data, 1.0, zn0->d_data, 1.0, acor->d_data, n_local_, stream_));
+    // delta = xsrc (./ ewt) ; acor += delta ; ycur = zn0 + acor ; del = wrms(delta) -- one pass
+    if (!xsrc) { VCHK(fspvec_set(delta_->d_data, 0.0, n_local_, stream_)); xsrc = delta_; divide = false; }
+    VCHK(fspvec_newton_update(xsrc->d_data, divide ? ewt->d_data : nullptr, ewt->d_data, acor->d_data, zn0->d_data,
+                              ycur->d_data, red, n_local_, stream_));
+    double ss_d = 0.0;
+    if (global_sum(red, &ss_d)) return BDF_MEM_FAIL;
+    del = std::sqrt(ss_d / n_global_);
     if (m > 0) crate_ = std::max(CRDOWN * crate_, del / delp);
     const double dcon = del * std::min(1.0, crate_) / tq_[4];
     if (dcon <= 1.0) {
@@ -552,6 +586,7 @@ int BdfCore::do_error_test(double saved_t, int *nef, double *dsm, int *again) {
     return BDF_SUCCESS;
   }
   // already at order 1: restart the step from fresh derivative information
+  flush_scale();
   eta_ = std::max(ETAMIN, hmin_ / std::fabs(h_));
   h_ *= eta_;
   next_h_ = h_;
@@ -578,10 +613,15 @@ void BdfCore::complete_step() {
   for (int i = q_; i >= 2; --i) tau_[i] = tau_[i - 1];
   if (q_ == 1 && nst_ > 1) tau_[2] = tau_[1];
   tau_[1] = h_;
-  for (int j = 0; j <= q_; ++j) {
-    vec_status_ |= fspvec_axpy(zn_[j]->d_data, l_[j], acor_->d_data, n_local_, stream_);
-    for (int is = 0; is < ns_; ++is)
-      vec_status_ |= fspvec_axpy(znS_[is][j]->d_data, l_[j], acorS_[is]->d_data, n_local_, stream_);
+  {
+    // zn[j] += l[j] acor for j = 0..q in one pass (cvCompleteStep)
+    double *Z[LMAX + 1];
+    for (int j = 0; j <= q_; ++j) Z[j] = zn_[j]->d_data;
+    vec_status_ |= fspvec_multi_axpy(Z, q_ + 1, l_, acor_->d_data, n_local_, stream_);
+    for (int is = 0; is < ns_; ++is) {
+      for (int j = 0; j <= q_; ++j) Z[j] = znS_[is][j]->d_data;
+      vec_status_ |= fspvec_multi_axpy(Z, q_ + 1, l_, acorS_[is]->d_data, n_local_, stream_);
+    }
   }
   qwait_--;
   if (qwait_ == 1 && q_ != QMAX) {
@@ -764,6 +804,7 @@ int BdfCore::Step(double *t_reached, Vec yout, Vec *sout) {
 }
 
 int BdfCore::interpolate(double t, Vec *zn, Vec out) {
+  flush_scale();
   const double tfuzz0 = FUZZ_FACTOR * DBL_EPSILON * (std::fabs(tn_) + std::fabs(hu_));
   const double tfuzz = hu_ < 0.0 ? -tfuzz0 : tfuzz0;
   const double tp = tn_ - hu_ - tfuzz, tn1 = tn_ + tfuzz;

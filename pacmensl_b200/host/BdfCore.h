@@ -111,13 +111,18 @@ class BdfCore {
   void increase_bdf();
   void decrease_bdf();
   void rescale();
+  void history_pass(const double *scale, int pascal, int q);  ///< fused rescale + Pascal product over zn_ (and znS_)
+  int  pending_q_ = 0;
+  int  global_sum(const double *dev_scalar, double *out);
+  void flush_scale();                                  ///< apply a rescale that no prediction has absorbed yet
+  double pending_scale_[LMAX + 1] = {0};
+  bool   scale_pending_ = false;
   void predict();
   void restore(double saved_t);
   void set_coeffs();
   void set_tq(double hsum, double alpha0, double alpha0_hat, double xi_inv, double xistar_inv);
   int  nls(Vec zn0, Vec zn1, Vec ewt, Vec acor, Vec ycur, Vec ftemp, int sens_index, double *acnrm);
-  int  lin_solve(Vec b, Vec ewt, Vec x, double tn, bool first_newton, int *converged);
-  int  atimes(Vec v, Vec z, double tn);
+  int  lin_solve(Vec b, Vec ewt, double ss_b, double tn, bool first_newton, int *converged, Vec *xsrc, bool *divide);
   void complete_step();
   void prepare_next_step(double dsm);
   void set_eta();

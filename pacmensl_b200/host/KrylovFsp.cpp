@@ -1,6 +1,7 @@
 #include "KrylovFsp.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace pacmensl {
 
@@ -17,6 +18,7 @@ PetscInt KrylovFsp::Solve() {
   petsc_err = VecCopy(*solution_, solution_tmp_);
   CHKERRQ(petsc_err);
   t_now_tmp_ = t_now_;
+  DestroyGraphs_();  // the operator may have been regenerated since the last Solve(): captured pointers are stale
 
   int       stop = 0;
   PetscReal error_excess = 0.0;
@@ -199,27 +201,11 @@ int KrylovFsp::AdvanceOneStep(const Vec &v) {
 // src/OdeSolver/KrylovFsp.cpp:264-322 -- incomplete orthogonalisation procedure (modified Gram-Schmidt over the
 // last q_iop vectors).  Device pipeline per basis vector j (all asynchronous, coefficients stay on the device):
 //   w = A V_j ; h_0 = <w, V_i0> ; [w -= h_k V_ik ; h_{k+1} = <w, V_ik+1>]... ; w -= h_last V_j ; s^2 = <w, w> ; w /= s
-int KrylovFsp::GenerateBasis(const Vec &v, int m_start, PetscBool *happy_breakdown) {
-  int ierr, istart;
-
-  *happy_breakdown = PETSC_FALSE;
-  if (m_start >= m_) return 0;
-
-  k1 = 2;
-  mb = m_;
-
-  ierr = VecNorm(v, NORM_2, &beta);
-  CHKERRQ(ierr);
-  ierr = VecCopy(v, Vm[0]);
-  CHKERRQ(ierr);
-  ierr = VecScale(Vm[0], 1.0 / beta);
-  CHKERRQ(ierr);
-
-  istart = 0;
-  if (m_start == 0) Hm.zeros();
-
+// The column loop of GenerateBasis (src/OdeSolver/KrylovFsp.cpp:294-318) as an asynchronous device pipeline.
+int KrylovFsp::BasisColumns_(int m_start) {
+  int ierr, istart = 0;
   void      *stream = comm_->stream;
-  const long n = v->n_local;
+  const long n = Vm[0]->n_local;
   const int  stride = m_max_ + 2;  // coefficients of column j live at hdev_[j*stride ...]
   const bool multi = comm_size_ > 1;
 
@@ -244,6 +230,106 @@ int KrylovFsp::GenerateBasis(const Vec &v, int m_start, PetscBool *happy_breakdo
     // hcol[c] now holds ||w||^2
     FSPCHKERRQ(fspvec_scale_rsqrt(w, hcol + c, n, stream));
   }
+
+  return 0;
+}
+
+bool KrylovFsp::GraphsUsable_() {
+  static const bool env_on = [] { const char *e = std::getenv("FSP_KRYLOV_GRAPH"); return !(e && e[0] == '0'); }();
+  return env_on && !graphs_disabled_ && comm_size_ == 1;
+}
+
+void KrylovFsp::DestroyGraphs_() {
+  for (auto &kv : graphs_) fsp_graph_destroy(kv.second);
+  graphs_.clear();
+  graph_seen_.clear();
+}
+
+int KrylovFsp::EnsureBasis_(int count) {
+  count = std::min(count, (int) Vm.size());
+  int have = 0;
+  while (have < (int) Vm.size() && Vm[have]) ++have;
+  if (have >= count) return 0;
+  // the missing vectors come from ONE device block
+  Vec *fresh = nullptr;
+  int  ierr = VecDuplicateVecsUninitialized(*solution_, count - have, &fresh);
+  CHKERRQ(ierr);
+  for (int i = have; i < count; ++i) Vm[i] = fresh[i - have];
+  delete[] fresh;  // the array only; the vectors live on in Vm and keep their block alive
+  return 0;
+}
+
+int KrylovFsp::GenerateBasis(const Vec &v, int m_start, PetscBool *happy_breakdown) {
+  int ierr;
+
+  *happy_breakdown = PETSC_FALSE;
+  ierr = EnsureBasis_(m_ + 1);
+  CHKERRQ(ierr);
+  if (m_start >= m_) return 0;
+
+  k1 = 2;
+  mb = m_;
+
+  ierr = VecNorm(v, NORM_2, &beta);
+  CHKERRQ(ierr);
+  ierr = VecCopy(v, Vm[0]);
+  CHKERRQ(ierr);
+  ierr = VecScale(Vm[0], 1.0 / beta);
+  CHKERRQ(ierr);
+
+  if (m_start == 0) Hm.zeros();
+
+  // Launch-bound regime (small state sets: every kernel of the column loop lasts a few microseconds): the whole loop
+  // for a given (m_start, m) is captured once into a CUDA graph and replayed with one launch.  rhs_ is evaluated at
+  // t = 0 for every column (KrylovFsp.cpp:296), so the captured coefficients stay valid for the whole Solve().
+  const long key = (long) m_start * 4096 + m_;
+  bool       done = false;
+  if (GraphsUsable_()) {
+    auto it = graphs_.find(key);
+    if (it != graphs_.end()) {
+      if (fsp_graph_launch(it->second, comm_->stream) == 0) {
+        num_rhs_evals_ += m_ - m_start;
+        done = true;
+      } else {
+        DestroyGraphs_();
+        graphs_disabled_ = true;
+      }
+    } else if (++graph_seen_[key] >= 2) {  // second time this shape is needed: worth capturing
+      if (!capture_stream_ && fsp_stream_create(&capture_stream_)) graphs_disabled_ = true;
+      if (!graphs_disabled_) {
+        void *saved = comm_->stream;
+        comm_->stream = capture_stream_;  // everything this rank submits now goes to the capturing stream
+        long rhs_before = num_rhs_evals_;
+        int  cerr = fsp_graph_begin_capture(capture_stream_);
+        if (cerr == 0) cerr = BasisColumns_(m_start);
+        comm_->stream = saved;
+        fsp_graph_t g = nullptr;
+        long        nk = 0, expect = 0;
+        for (int j = m_start; j < m_; ++j) expect += 3 + (j - ((q_iop > 0 && j - q_iop + 1 >= 0) ? j - q_iop + 1 : 0) + 1);
+        if (cerr != 0) {
+          fsp_graph_abort_capture(capture_stream_);
+        } else if (fsp_graph_end_capture(capture_stream_, &g) == 0) {
+          fsp_graph_num_kernels(g, &nk);
+          if (nk >= expect && fsp_graph_launch(g, comm_->stream) == 0) {
+            graphs_[key] = g;
+            done = true;
+          } else {
+            fsp_graph_destroy(g);  // part of the work bypassed the capturing stream: not capturable
+          }
+        }
+        if (!done) {  // fall back to plain launches for the rest of this solver's life (a genuine rhs_ error repeats below)
+          num_rhs_evals_ = rhs_before;
+          graphs_disabled_ = true;
+        }
+      }
+    }
+  }
+  if (!done) {
+    ierr = BasisColumns_(m_start);
+    PACMENSLCHKERRQ(ierr);
+  }
+  void     *stream = comm_->stream;
+  const int stride = m_max_ + 2;
 
   // one transfer of all coefficients, then the (deferred) happy-breakdown test
   const int ncols = m_ - m_start;
@@ -276,14 +362,14 @@ int KrylovFsp::SetUpWorkSpace() {
     return -1;
   }
   int ierr;
-  Vm.resize(m_max_ + 1);
-  for (int i{0}; i < m_max_ + 1; ++i) {
-    ierr = VecDuplicate(*solution_, &Vm[i]);
-    CHKERRQ(ierr);
-  }
-  ierr = VecDuplicate(*solution_, &av);
+  // The reference allocates all m_max+1 basis vectors up front (:334-340).  Here the basis vectors are created when
+  // the adaptive dimension m first needs them (EnsureBasis_): with the default range [25, 60] a solve that never
+  // raises m holds 26 instead of 61 vectors -- at 1e8 states that is 28 GB less HBM and no allocation/zero-fill of
+  // memory that is never touched.  Workspace vectors are always written before they are read: no zero-fill.
+  Vm.assign((size_t) m_max_ + 1, nullptr);
+  ierr = VecDuplicateUninitialized(*solution_, &av);
   CHKERRQ(ierr);
-  ierr = VecDuplicate(*solution_, &solution_tmp_);
+  ierr = VecDuplicateUninitialized(*solution_, &solution_tmp_);
   CHKERRQ(ierr);
 
   first_step_initialized_ = false;
@@ -333,11 +419,16 @@ int KrylovFsp::GetDky(PetscReal t, int deg, Vec p_vec) {
   return 0;
 }
 
-KrylovFsp::~KrylovFsp() { FreeWorkspace(); }
+KrylovFsp::~KrylovFsp() {
+  FreeWorkspace();
+  if (capture_stream_) fsp_stream_destroy(capture_stream_);
+}
 
 int KrylovFsp::FreeWorkspace() {
   OdeSolverBase::FreeWorkspace();
-  for (size_t i{0}; i < Vm.size(); ++i) VecDestroy(&Vm[i]);
+  DestroyGraphs_();
+  for (size_t i{0}; i < Vm.size(); ++i)
+    if (Vm[i]) VecDestroy(&Vm[i]);
   Vm.clear();
   if (av != nullptr) VecDestroy(&av);
   if (solution_tmp_ != nullptr) VecDestroy(&solution_tmp_);

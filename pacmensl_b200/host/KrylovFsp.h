@@ -4,6 +4,8 @@
 // basis vector 1 Action + (q + 1) fused MGS passes + 1 scale, no host synchronisation inside the loop.
 #pragma once
 
+#include <map>
+
 #include "OdeSolverBase.h"
 
 namespace pacmensl {
@@ -46,6 +48,15 @@ class PACMENSL_API KrylovFsp : public OdeSolverBase {
   std::vector<double>  hhost_;
 
   int SetUpWorkSpace();
+  int EnsureBasis_(int count);  ///< create basis vectors Vm[0..count) on first use
+  int BasisColumns_(int m_start);  ///< the column loop of GenerateBasis as an asynchronous device pipeline
+  // CUDA graphs of the column loop, keyed by (m_start, m); single rank only (FSP_KRYLOV_GRAPH=0 disables)
+  std::map<long, fsp_graph_t> graphs_;
+  std::map<long, int>         graph_seen_;
+  void                       *capture_stream_ = nullptr;
+  bool                        graphs_disabled_ = false;
+  bool GraphsUsable_();
+  void DestroyGraphs_();
   int GenerateBasis(const Vec &v, int m_start, PetscBool *happy_breakdown);
   int AdvanceOneStep(const Vec &v);
   int GetDky(PetscReal t, int deg, Vec p_vec);

@@ -42,12 +42,19 @@ void solve(M P, M &Q) {
       for (uword j = 0; j < m; ++j) std::swap(Q(k, j), Q(piv, j));
     }
     const double inv = 1.0 / P(k, k);
-    for (uword i = k + 1; i < n; ++i) {
-      const double f = P(i, k) * inv;
-      if (f == 0.0) continue;
-      P(i, k) = 0.0;
-      for (uword j = k + 1; j < n; ++j) P(i, j) -= f * P(k, j);
-      for (uword j = 0; j < m; ++j) Q(i, j) -= f * Q(k, j);
+    double      *lk = P.colptr(k);  // multipliers stored in place of the eliminated column
+    for (uword i = k + 1; i < n; ++i) lk[i] *= inv;
+    for (uword j = k + 1; j < n; ++j) {  // column-major friendly rank-1 update
+      double      *pj = P.colptr(j);
+      const double pkj = pj[k];
+      if (pkj == 0.0) continue;
+      for (uword i = k + 1; i < n; ++i) pj[i] -= lk[i] * pkj;
+    }
+    for (uword j = 0; j < m; ++j) {
+      double      *qj = Q.colptr(j);
+      const double qkj = qj[k];
+      if (qkj == 0.0) continue;
+      for (uword i = k + 1; i < n; ++i) qj[i] -= lk[i] * qkj;
     }
   }
   for (uword j = 0; j < m; ++j)
@@ -59,10 +66,36 @@ void solve(M P, M &Q) {
 }
 }  // namespace
 
+static Mat<double> expmat_dense(const Mat<double> &Ain);
+
+// exp of a square matrix.  The Krylov matrix handed in by KrylovFsp is (m_max+2)^2 = 62x62 with only its leading
+// (m+2)x(m+2) block non-zero; exp([[B,0],[0,0]]) = [[exp(B),0],[0,I]] and every step of the Pade/scaling-squaring
+// arithmetic preserves that block structure exactly (the trailing block only ever holds multiples of I), so the
+// work is done on the active block: same result, (m+2)^3 instead of 62^3 flops on the host between two basis
+// generations.
 Mat<double> expmat(const Mat<double> &Ain) {
   if (Ain.n_rows != Ain.n_cols) throw std::logic_error("expmat: matrix must be square");
   const uword n = Ain.n_rows;
   if (n == 0) return Ain;
+  uword na = 0;  // active size: 1 + largest row/column index holding a non-zero
+  for (uword j = 0; j < n; ++j)
+    for (uword i = 0; i < n; ++i)
+      if (Ain(i, j) != 0.0) na = std::max(na, std::max(i, j) + 1);
+  if (na == n) return expmat_dense(Ain);
+  Mat<double> out(n, n, fill::zeros);
+  for (uword i = 0; i < n; ++i) out(i, i) = 1.0;
+  if (na == 0) return out;
+  Mat<double> B(na, na);
+  for (uword j = 0; j < na; ++j)
+    for (uword i = 0; i < na; ++i) B(i, j) = Ain(i, j);
+  Mat<double> E = expmat_dense(B);
+  for (uword j = 0; j < na; ++j)
+    for (uword i = 0; i < na; ++i) out(i, j) = E(i, j);
+  return out;
+}
+
+static Mat<double> expmat_dense(const Mat<double> &Ain) {
+  const uword n = Ain.n_rows;
   static const double b[14] = {64764752532480000.0, 32382376266240000.0, 7771770303897600.0, 1187353796428800.0,
                                129060195264000.0,   10559470521600.0,    670442572800.0,     33522128640.0,
                                1323241920.0,        40840800.0,          960960.0,           16380.0,

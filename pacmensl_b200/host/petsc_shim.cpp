@@ -123,7 +123,7 @@ PetscErrorCode VecDestroy(Vec *v) {
   return 0;
 }
 
-PetscErrorCode VecDuplicate(Vec v, Vec *out) {
+static PetscErrorCode vec_duplicate(Vec v, Vec *out, bool zero) {
   if (!v->d_data && v->n_local >= 0) { PetscErrorCode e = VecSetUp(v); if (e) return e; }
   Vec w = new _p_Vec();
   w->comm = v->comm;
@@ -132,10 +132,47 @@ PetscErrorCode VecDuplicate(Vec v, Vec *out) {
   w->own_start = v->own_start;
   PetscErrorCode ierr = fsp_malloc((void **) &w->d_data, sizeof(double) * (size_t) (w->n_local > 0 ? w->n_local : 1));
   if (ierr) { delete w; return ierr; }
-  ierr = fspvec_set(w->d_data, 0.0, w->n_local, S(w));
+  if (zero) ierr = fspvec_set(w->d_data, 0.0, w->n_local, S(w));
   *out = w;
   return ierr;
 }
+static PetscErrorCode vec_duplicate_vecs(Vec v, PetscInt m, Vec **V, bool zero) {
+  *V = nullptr;
+  if (m <= 0) return 0;
+  if (!v->d_data && v->n_local >= 0) { PetscErrorCode e = VecSetUp(v); if (e) return e; }
+  const size_t n = (size_t) (v->n_local > 0 ? v->n_local : 1);
+  const size_t stride = (n + 31) / 32 * 32;  // every vector starts 256-byte aligned
+  double *block = nullptr;
+  PetscErrorCode ierr = fsp_malloc((void **) &block, sizeof(double) * stride * (size_t) m);
+  if (ierr) return ierr;
+  std::shared_ptr<void> slab(block, [](void *p) { fsp_free(p); });
+  if (zero) { ierr = fspvec_set(block, 0.0, (long) (stride * (size_t) m), S(v)); if (ierr) return ierr; }
+  Vec *arr = new Vec[(size_t) m];
+  for (PetscInt i = 0; i < m; ++i) {
+    Vec w = new _p_Vec();
+    w->comm = v->comm;
+    w->n_local = v->n_local;
+    w->n_global = v->n_global;
+    w->own_start = v->own_start;
+    w->d_data = block + stride * (size_t) i;
+    w->owns_data = false;
+    w->slab = slab;
+    arr[i] = w;
+  }
+  *V = arr;
+  return 0;
+}
+PetscErrorCode VecDuplicateVecs(Vec v, PetscInt m, Vec **V) { return vec_duplicate_vecs(v, m, V, true); }
+PetscErrorCode VecDuplicateVecsUninitialized(Vec v, PetscInt m, Vec **V) { return vec_duplicate_vecs(v, m, V, false); }
+PetscErrorCode VecDestroyVecs(PetscInt m, Vec **V) {
+  if (!V || !*V) return 0;
+  for (PetscInt i = 0; i < m; ++i) VecDestroy(&(*V)[i]);
+  delete[] *V;
+  *V = nullptr;
+  return 0;
+}
+PetscErrorCode VecDuplicate(Vec v, Vec *out) { return vec_duplicate(v, out, true); }
+PetscErrorCode VecDuplicateUninitialized(Vec v, Vec *out) { return vec_duplicate(v, out, false); }
 
 PetscErrorCode VecSet(Vec v, PetscScalar a) {
   if (!v->d_data) { PetscErrorCode e = VecSetUp(v); if (e) return e; }
