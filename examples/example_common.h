@@ -13,6 +13,7 @@
 
 inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, const char *custom_fixture) {
   using namespace pacmensl;
+  std::setvbuf(stdout, nullptr, _IOLBF, 0);  // keep diagnostics if the solve throws
   Environment my_env(&argc, &argv, nullptr);
   std::string solver = "cvode", constraints = "default";
   double      t_final_override = -1.0;

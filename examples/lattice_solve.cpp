@@ -4,7 +4,7 @@
 //   (edge^3 states), one rank per GPU (tools/launch_ranks.sh N build/examples/lattice_solve ...).
 // The three species are independent M/M/inf queues started empty, so p(t_f) is the product of three Poisson
 // pmfs with means (b_s/gamma_s)(1 - exp(-gamma_s t_f)); for N <= 3e7 the 1-norm error against it is reported.
-//   usage: lattice_solve [--edge 215] [--solver krylov|cvode] [--tfinal 1.0] [--rtol 1e-6] [--atol 1e-14] [--repeat 1]
+//   usage: lattice_solve [--edge 215] [--solver krylov|cvode] [--tfinal 1.0] [--rtol 1e-6] [--atol 1e-14] [--repeat 1] [--no-fused]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -56,6 +56,9 @@ int main(int argc, char *argv[]) {
   const double t_build = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
   auto AV = [&](PetscReal t, Vec x, Vec y) { return A.Action(t, x, y); };
+  auto AVF = [&](PetscReal t, Vec x, Vec y, const fspmat_epilogue &ep) { return A.ActionFused(t, x, y, ep); };
+  bool fused = true;
+  for (int i = 1; i < argc; ++i) if (!std::strcmp(argv[i], "--no-fused")) fused = false;
   double wall_best = 1e300, setup_best = 1e300, psum = 0.0, l1err = -1.0;
   long   nrhs = 0;
   int    stat = 0;
@@ -74,6 +77,7 @@ int main(int argc, char *argv[]) {
     if (solver == "cvode") {
       CvodeFsp ode(PETSC_COMM_WORLD, CV_BDF);
       ode.SetFinalTime(t_final); ode.SetInitialSolution(&P); ode.SetRhs(AV); ode.SetTolerances(rtol, atol);
+      if (fused) ode.SetFusedRhs(AVF);
       ode.SetStatusOutput(0);
       if (ode.SetUp()) return 1;
       fsp_device_sync();
@@ -84,6 +88,7 @@ int main(int argc, char *argv[]) {
     } else {
       KrylovFsp ode(PETSC_COMM_WORLD);
       ode.SetFinalTime(t_final); ode.SetInitialSolution(&P); ode.SetRhs(AV); ode.SetFspMatPtr(&A);
+      if (fused) ode.SetFusedRhs(AVF);
       ode.SetTolerances(rtol, atol);
       ode.SetStatusOutput(0);
       if (ode.SetUp()) return 1;

@@ -39,6 +39,9 @@ FSP_API int         fsp_malloc_host(void **ptr_host, size_t bytes); /* pinned */
 FSP_API int         fsp_free_host(void *ptr_host);
 FSP_API int         fsp_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
 FSP_API int         fsp_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+/* asynchronous variants: the host buffer must be pinned (fsp_malloc_host) and stay valid until the stream reaches the copy */
+FSP_API int         fsp_memcpy_h2d_async(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+FSP_API int         fsp_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void *stream);
 FSP_API int         fsp_memcpy_d2d(void *dst_dev, const void *src_dev, size_t bytes, void *stream);
 FSP_API int         fsp_memset(void *dst_dev, int byte, size_t bytes, void *stream);
 FSP_API int         fsp_stream_create(void **stream);
@@ -48,6 +51,7 @@ FSP_API int         fsp_device_sync(void);
 FSP_API int         fsp_event_create(void **event);
 FSP_API int         fsp_event_destroy(void *event);
 FSP_API int         fsp_event_record(void *event, void *stream);
+FSP_API int         fsp_event_sync(void *event);
 FSP_API int         fsp_stream_wait_event(void *stream, void *event);
 FSP_API int         fsp_event_elapsed_ms(void *start, void *stop, float *ms); /* syncs on stop */
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
@@ -256,6 +260,22 @@ FSP_API int fspmat_clear(fspmat_t h); /* Destroy(): frees values, object reusabl
  * (K doubles) instead of y; pass NULL to drop them. */
 FSP_API int fspmat_action(fspmat_t h, const double *coef_host, const double *x_dev, const double *ghost_dev,
                           double *y_dev, double *sink_out_dev, void *stream);
+/* Action with a fused epilogue, for the solver loops that would otherwise re-read y in separate passes (single GPU):
+ *   y = scale .* (beta x + alpha A(t) x)      (scale_dev == NULL: no scaling; applies to the K sink rows too)
+ *   dot_out_dev[k] = <y, dot_vec_dev[k]> for k < n_dots <= 2   (dot_vec_dev[k] == NULL: <y, y>)
+ * KrylovFsp: alpha = 1, beta = 0, one dot with the first basis vector of the orthogonalisation window
+ * (KrylovFsp.cpp:296-305).  CVODE's scaled GMRES: y = s1 .* (v - gamma J v), <y, V_0>, <y, y>.
+ * Inner products are accumulated per CTA and summed in a fixed order: deterministic. */
+typedef struct fspmat_epilogue {
+  double        alpha, beta;
+  const double *scale_dev;
+  int           n_dots;
+  const double *dot_vec_dev[2];
+  double       *dot_out_dev;
+} fspmat_epilogue;
+FSP_API int fspmat_fused_supported(fspmat_t h); /* 1: fspmat_action_fused can be used (values present, no ghost columns) */
+FSP_API int fspmat_action_fused(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev,
+                                const fspmat_epilogue *ep, void *stream);
 /* Split action for overlapping the halo exchange with compute (multi-GPU):
  *   phase 1  interior pass: all rows with ghost entries counted as 0, no sink rows (ghost_dev unused)
  *   phase 2  boundary rows only (the rows that reference ghost slots; needs ghost_dev) -- run after phase 1
@@ -272,6 +292,15 @@ FSP_API int fspmat_action_sinks_p2p(fspmat_t h, const double *coef_host, const d
                                     const struct fsphalo_epoch *e, void *stream);
 FSP_API int fspmat_action_boundary_p2p(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev,
                                        const struct fsphalo_epoch *e, void *stream);
+/* The whole multi-GPU action as ONE kernel: CTAs whose rows reference no ghost entry run first, the CTAs with ghost rows
+ * wait in device code for the peers' flags, a trailing CTA on the sink owner adds the sink slots.  Every row is
+ * computed once (no interior pass + redo), and there is no kernel boundary between local and halo-dependent work. */
+FSP_API int fspmat_action_p2p(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev,
+                              const struct fsphalo_epoch *e, void *stream);
+/* CTAs of fspmat_action_p2p that never wait (no ghost rows) / all CTAs.  The host uses it to decide whether the push
+ * kernel must be complete before the action kernel starts (few ghost-free CTAs: waiting CTAs could otherwise occupy
+ * every SM slot before this GPU's own push kernel has been scheduled). */
+FSP_API int fspmat_p2p_cta_counts(fspmat_t h, long *n_interior, long *n_total);
 FSP_API int fspmat_flops(fspmat_t h, long *nflops);
 FSP_API int fspmat_num_rows(fspmat_t h, int *n_rows);
 /* algorithmic bytes of one Action: n*(16 + 12 P + 8 (n_tv + [n_ti>0])) + 12 nnz_sink + 8 K */

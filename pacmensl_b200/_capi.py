@@ -29,6 +29,10 @@ class FspMatDesc(C.Structure):
     ]
 
 
+class FspMatEpilogue(C.Structure):
+    _fields_ = [("alpha", cd), ("beta", cd), ("scale_dev", vp), ("n_dots", ci), ("dot_vec_dev", vp * 2), ("dot_out_dev", vp)]
+
+
 # name -> (restype, argtypes); every symbol include/fsp_b200.h declares
 SIGNATURES = {
     "fsp_device_count": (ci, [ip]),
@@ -43,6 +47,8 @@ SIGNATURES = {
     "fsp_memcpy_h2d": (ci, [vp, vp, C.c_size_t, vp]),
     "fsp_memcpy_d2h": (ci, [vp, vp, C.c_size_t, vp]),
     "fsp_memcpy_d2d": (ci, [vp, vp, C.c_size_t, vp]),
+    "fsp_memcpy_h2d_async": (ci, [vp, vp, C.c_size_t, vp]),
+    "fsp_memcpy_d2h_async": (ci, [vp, vp, C.c_size_t, vp]),
     "fsp_memset": (ci, [vp, ci, C.c_size_t, vp]),
     "fsp_stream_create": (ci, [vpp]),
     "fsp_stream_destroy": (ci, [vp]),
@@ -52,6 +58,7 @@ SIGNATURES = {
     "fsp_event_destroy": (ci, [vp]),
     "fsp_event_record": (ci, [vp, vp]),
     "fsp_stream_wait_event": (ci, [vp, vp]),
+    "fsp_event_sync": (ci, [vp]),
     "fsp_event_elapsed_ms": (ci, [vp, vp, C.POINTER(C.c_float)]),
     "fsp_graph_begin_capture": (ci, [vp]),
     "fsp_graph_end_capture": (ci, [vp, vpp]),
@@ -116,8 +123,12 @@ SIGNATURES = {
     "fspmat_action": (ci, [vp, dp, vp, vp, vp, vp, vp]),
     "fspmat_action_phase": (ci, [vp, dp, vp, vp, vp, vp, ci, vp]),
     "fspmat_num_boundary_rows": (ci, [vp, lp]),
+    "fspmat_fused_supported": (ci, [vp]),
+    "fspmat_action_fused": (ci, [vp, dp, vp, vp, vp, vp]),
     "fspmat_action_sinks_p2p": (ci, [vp, dp, vp, vp, vp]),
     "fspmat_action_boundary_p2p": (ci, [vp, dp, vp, vp, vp, vp]),
+    "fspmat_action_p2p": (ci, [vp, dp, vp, vp, vp, vp]),
+    "fspmat_p2p_cta_counts": (ci, [vp, lp, lp]),
     "fspmat_flops": (ci, [vp, lp]),
     "fspmat_num_rows": (ci, [vp, ip]),
     "fspmat_action_bytes": (ci, [vp, dp]),

@@ -65,14 +65,39 @@ int fsp_malloc(void **p, size_t bytes) { FSP_CUDA_CHECK(pool_malloc_bytes(p, byt
 int fsp_free(void *p) { if (p) FSP_CUDA_CHECK(pool_free(p)); return 0; }
 int fsp_malloc_host(void **p, size_t bytes) { FSP_CUDA_CHECK(cudaMallocHost(p, bytes ? bytes : 8)); return 0; }
 int fsp_free_host(void *p) { if (p) FSP_CUDA_CHECK(cudaFreeHost(p)); return 0; }
+// Small transfers (solver scalars, Hessenberg columns, sink entries: a few doubles, many times per step) are staged
+// through a per-thread pinned buffer: a copy to/from pageable memory goes through the driver's own staging path and
+// costs about twice the latency.
+static constexpr size_t kStageBytes = 8192;
+static void *stage_buffer() {
+  static thread_local void *buf = nullptr;
+  if (!buf && cudaMallocHost(&buf, kStageBytes) != cudaSuccess) { buf = nullptr; cudaGetLastError(); }
+  return buf;
+}
 int fsp_memcpy_h2d(void *d, const void *s, size_t b, void *st) {
-  FSP_CUDA_CHECK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, resolve_stream(st)));
+  void *stage = b <= kStageBytes ? stage_buffer() : nullptr;
+  if (stage) {
+    memcpy(stage, s, b);
+    FSP_CUDA_CHECK(cudaMemcpyAsync(d, stage, b, cudaMemcpyHostToDevice, resolve_stream(st)));
+  } else {
+    FSP_CUDA_CHECK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, resolve_stream(st)));
+  }
   FSP_CUDA_CHECK(cudaStreamSynchronize(resolve_stream(st)));
   return 0;
 }
 int fsp_memcpy_d2h(void *d, const void *s, size_t b, void *st) {
-  FSP_CUDA_CHECK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, resolve_stream(st)));
+  void *stage = b <= kStageBytes ? stage_buffer() : nullptr;
+  FSP_CUDA_CHECK(cudaMemcpyAsync(stage ? stage : d, s, b, cudaMemcpyDeviceToHost, resolve_stream(st)));
   FSP_CUDA_CHECK(cudaStreamSynchronize(resolve_stream(st)));
+  if (stage) memcpy(d, stage, b);
+  return 0;
+}
+int fsp_memcpy_h2d_async(void *d, const void *s, size_t b, void *st) {
+  FSP_CUDA_CHECK(cudaMemcpyAsync(d, s, b, cudaMemcpyHostToDevice, resolve_stream(st)));
+  return 0;
+}
+int fsp_memcpy_d2h_async(void *d, const void *s, size_t b, void *st) {
+  FSP_CUDA_CHECK(cudaMemcpyAsync(d, s, b, cudaMemcpyDeviceToHost, resolve_stream(st)));
   return 0;
 }
 int fsp_memcpy_d2d(void *d, const void *s, size_t b, void *st) {
@@ -104,6 +129,7 @@ int fsp_event_create(void **e) {
 }
 int fsp_event_destroy(void *e) { if (e) FSP_CUDA_CHECK(cudaEventDestroy((cudaEvent_t) e)); return 0; }
 int fsp_event_record(void *e, void *s) { FSP_CUDA_CHECK(cudaEventRecord((cudaEvent_t) e, resolve_stream(s))); return 0; }
+int fsp_event_sync(void *e) { FSP_CUDA_CHECK(cudaEventSynchronize((cudaEvent_t) e)); return 0; }
 int fsp_stream_wait_event(void *s, void *e) {
   FSP_CUDA_CHECK(cudaStreamWaitEvent(resolve_stream(s), (cudaEvent_t) e, 0));
   return 0;

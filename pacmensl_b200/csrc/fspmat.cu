@@ -62,9 +62,24 @@ struct MatView {
   int           ghost_zero;    // 1: ghost entries contribute 0 (interior pass, halo still in flight)
   const int    *row_list;      // non-null: process only these rows (boundary pass); n = list length
   int           write_y_sinks; // 0: sink role writes only sink_out (the owner copies the reduced values later)
+  const int    *cta_order;     // single-kernel peer-memory action: CTAs without ghost rows first, the others last
+  int           n_interior_ctas;
   // peer-memory mode: sink_out is the sink owner's slot row of this rank; publish this flag after writing it
   unsigned long long *sink_flag_remote;
   unsigned long long  sink_epoch;
+};
+
+// Fused epilogue of the single-GPU action (fspmat_action_fused): y = scale .* (beta x + alpha A x) and up to two
+// inner products of y, accumulated through per-CTA partials and summed in a fixed order by the last CTA.
+struct Epi {
+  double        alpha, beta;
+  const double *scale;
+  int           n_dots;
+  const double *vec[2];
+  double       *out;
+  double       *partials;  // [(G + 1) * 2]: G main CTAs + one slot for the sink rows
+  unsigned     *counter;
+  int           G;
 };
 
 struct P2PWait {
@@ -304,6 +319,120 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_lean(MatView m, Coefs 
   y[i] = fma(-d, __ldg(x + i), acc);
 }
 
+// Action with fused epilogue (solver hot loops): grid-stride over the rows with G CTAs so that the per-CTA partial
+// inner products stay few; the K sink rows get the same epilogue in the last-arriving sink CTA.
+template <int P>
+__global__ void __launch_bounds__(kThreads) fsp_action_epi(MatView m, Coefs cf, Epi e, const double *__restrict__ x,
+                                                           double *__restrict__ y) {
+  __shared__ double red[32];
+  __shared__ bool   last_cta;
+  double            d0 = 0.0, d1 = 0.0;
+  if ((int) blockIdx.x >= m.main_blocks) {
+    // ---- sink rows: partial sums per chunk, then the last sink CTA finishes rows n..n+K-1 with the epilogue ----
+    __shared__ bool is_last;
+    const int       sb = blockIdx.x - m.main_blocks;
+    double          acc = 0.0;
+    {
+      const long b = m.sb_begin[sb], en = m.sb_end[sb];
+      for (long q = b + threadIdx.x; q < en; q += blockDim.x)
+        acc = fma(ld_stream(m.sink_val + q), __ldg(x + ld_stream(m.sink_idx + q)), acc);
+    }
+    const double r = block_sum(acc, red);
+    if (threadIdx.x == 0) m.sink_partials[sb] = r;
+    __threadfence();
+    if (threadIdx.x == 0) is_last = (atomicAdd(m.sink_counter, 1u) == (unsigned) m.sink_blocks - 1u);
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+      for (int k = warp; k < m.K; k += nw) {
+        double s = 0.0;
+        for (int b = lane; b < m.sink_blocks; b += 32) {
+          const int seg = m.sb_seg[b];
+          if (seg >= 0 && seg % m.K == k) s = fma(cf.cd[seg / m.K], __ldcg(m.sink_partials + b), s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+          const long i = (long) m.n_rows_main + k;
+          double     v = fma(e.alpha, s, e.beta * __ldg(x + i));
+          if (e.scale) v *= __ldg(e.scale + i);
+          y[i] = v;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        *m.sink_counter = 0u;
+        for (int k = 0; k < m.K; ++k) {  // fixed order
+          const long   i = (long) m.n_rows_main + k;
+          const double v = y[i];
+          if (e.n_dots > 0) d0 = fma(v, e.vec[0] ? __ldg(e.vec[0] + i) : v, d0);
+          if (e.n_dots > 1) d1 = fma(v, e.vec[1] ? __ldg(e.vec[1] + i) : v, d1);
+        }
+        e.partials[2 * e.G] = d0;
+        e.partials[2 * e.G + 1] = d1;
+      }
+    }
+  } else {
+    const long stride = (long) m.main_blocks * kThreads;
+    for (long i = (long) blockIdx.x * kThreads + threadIdx.x; i < m.n; i += stride) {
+      const int    *cp = m.col + i;
+      const double *op = m.off + i;
+      double        acc = 0.0;
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const int    c = ld_stream(cp + (size_t) p * m.ld);
+        const double o = ld_stream(op + (size_t) p * m.ld);
+        const double xs = c >= 0 ? __ldg(x + c) : 0.0;
+        acc = fma(cf.c[p] * o, xs, acc);
+      }
+      double        d = 0.0;
+      const double *dp = m.diag + i;
+      for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
+      const double xi = __ldg(x + i);
+      double       v = fma(e.alpha, fma(-d, xi, acc), e.beta * xi);
+      if (e.scale) v *= __ldg(e.scale + i);
+      y[i] = v;
+      if (e.n_dots > 0) d0 = fma(v, e.vec[0] ? __ldg(e.vec[0] + i) : v, d0);
+      if (e.n_dots > 1) d1 = fma(v, e.vec[1] ? __ldg(e.vec[1] + i) : v, d1);
+    }
+    if (e.n_dots > 0) {
+      const double r0 = block_sum(d0, red);
+      const double r1 = e.n_dots > 1 ? block_sum(d1, red) : 0.0;
+      if (threadIdx.x == 0) {
+        e.partials[2 * blockIdx.x] = r0;
+        e.partials[2 * blockIdx.x + 1] = r1;
+      }
+    }
+  }
+  if (e.n_dots == 0) return;
+  // ---- last CTA of the whole grid: fixed-order sum of the partials ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_cta = (atomicAdd(e.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence();
+  const int slots = e.G + (m.sink_blocks > 0 ? 1 : 0);
+  for (int k = 0; k < e.n_dots; ++k) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < slots; b += blockDim.x) v += __ldcg(e.partials + 2 * b + k);
+    const double r = block_sum(v, red);
+    if (threadIdx.x == 0) e.out[k] = r;
+  }
+  if (threadIdx.x == 0) *e.counter = 0u;
+}
+
+typedef void (*epi_fn)(MatView, Coefs, Epi, const double *, double *);
+epi_fn pick_epi(int P) {
+  switch (P) {
+#define FSP_CASE(N) case N: return fsp_action_epi<N>;
+    FSP_CASE(1) FSP_CASE(2) FSP_CASE(3) FSP_CASE(4) FSP_CASE(5) FSP_CASE(6) FSP_CASE(7) FSP_CASE(8)
+    FSP_CASE(9) FSP_CASE(10) FSP_CASE(11) FSP_CASE(12) FSP_CASE(13) FSP_CASE(14) FSP_CASE(15) FSP_CASE(16)
+#undef FSP_CASE
+    default: return nullptr;
+  }
+}
+
 // boundary rows of the split multi-GPU action (short list; runtime plane loop)
 __global__ void __launch_bounds__(kThreads) fsp_action_rowlist(MatView m, Coefs cf, const double *__restrict__ x,
                                                                const double *__restrict__ ghost,
@@ -355,6 +484,59 @@ __global__ void __launch_bounds__(kThreads) fsp_action_boundary_p2p_kernel(MatVi
     acc = fma(cf.c[p] * ld_stream(m.off + p * m.ld + i), xs, acc);
   }
   y[i] = fma(-d, xi, acc);
+}
+
+// Whole multi-GPU action in ONE kernel (peer-memory mode).  CTAs are issued in the order cta_order[]: first the CTAs
+// whose 256 rows reference no ghost entry (they overlap the arrival of the halo), then the CTAs with ghost rows, which
+// wait in device code for the peers' epoch flags before they start; one trailing CTA on the sink owner adds the
+// partial sink sums of all ranks in rank order.  No second pass over the boundary rows, no kernel boundary between
+// "interior" and "boundary" work, nothing for the host to do between them.
+template <int P>
+__global__ void __launch_bounds__(kThreads, 8) fsp_action_p2p_kernel(MatView m, Coefs cf, P2PWait w,
+                                                                     const double *__restrict__ x, const double *ghost,
+                                                                     double *__restrict__ y) {
+  if ((int) blockIdx.x >= m.main_blocks) {
+    if ((int) threadIdx.x < w.n_ranks) wait_flag(w.sink_flags + threadIdx.x, w.epoch, w.err);
+    __syncthreads();
+    if ((int) threadIdx.x < m.K) {
+      double s = 0.0;
+      for (int p = 0; p < w.n_ranks; ++p) s += __ldcg(w.sink_slots + (size_t) p * FSP_P2P_MAX_SINKS + threadIdx.x);
+      y[m.n_rows_main + threadIdx.x] = s;
+    }
+    return;
+  }
+  const int cta = m.cta_order[blockIdx.x];
+  if ((int) blockIdx.x >= m.n_interior_ctas) {
+    if ((int) threadIdx.x < w.n_ranks && (int) threadIdx.x != w.rank) wait_flag(w.halo_flags + threadIdx.x, w.epoch, w.err);
+    __syncthreads();
+  }
+  const int i = cta * kThreads + (int) threadIdx.x;
+  if (i >= m.n) return;
+  const int    *cp = m.col + i;
+  const double *op = m.off + i;
+  double acc = 0.0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int    c = ld_stream(cp + (size_t) p * m.ld);
+    const double o = ld_stream(op + (size_t) p * m.ld);
+    // ghost entries were stored by other GPUs while this kernel was running: read them at L2 (ld.cg), never L1
+    const double xs = c >= 0 ? __ldg(x + c) : (c == -1 ? 0.0 : __ldcg(ghost + (-(c + 2))));
+    acc = fma(cf.c[p] * o, xs, acc);
+  }
+  double d = 0.0;
+  const double *dp = m.diag + i;
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
+  y[i] = fma(-d, __ldg(x + i), acc);
+}
+typedef void (*p2p_fn)(MatView, Coefs, P2PWait, const double *, const double *, double *);
+p2p_fn pick_p2p(int P) {
+  switch (P) {
+#define FSP_CASE(N) case N: return fsp_action_p2p_kernel<N>;
+    FSP_CASE(1) FSP_CASE(2) FSP_CASE(3) FSP_CASE(4) FSP_CASE(5) FSP_CASE(6) FSP_CASE(7) FSP_CASE(8)
+    FSP_CASE(9) FSP_CASE(10) FSP_CASE(11) FSP_CASE(12) FSP_CASE(13) FSP_CASE(14) FSP_CASE(15) FSP_CASE(16)
+#undef FSP_CASE
+    default: return nullptr;
+  }
 }
 
 typedef void (*action_fn)(MatView, Coefs, const double *, const double *, double *, double *);
@@ -460,6 +642,14 @@ __global__ void remap_cols_kernel(int *col, long n, int lo, int hi, const int *g
   }
   col[q] = -((int) a + 2);
 }
+__global__ void mark_cta_kernel(const int *__restrict__ rows, long n_rows, int *__restrict__ cta_flag) {
+  long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_rows) cta_flag[rows[q] / kThreads] = 1;
+}
+struct CtaIsInterior {
+  const int *flag;
+  __host__ __device__ bool operator()(const int &c) const { return flag[c] == 0; }
+};
 struct RowHasGhost {
   const int *col; long ld; int P;
   __host__ __device__ bool operator()(const int &i) const {
@@ -497,6 +687,10 @@ struct fspmat_s {
   long     flops = 0;
   double   bytes = 0.0;
   int      variant = 0;
+  int     *d_cta_order = nullptr;      // CTA issue order of the single-kernel peer-memory action
+  int      n_ctas = 0, n_interior_ctas = 0;
+  double  *d_epi_partials = nullptr;   // fused-epilogue inner-product partials (allocated on first use)
+  unsigned *d_epi_counter = nullptr;
   int     *d_boundary_rows = nullptr;  // rows referencing ghost entries (multi-GPU)
   long     n_boundary = 0;
 };
@@ -506,6 +700,7 @@ static int free_values(fspmat_s *h) {
   pfree(h->d_sink_idx); pfree(h->d_sink_val);
   pfree(h->d_sb_seg); pfree(h->d_sb_begin); pfree(h->d_sb_end);
   pfree(h->d_sink_partials); pfree(h->d_sink_counter); pfree(h->d_boundary_rows);
+  pfree(h->d_epi_partials); pfree(h->d_epi_counter); pfree(h->d_cta_order);
   int variant = h->variant;
   *h = fspmat_s();
   h->variant = variant;
@@ -594,6 +789,32 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
     FSP_CUDA_CHECK(cudaMemcpy(&nb, d_num, sizeof(int), cudaMemcpyDeviceToHost));
     h->n_boundary = nb;
     pfree(d_num); pfree(d_tmp);
+  }
+  if (h->n_ghost > 0 && P > 0 && n > 0) {
+    // CTA issue order of the single-kernel peer-memory action: CTAs free of ghost rows first
+    const int n_ctas = (int) ((n + kThreads - 1) / kThreads);
+    int      *d_flag = nullptr, *d_num = nullptr;
+    void     *d_tmp = nullptr;
+    size_t    need = 0;
+    FSP_CUDA_CHECK(pmalloc(&d_flag, sizeof(int) * n_ctas));
+    FSP_CUDA_CHECK(pmalloc(&d_num, sizeof(int)));
+    FSP_CUDA_CHECK(pmalloc(&h->d_cta_order, sizeof(int) * n_ctas));
+    FSP_CUDA_CHECK(cudaMemsetAsync(d_flag, 0, sizeof(int) * n_ctas, st));
+    if (h->n_boundary > 0) {
+      mark_cta_kernel<<<(unsigned) ((h->n_boundary + 255) / 256), 256, 0, st>>>(h->d_boundary_rows, h->n_boundary, d_flag);
+      FSP_LAUNCH_CHECK();
+    }
+    cub::CountingInputIterator<int> iota(0);
+    CtaIsInterior pred{d_flag};
+    cub::DevicePartition::If(nullptr, need, iota, h->d_cta_order, d_num, n_ctas, pred, st);
+    FSP_CUDA_CHECK(pmalloc(&d_tmp, need));
+    FSP_CUDA_CHECK(cub::DevicePartition::If(d_tmp, need, iota, h->d_cta_order, d_num, n_ctas, pred, st));
+    count_launch();
+    int ni = 0;
+    FSP_CUDA_CHECK(cudaMemcpy(&ni, d_num, sizeof(int), cudaMemcpyDeviceToHost));
+    h->n_ctas = n_ctas;
+    h->n_interior_ctas = ni;
+    pfree(d_flag); pfree(d_num); pfree(d_tmp);
   }
 
   // ---- flops: 2 nnz per matrix (+ rows per TV axpy); FspMatrixBase.cpp:429-444 -------------------
@@ -708,6 +929,7 @@ static int launch_action(fspmat_t h, const double *coef_host, const double *x, c
   m.owns_sinks = h->owns_sinks;
   m.ghost_zero = 0; m.row_list = nullptr; m.write_y_sinks = 1;
   m.sink_flag_remote = nullptr; m.sink_epoch = 0;
+  m.cta_order = nullptr; m.n_interior_ctas = 0;
 
   // Kernel selection.  variant 0 (default) = lean kernel: 1 row per thread, 32 registers, 8 CTAs/SM.  Measured on
   // one B200 (465^3 lattice, same GPU, profiles/r01_variants.md): lean 6.77 TB/s, 2 rows/thread (64 regs) 6.15 TB/s,
@@ -767,7 +989,35 @@ static void fill_coefs_view(fspmat_t h, const double *coef_host, Coefs &cf, MatV
   m.owns_sinks = h->owns_sinks;
   m.ghost_zero = 0; m.row_list = nullptr; m.write_y_sinks = 0;
   m.sink_flag_remote = nullptr; m.sink_epoch = 0;
+  m.cta_order = nullptr; m.n_interior_ctas = 0;
   m.main_blocks = 0;
+}
+
+int fspmat_fused_supported(fspmat_t h) { return (h->has_values && h->n_ghost == 0 && h->P >= 1 && h->P <= 16) ? 1 : 0; }
+
+int fspmat_action_fused(fspmat_t h, const double *coef_host, const double *x, double *y, const fspmat_epilogue *ep,
+                        void *stream) {
+  if (!fspmat_fused_supported(h)) { set_error("fspmat_action_fused: not available for this operator (ghost columns, no values or > 16 reactions)"); return -1; }
+  if (ep->n_dots < 0 || ep->n_dots > 2) { set_error("fspmat_action_fused: n_dots must be 0, 1 or 2"); return -1; }
+  const int maxG = sm_count() * 8;
+  if (!h->d_epi_partials) {
+    FSP_CUDA_CHECK(pmalloc(&h->d_epi_partials, sizeof(double) * 2 * (size_t) (maxG + 1)));
+    FSP_CUDA_CHECK(pmalloc(&h->d_epi_counter, sizeof(unsigned)));
+    FSP_CUDA_CHECK(cudaMemsetAsync(h->d_epi_counter, 0, sizeof(unsigned), (cudaStream_t) 0));
+    FSP_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) 0));
+  }
+  Coefs cf; MatView m;
+  fill_coefs_view(h, coef_host, cf, m);
+  m.sink_blocks = (h->K > 0 && h->owns_sinks) ? h->sink_blocks : 0;
+  m.main_blocks = (int) std::min<long>(maxG, std::max<long>(1, ((long) h->n + kThreads - 1) / kThreads));
+  Epi e;
+  e.alpha = ep->alpha; e.beta = ep->beta; e.scale = ep->scale_dev; e.n_dots = ep->n_dots;
+  e.vec[0] = ep->dot_vec_dev[0]; e.vec[1] = ep->dot_vec_dev[1];
+  e.out = ep->dot_out_dev; e.partials = h->d_epi_partials; e.counter = h->d_epi_counter; e.G = m.main_blocks;
+  epi_fn fn = pick_epi(h->P);
+  fn<<<m.main_blocks + m.sink_blocks, kThreads, 0, resolve_stream(stream)>>>(m, cf, e, x, y);
+  FSP_LAUNCH_CHECK();
+  return 0;
 }
 
 int fspmat_action_sinks_p2p(fspmat_t h, const double *coef_host, const double *x, const fsphalo_epoch *e, void *stream) {
@@ -781,6 +1031,32 @@ int fspmat_action_sinks_p2p(fspmat_t h, const double *coef_host, const double *x
   if (!fn) fn = fsp_action_generic;
   fn<<<m.sink_blocks, kThreads, 0, resolve_stream(stream)>>>(m, cf, x, nullptr, nullptr, e->sink_slot_remote);
   FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fspmat_action_p2p(fspmat_t h, const double *coef_host, const double *x, double *y, const fsphalo_epoch *e, void *stream) {
+  if (!h->has_values) return 0;
+  p2p_fn fn = pick_p2p(h->P);
+  if (!fn || !h->d_cta_order) { set_error("fspmat_action_p2p: needs an operator with ghost columns and <= 16 reactions"); return -1; }
+  Coefs cf; MatView m;
+  fill_coefs_view(h, coef_host, cf, m);
+  m.cta_order = h->d_cta_order;
+  m.n_interior_ctas = h->n_interior_ctas;
+  m.main_blocks = h->n_ctas;
+  P2PWait w;
+  w.halo_flags = e->halo_flags;
+  const bool finish_sinks = h->K > 0 && h->owns_sinks;
+  w.sink_flags = finish_sinks ? e->sink_flags : nullptr;
+  w.sink_slots = e->sink_slots;
+  w.epoch = e->epoch; w.n_ranks = e->n_ranks; w.err = e->error_flag; w.rank = e->self_rank;
+  fn<<<m.main_blocks + (finish_sinks ? 1 : 0), kThreads, 0, resolve_stream(stream)>>>(m, cf, w, x, e->ghost, y);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fspmat_p2p_cta_counts(fspmat_t h, long *n_interior, long *n_total) {
+  *n_interior = h->n_interior_ctas;
+  *n_total = h->n_ctas;
   return 0;
 }
 

@@ -410,9 +410,7 @@ int mdot_impl(double *out, const double *x, const double *const *Y, long n, void
 }
 
 int host_result(double *out_host, double *tmp_dev, void *stream) {
-  FSP_CUDA_CHECK(cudaMemcpyAsync(out_host, tmp_dev, sizeof(double), cudaMemcpyDeviceToHost, resolve_stream(stream)));
-  FSP_CUDA_CHECK(cudaStreamSynchronize(resolve_stream(stream)));
-  return 0;
+  return fsp_memcpy_d2h(out_host, tmp_dev, sizeof(double), stream);  // staged through pinned memory
 }
 
 thread_local double *g_tmp[16] = {nullptr};

@@ -216,6 +216,20 @@ class DeviceFspMatrix:
         check(lib().fspmat_action(self.h, _dp(c), _ptr(x), _ptr(ghost), _ptr(y), _ptr(sink_out), _stream(stream)),
               "fspmat_action")
 
+    def action_fused(self, coef, x, y, alpha=1.0, beta=0.0, scale=None, dot_vecs=(), dot_out=None, stream=None):
+        """y = scale .* (beta x + alpha A x); dot_out[k] = <y, dot_vecs[k]> (None entry: <y, y>)."""
+        c = np.ascontiguousarray(coef, dtype=np.float64)
+        if len(c) < self.R:
+            c = np.concatenate([c, np.ones(self.R - len(c))])
+        ep = _capi.FspMatEpilogue()
+        ep.alpha, ep.beta = float(alpha), float(beta)
+        ep.scale_dev = scale.data_ptr() if scale is not None else None
+        ep.n_dots = len(dot_vecs)
+        for k, v in enumerate(dot_vecs):
+            ep.dot_vec_dev[k] = v.data_ptr() if v is not None else None
+        ep.dot_out_dev = dot_out.data_ptr() if dot_out is not None else None
+        check(lib().fspmat_action_fused(self.h, _dp(c), _ptr(x), _ptr(y), C.byref(ep), _stream(stream)), "fspmat_action_fused")
+
     def flops(self):
         f = C.c_long()
         check(lib().fspmat_flops(self.h, C.byref(f)), "fspmat_flops")

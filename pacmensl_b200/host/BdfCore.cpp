@@ -380,17 +380,29 @@ int BdfCore::lin_solve(Vec b, Vec ewt, double ss_b, double tn, bool first_newton
     if ((int) V_.size() < l + 2) { V_.push_back(nullptr); if (alloc_like(b, &V_[l + 1])) return BDF_MEM_FAIL; }
     // w = J vtemp ; V_{l+1} = s1 .* (vtemp - gamma w)   (vtemp = V_l ./ s2 was formed by the previous fused pass)
     njtv_ += 1;
-    int r = jtv_(tn, vtemp_, V_[l + 1]);
-    if (r != 0) return r < 0 ? BDF_LSOLVE_FAIL : r;
-    VCHK(fspvec_wlincomb(V_[l + 1]->d_data, ewt->d_data, 1.0, vtemp_->d_data, -gamma_, V_[l + 1]->d_data, n_local_, stream_));
+    double *hd = hdev_.get();
+    double *w = V_[l + 1]->d_data;
+    int     r;
+    if (fused_jtv_) {
+      // ONE kernel: V_{l+1} = s1 .* (vtemp - gamma J vtemp), <V_{l+1}, V_0> and <V_{l+1}, V_{l+1}>
+      fspmat_epilogue ep{};
+      ep.alpha = -gamma_; ep.beta = 1.0; ep.scale_dev = ewt->d_data; ep.n_dots = 2;
+      ep.dot_vec_dev[0] = V_[0]->d_data; ep.dot_vec_dev[1] = nullptr; ep.dot_out_dev = hd + lmax + 4;
+      r = fused_jtv_(tn, vtemp_, V_[l + 1], ep);
+      if (r != 0) return r < 0 ? BDF_LSOLVE_FAIL : r;
+    } else {
+      r = jtv_(tn, vtemp_, V_[l + 1]);
+      if (r != 0) return r < 0 ? BDF_LSOLVE_FAIL : r;
+      VCHK(fspvec_wlincomb(V_[l + 1]->d_data, ewt->d_data, 1.0, vtemp_->d_data, -gamma_, V_[l + 1]->d_data, n_local_, stream_));
+    }
     nli_ += 1;
     // modified Gram-Schmidt against V_0..V_l with device-resident coefficients:
     //   hd[0] = <w, V_0>, hd[l+2] = <w, w> (norm before orthogonalisation); then fused axpy+dot chain
-    double *hd = hdev_.get();
-    double *w = V_[l + 1]->d_data;
     {
-      const double *two[2] = {V_[0]->d_data, w};
-      VCHK(fspvec_mdot(hd + lmax + 4, w, 2, two, n_local_, stream_));  // [<w,V0>, <w,w>]
+      if (!fused_jtv_) {
+        const double *two[2] = {V_[0]->d_data, w};
+        VCHK(fspvec_mdot(hd + lmax + 4, w, 2, two, n_local_, stream_));  // [<w,V0>, <w,w>]
+      }
       VCHK(fsp_memcpy_d2d(hd + 0, hd + lmax + 4, sizeof(double), stream_));
       if (multi) {
         VCHK(fspcomm_allreduce_sum(comm_->nccl, hd + 0, 1, stream_));

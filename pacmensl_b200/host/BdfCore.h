@@ -28,6 +28,9 @@ class BdfCore {
   using JtvFn = std::function<int(double t, Vec v, Vec Jv)>;
   // sensitivity right-hand side: sdot = J s_i + (df/dtheta_i)(t, y)
   using SensRhsFn = std::function<int(int is, double t, Vec y, Vec ydot, Vec s, Vec sdot)>;
+  /// J v with a fused epilogue (FspMatrixBase::ActionFused); optional, used by the state GMRES loop when set
+  using FusedJtvFn = std::function<int(double t, Vec v, Vec out, const fspmat_epilogue &ep)>;
+  void SetFusedJtv(FusedJtvFn f) { fused_jtv_ = std::move(f); }
 
   explicit BdfCore(MPI_Comm comm);
   ~BdfCore();
@@ -73,6 +76,7 @@ class BdfCore {
   RhsFn     f_;
   JtvFn     jtv_;
   SensRhsFn fs_;
+  FusedJtvFn fused_jtv_;
 
   // Nordsieck history and work vectors
   Vec zn_[LMAX + 1] = {nullptr};

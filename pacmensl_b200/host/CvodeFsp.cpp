@@ -25,6 +25,7 @@ PacmenslErrorCode CvodeFsp::SetUp() {
   core_->SetMaxNonlinIters(10000);   // CVodeSetMaxNonlinIters(cvode_mem, 10000)
   core_->SetMaxKrylov(100);          // SUNLinSol_SPGMR(y, PREC_NONE, 100)
   auto f = [this](double t, Vec y, Vec ydot) { return EvaluateRHS(t, y, ydot); };  // J v == A(t) v (linear ODE)
+  if (fused_rhs_) core_->SetFusedJtv([this](double t, Vec v, Vec out, const fspmat_epilogue &ep) { return fused_rhs_(t, v, out, ep); });
   cvode_stat = core_->Init(t_now_tmp, solution_work_, f, f, t_final_);
   if (cvode_stat < 0) {
     printf("\nBDF integrator error: initialisation failed with flag = %d\n\n", cvode_stat);

@@ -1,6 +1,7 @@
 #include "FspMatrixBase.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 PetscErrorCode MatMult(Mat A, Vec x, Vec y) {
@@ -40,9 +41,11 @@ FspMatrixBase::~FspMatrixBase() {
     fsp_stream_destroy(comm_stream_);
     fsp_event_destroy(ev_x_ready_);
     fsp_event_destroy(ev_comm_done_);
+    fsp_event_destroy(ev_push_done_);
   }
   if (dmat_) fspmat_destroy(dmat_);
   dmat_ = nullptr;
+  FreePinned_();
   comm_ = MPI_COMM_NULL;
 }
 
@@ -175,14 +178,8 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
     }
     const long n_new = n - cache_n_;
     if (n_new > 0) {
-      shifted.resize((size_t) n_new * n_species);  // host copy of the NEW states only
-      vals.resize((size_t) n_new);
-      FSPCHKERRQ(fspset_copy_states(dset, cache_n_, n_new, shifted.data()));
-      for (int r : enable_reactions_) {
-        ierr = new_prop_x(r, n_species, (int) n_new, shifted.data(), vals.data(), prop_x_args);
-        PACMENSLCHKERRQ(ierr);
-        FSPCHKERRQ(fsp_memcpy_h2d(diag_cache_.get() + (size_t) r * cache_ld_ + cache_n_, vals.data(), sizeof(double) * n_new, nullptr));
-      }
+      ierr = EvaluatePropensitiesHost_(dset, n_species, cache_n_, n_new, new_prop_x, prop_x_args);
+      PACMENSLCHKERRQ(ierr);
       cache_n_ = n;
     }
     for (int p = 0; p < P && n > 0; ++p) {
@@ -257,8 +254,92 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
   if (num_constraints_ > 0 && comm_size_ > 1) {
     if (sink_buf_.resize((size_t) num_constraints_)) PACMENSLCHKERRQ(-1);
   }
+  if (comm_size_ > 1) {
+    long n_int = 0, n_tot = 0;
+    int  sms = 148;
+    FSPCHKERRQ(fspmat_p2p_cta_counts(dmat_, &n_int, &n_tot));
+    fsp_device_sm_count(&sms);
+    push_first_ = n_int < 4L * 8L * sms;  // fewer than four full waves of ghost-free CTAs ahead of the waiting ones
+  }
   has_values_ = PETSC_TRUE;
   return 0;
+}
+
+// Host prop_x callbacks (the API contract, src/Models/Model.h:44-60) on the states [first, first + count), results into
+// diag_cache_.  The reference makes one call per reaction over ALL states (FspMatrixBase.cpp:135-136,180,232) and
+// inserts the values one MatSetValue at a time.  Here the states are streamed from the device in super-chunks through
+// pinned double buffers; inside a super-chunk the callback is invoked per reaction on cache-sized blocks (the state
+// block is read from the host cache for every reaction instead of from DRAM R times), and the values of a finished
+// super-chunk go to the device with asynchronous copies that overlap the evaluation of the next one.
+int FspMatrixBase::EvaluatePropensitiesHost_(fspset_t dset, int n_species, long first, long count, const PropFun &prop_x,
+                                             void *prop_x_args) {
+  const long kBlock = 1L << 14;   // states per callback invocation
+  const long kSuper = 1L << 18;   // states per pinned buffer
+  const int  R = (int) enable_reactions_.size();
+  if (count <= 0 || R == 0) return 0;
+  static const bool pipeline = [] { const char *e = std::getenv("FSP_HOST_PIPELINE"); return !(e && e[0] == '0'); }();
+  if (count <= kBlock || !pipeline) {  // small increments: no pipeline needed
+    std::vector<int>    st((size_t) count * n_species);
+    std::vector<double> vals((size_t) count);
+    FSPCHKERRQ(fspset_copy_states(dset, first, count, st.data()));
+    for (int r : enable_reactions_) {
+      int ierr = prop_x(r, n_species, (int) count, st.data(), vals.data(), prop_x_args);
+      PACMENSLCHKERRQ(ierr);
+      FSPCHKERRQ(fsp_memcpy_h2d(diag_cache_.get() + (size_t) r * cache_ld_ + first, vals.data(), sizeof(double) * count, nullptr));
+    }
+    return 0;
+  }
+  const long super = std::min(kSuper, (count + kBlock - 1) / kBlock * kBlock);
+  if (!pin_states_[0] || pin_species_ < n_species || pin_R_ < R || pin_super_ < super) {
+    FreePinned_();
+    for (int b = 0; b < 2; ++b) {
+      FSPCHKERRQ(fsp_malloc_host((void **) &pin_states_[b], sizeof(int) * (size_t) super * n_species));
+      FSPCHKERRQ(fsp_malloc_host((void **) &pin_vals_[b], sizeof(double) * (size_t) super * R));
+      FSPCHKERRQ(fsp_event_create(&pin_done_[b]));
+    }
+    FSPCHKERRQ(fsp_stream_create(&copy_stream_));
+    pin_species_ = n_species; pin_R_ = R; pin_super_ = super;
+  }
+  FSPCHKERRQ(fsp_device_sync());  // diag_cache_ may just have been (re)allocated / copied on the main stream
+  bool used[2] = {false, false};
+  int  sc = 0;
+  for (long s0 = 0; s0 < count; s0 += super, ++sc) {
+    const int  b = sc & 1;
+    const long m = std::min(super, count - s0);
+    if (used[b]) FSPCHKERRQ(fsp_event_sync(pin_done_[b]));  // the copies that last read this buffer have finished
+    FSPCHKERRQ(fspset_copy_states(dset, first + s0, m, pin_states_[b]));
+    for (long o = 0; o < m; o += kBlock) {
+      const int mb = (int) std::min(kBlock, m - o);
+      int       q = 0;
+      for (int r : enable_reactions_) {
+        int ierr = prop_x(r, n_species, mb, pin_states_[b] + (size_t) o * n_species, pin_vals_[b] + (size_t) q * super + o, prop_x_args);
+        PACMENSLCHKERRQ(ierr);
+        ++q;
+      }
+    }
+    int q = 0;
+    for (int r : enable_reactions_) {
+      FSPCHKERRQ(fsp_memcpy_h2d_async(diag_cache_.get() + (size_t) r * cache_ld_ + first + s0, pin_vals_[b] + (size_t) q * super,
+                                      sizeof(double) * m, copy_stream_));
+      ++q;
+    }
+    FSPCHKERRQ(fsp_event_record(pin_done_[b], copy_stream_));
+    used[b] = true;
+  }
+  FSPCHKERRQ(fsp_stream_sync(copy_stream_));
+  return 0;
+}
+
+void FspMatrixBase::FreePinned_() {
+  for (int b = 0; b < 2; ++b) {
+    if (pin_states_[b]) fsp_free_host(pin_states_[b]);
+    if (pin_vals_[b]) fsp_free_host(pin_vals_[b]);
+    if (pin_done_[b]) fsp_event_destroy(pin_done_[b]);
+    pin_states_[b] = nullptr; pin_vals_[b] = nullptr; pin_done_[b] = nullptr;
+  }
+  if (copy_stream_) { fsp_stream_sync(copy_stream_); fsp_stream_destroy(copy_stream_); copy_stream_ = nullptr; }
+  pin_species_ = pin_R_ = 0;
+  pin_super_ = 0;
 }
 
 PacmenslErrorCode FspMatrixBase::SetTimeFun(TcoefFun new_t_fun, void *new_t_fun_args) {
@@ -276,6 +357,60 @@ PacmenslErrorCode FspMatrixBase::Action(PetscReal t, Vec x, Vec y) {
     PACMENSLCHKERRQ(ierr);
   }
   return ActionWithCoefficients(time_coefficients_.memptr(), x, y);
+}
+
+// y = scale .* (beta x + alpha A(t) x) plus up to two inner products of y in the same pass (fspmat_epilogue).
+// Single GPU: one fused kernel.  Multi-GPU (or operators the fused kernel does not cover): Action followed by the
+// equivalent vector passes; the inner products are then LOCAL partial sums -- the solver all-reduces them.
+PacmenslErrorCode FspMatrixBase::ActionFused(PetscReal t, Vec x, Vec y, const fspmat_epilogue &ep) {
+  if (has_values_ == PETSC_TRUE && !tv_reactions_.empty()) {
+    int ierr = t_fun_(t, num_reactions_, time_coefficients_.memptr(), t_fun_args_);
+    if (ierr != 0) VecSet(y, 0.0);
+    PACMENSLCHKERRQ(ierr);
+  }
+  void *stream = comm_ ? comm_->stream : nullptr;
+  if (has_values_ == PETSC_TRUE && comm_size_ == 1 && fspmat_fused_supported(dmat_)) {
+    if (x->n_local != num_rows_local_ || y->n_local != num_rows_local_) PACMENSLCHKERRQ(-1);
+    FSPCHKERRQ(fspmat_action_fused(dmat_, time_coefficients_.memptr(), x->d_data, y->d_data, &ep, stream));
+    static const bool self_check = [] { const char *e = std::getenv("FSP_FUSED_CHECK"); return e && e[0] == '1'; }();
+    if (self_check) {
+      // diagnostics: recompute with Action + separate vector passes and compare (host synchronisation, slow)
+      Vec z, u;
+      VecDuplicate(y, &z);
+      VecDuplicate(y, &u);
+      PacmenslErrorCode ie = ActionWithCoefficients(time_coefficients_.memptr(), x, z);
+      PACMENSLCHKERRQ(ie);
+      FSPCHKERRQ(fspvec_wlincomb(u->d_data, ep.scale_dev, ep.beta, x->d_data, ep.alpha, z->d_data, y->n_local, stream));
+      double un = 0, gap = 0, dref[2] = {0, 0}, dgot[2] = {0, 0};
+      VecNorm(u, NORM_2, &un);
+      for (int k = 0; k < ep.n_dots; ++k)
+        fspvec_dot_h(&dref[k], u->d_data, ep.dot_vec_dev[k] ? ep.dot_vec_dev[k] : u->d_data, y->n_local, stream);
+      if (ep.n_dots > 0) fsp_memcpy_d2h(dgot, ep.dot_out_dev, sizeof(double) * ep.n_dots, stream);
+      VecAXPY(u, -1.0, y);
+      VecNorm(u, NORM_2, &gap);
+      static long calls = 0;
+      ++calls;
+      bool bad = !(gap <= 1e-12 * un) || !std::isfinite(un);
+      for (int k = 0; k < ep.n_dots; ++k) bad = bad || !(std::fabs(dgot[k] - dref[k]) <= 1e-9 * (std::fabs(dref[k]) + un * un + 1e-300));
+      if (bad)
+        printf("[FSP_FUSED_CHECK] call %ld n=%d: |y|=%.6e |y_fused - y_ref|=%.3e dots fused (%.12e, %.12e) ref (%.12e, %.12e)\n", calls,
+               y->n_local, un, gap, dgot[0], dgot[1], dref[0], dref[1]);
+      VecDestroy(&z);
+      VecDestroy(&u);
+    }
+    return 0;
+  }
+  PacmenslErrorCode ierr = ActionWithCoefficients(time_coefficients_.memptr(), x, y);
+  PACMENSLCHKERRQ(ierr);
+  const long n = y->n_local;
+  if (ep.scale_dev || ep.alpha != 1.0 || ep.beta != 0.0)
+    FSPCHKERRQ(fspvec_wlincomb(y->d_data, ep.scale_dev, ep.beta, x->d_data, ep.alpha, y->d_data, n, stream));
+  if (ep.n_dots > 0) {
+    const double *vecs[2] = {ep.dot_vec_dev[0] ? ep.dot_vec_dev[0] : y->d_data,
+                             ep.n_dots > 1 && ep.dot_vec_dev[1] ? ep.dot_vec_dev[1] : y->d_data};
+    FSPCHKERRQ(fspvec_mdot(ep.dot_out_dev, y->d_data, ep.n_dots, vecs, n, stream));
+  }
+  return 0;
 }
 
 PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec x, Vec y) {
@@ -324,6 +459,7 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
     FSPCHKERRQ(fsp_stream_create(&comm_stream_));
     FSPCHKERRQ(fsp_event_create(&ev_x_ready_));
     FSPCHKERRQ(fsp_event_create(&ev_comm_done_));
+    FSPCHKERRQ(fsp_event_create(&ev_push_done_));
   }
   if (halo_) {
     // Peer-memory path (NVLink/NVSwitch, no NCCL call, no host synchronisation):
@@ -332,14 +468,28 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
     //   main stream : interior pass; then the boundary kernel waits for the peers' flags in device code, redoes the
     //                 rows with ghost entries and (sink owner) adds the slots in rank order into y[n..n+K)
     fsphalo_epoch ep;
+    static const bool split = [] { const char *e = std::getenv("FSP_P2P_SPLIT"); return e && e[0] == '1'; }();
     FSPCHKERRQ(fsp_event_record(ev_x_ready_, stream));
     FSPCHKERRQ(fsp_stream_wait_event(comm_stream_, ev_x_ready_));
     FSPCHKERRQ(fsphalo_begin(halo_, x->d_data, comm_stream_, &ep));
+    if (!split && push_first_) {
+      // few ghost-free CTAs: CTAs waiting for the peers could fill every SM slot before this GPU's own push kernel has
+      // been scheduled (and every GPU could do the same to its peers) -- let the push complete first
+      FSPCHKERRQ(fsp_event_record(ev_push_done_, comm_stream_));
+      FSPCHKERRQ(fsp_stream_wait_event(stream, ev_push_done_));
+    }
     if (num_constraints_ > 0) FSPCHKERRQ(fspmat_action_sinks_p2p(dmat_, coefs, x->d_data, &ep, comm_stream_));
     FSPCHKERRQ(fsp_event_record(ev_comm_done_, comm_stream_));
+    if (!split) {
+      // ONE kernel for all rows: ghost-free CTAs first, CTAs with ghost rows wait for the peers' flags in device code
+      FSPCHKERRQ(fspmat_action_p2p(dmat_, coefs, x->d_data, y->d_data, &ep, stream));
+      // join: x must not be modified by later work on the main stream while the push / sink kernels still read it
+      FSPCHKERRQ(fsp_stream_wait_event(stream, ev_comm_done_));
+      return 0;
+    }
+    // FSP_P2P_SPLIT=1 (A/B diagnostics): interior pass, then a boundary kernel that waits for the flags and redoes the
+    // rows with ghost entries
     FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, nullptr, y->d_data, nullptr, 1, stream));
-    // own push/sink kernels are complete before the boundary kernel may start waiting (no scheduling dependence
-    // between a spinning kernel and a not-yet-scheduled one on this GPU)
     FSPCHKERRQ(fsp_stream_wait_event(stream, ev_comm_done_));
     FSPCHKERRQ(fspmat_action_boundary_p2p(dmat_, coefs, x->d_data, y->d_data, &ep, stream));
     return 0;

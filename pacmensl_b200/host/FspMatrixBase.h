@@ -42,6 +42,9 @@ class PACMENSL_API FspMatrixBase {
 
   /// y = A(t) x.  Collective.  x must not alias y.
   virtual PacmenslErrorCode Action(PetscReal t, Vec x, Vec y);
+  /// Extension: y = scale .* (beta x + alpha A(t) x) with up to two inner products of y fused into the same kernel
+  /// (include/fsp_b200.h: fspmat_epilogue) -- what the Krylov and BDF/GMRES loops need right after every Action.
+  virtual PacmenslErrorCode ActionFused(PetscReal t, Vec x, Vec y, const fspmat_epilogue &ep);
   /// y = (sum_r coef[r] A_r) x with the coefficient vector supplied directly (used by SensFspMatrix).
   PacmenslErrorCode ActionWithCoefficients(const double *coefs, Vec x, Vec y);
 
@@ -88,6 +91,15 @@ class PACMENSL_API FspMatrixBase {
   long                 cache_n_ = 0, cache_ld_ = 0;
   int                  cache_R_ = 0;
   std::vector<int>     cache_enabled_;
+  // pinned double buffers + copy stream of the pipelined host-callback evaluation
+  int    *pin_states_[2] = {nullptr, nullptr};
+  double *pin_vals_[2] = {nullptr, nullptr};
+  void   *pin_done_[2] = {nullptr, nullptr};
+  void   *copy_stream_ = nullptr;
+  int     pin_species_ = 0, pin_R_ = 0;
+  long    pin_super_ = 0;
+  int  EvaluatePropensitiesHost_(fspset_t dset, int n_species, long first, long count, const PropFun &prop_x, void *prop_x_args);
+  void FreePinned_();
 
   // set when GenerateValues(fsp, model) is used with a model that has a mass-action description
   std::shared_ptr<MassActionPropensity> mass_action_;
@@ -99,6 +111,8 @@ class PACMENSL_API FspMatrixBase {
   // multi-GPU halo exchange (ghost entries of x) and sink reduction
   long                 n_ghost_ = 0;
   DeviceBuffer<double> ghost_buf_, send_buf_, sink_buf_;
+  void                *ev_push_done_ = nullptr;
+  bool                 push_first_ = true;                   ///< see ActionWithCoefficients (peer-memory path)
   fsphalo_t            halo_ = nullptr;                      ///< peer-memory halo (fused pack+store+signal kernel); null => NCCL path
   DeviceBuffer<int>    send_idx_;
   std::vector<long>    send_counts_, recv_counts_;

@@ -1,5 +1,7 @@
 #include "FspSolverMultiSinks.h"
 
+#include <cstdlib>
+
 namespace pacmensl {
 
 static double now_s() {
@@ -43,6 +45,18 @@ DiscreteDistribution FspSolverMultiSinks::Advance_(PetscReal t_final, PetscReal 
   ode_solver_->SetFinalTime(t_final);
   ode_solver_->SetTolerances(ode_rtol_, ode_atol_);
   ode_solver_->SetRhs(this->tmatvec_);
+  static const bool use_fused = [] { const char *e = std::getenv("FSP_FUSED_ACTION"); return !(e && e[0] == '0'); }();
+  if (use_fused) ode_solver_->SetFusedRhs([this](Real t, Vec x, Vec y, const fspmat_epilogue &ep) {
+    // the same operator as tmatvec_, with the solver's scaling / inner products fused into the kernel
+    if (!logging_enabled) return A_->ActionFused(t, x, y, ep);
+    double t1 = now_s();
+    int    ie = A_->ActionFused(t, x, y, ep);
+    t_rhs_ += now_s() - t1;
+    PetscInt f;
+    A_->GetLocalMVFlops(&f);
+    flops_ += f;
+    return ie;
+  });
   if (fsp_tol_ > 0.0) {
     auto error_checking_fp = [&](PetscReal t, Vec p, PetscReal &te, void *) { return CheckFspTolerance_(t, p, te); };
     ode_solver_->SetStopCondition(error_checking_fp, nullptr);

@@ -1,6 +1,7 @@
 #include "KrylovFsp.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 namespace pacmensl {
@@ -124,6 +125,24 @@ int KrylovFsp::AdvanceOneStep(const Vec &v) {
       else err_loc = phi1;
     }
 
+    if (!std::isfinite(err_loc) || !std::isfinite(err_loc / (abs_tol_ * t_step_))) {
+      // exp(tau H) overflowed: the trial step is far too long.  The reference's controller cannot recover from a
+      // non-finite omega (pow/log of inf give a NaN step suggestion and an undefined dimension suggestion, and the
+      // same step is retried until max_reject_: observed on hog1p at t = 145); shrink the step by the controller's
+      // own lower bound (factor 0.2, KrylovFsp.cpp:196) and keep the basis.
+      if (ireject == max_reject_) {
+        PetscPrintf(comm_, "KrylovFsp: maximum number of failed steps reached\n");
+        return -1;
+      }
+      ireject++;
+      t_step_old = t_step_;
+      m_old = m_;
+      m_start = m_;
+      m_next_ = m_;
+      t_step_next_ = 0.2 * t_step_;
+      bsize_changed = PETSC_FALSE;
+      continue;
+    }
     omega_old = omega;
     omega = err_loc / (abs_tol_ * t_step_);  // :182 -- only atol enters
 
@@ -166,6 +185,10 @@ int KrylovFsp::AdvanceOneStep(const Vec &v) {
       if (bsize_changed) Hm(m_ + 1, m_) = 0.0;
       if (print_intermediate)
         PetscPrintf(comm_, "t_step = %.2e m = %d t_step_next = %.2e err_loc = %.2e \n", t_step_, m_, t_step_next_, err_loc);
+      static const bool dbg = [] { const char *e = std::getenv("FSP_KRYLOV_DEBUG"); return e && e[0] == '1'; }();
+      if (dbg && (ireject < 5 || ireject % 1000 == 0))
+        printf("[krylov] reject %d: t=%.6e tau=%.3e m=%d mb=%d k1=%d beta=%.6e avnorm=%.6e err_loc=%.3e omega=%.3e H00=%.6e H10=%.6e H(m,m-1)=%.6e F(m,0)=%.3e F(m+1,0)=%.3e\n",
+               (int) ireject, t_now_tmp_, t_step_, m_, mb, (int) k1, beta, avnorm, err_loc, omega, Hm(0, 0), Hm(1, 0), Hm(m_, m_ - 1), F(m_, 0), F(m_ + 1, 0));
       if (ireject == max_reject_) {
         PetscPrintf(comm_, "KrylovFsp: maximum number of failed steps reached\n");
         return -1;
@@ -211,14 +234,22 @@ int KrylovFsp::BasisColumns_(int m_start) {
 
   for (int j{m_start}; j < m_; j++) {
     num_rhs_evals_ += 1;
-    ierr = rhs_(0.0, Vm[j], Vm[j + 1]);
-    PACMENSLCHKERRQ(ierr);
     if (q_iop > 0) istart = (j - q_iop + 1 >= 0) ? j - q_iop + 1 : 0;
-
     double *hcol = hdev_.get() + (size_t) j * stride;
     double *w = Vm[j + 1]->d_data;
-    // first coefficient: plain dot
-    FSPCHKERRQ(fspvec_dot(hcol + 0, w, Vm[istart]->d_data, n, stream));
+    if (fused_rhs_) {
+      // w = A V_j and the first coefficient <w, V_istart> in ONE kernel
+      fspmat_epilogue ep{};
+      ep.alpha = 1.0; ep.beta = 0.0; ep.scale_dev = nullptr; ep.n_dots = 1;
+      ep.dot_vec_dev[0] = Vm[istart]->d_data; ep.dot_vec_dev[1] = nullptr; ep.dot_out_dev = hcol + 0;
+      ierr = fused_rhs_(0.0, Vm[j], Vm[j + 1], ep);
+      PACMENSLCHKERRQ(ierr);
+    } else {
+      ierr = rhs_(0.0, Vm[j], Vm[j + 1]);
+      PACMENSLCHKERRQ(ierr);
+      // first coefficient: plain dot
+      FSPCHKERRQ(fspvec_dot(hcol + 0, w, Vm[istart]->d_data, n, stream));
+    }
     if (multi) FSPCHKERRQ(fspcomm_allreduce_sum(comm_->nccl, hcol + 0, 1, stream));
     int c = 0;
     for (int i = istart; i <= j; ++i, ++c) {
@@ -305,7 +336,7 @@ int KrylovFsp::GenerateBasis(const Vec &v, int m_start, PetscBool *happy_breakdo
         comm_->stream = saved;
         fsp_graph_t g = nullptr;
         long        nk = 0, expect = 0;
-        for (int j = m_start; j < m_; ++j) expect += 3 + (j - ((q_iop > 0 && j - q_iop + 1 >= 0) ? j - q_iop + 1 : 0) + 1);
+        for (int j = m_start; j < m_; ++j) expect += (fused_rhs_ ? 2 : 3) + (j - ((q_iop > 0 && j - q_iop + 1 >= 0) ? j - q_iop + 1 : 0) + 1);
         if (cerr != 0) {
           fsp_graph_abort_capture(capture_stream_);
         } else if (fsp_graph_end_capture(capture_stream_, &g) == 0) {

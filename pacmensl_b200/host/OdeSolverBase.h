@@ -25,6 +25,10 @@ class PACMENSL_API OdeSolverBase {
   PacmenslErrorCode SetInitialSolution(Vec *_sol);
   PacmenslErrorCode SetFspMatPtr(FspMatrixBase *mat);
   PacmenslErrorCode SetRhs(std::function<PacmenslErrorCode(PetscReal, Vec, Vec)> _rhs);
+  /// Extension: the same operator with a fused epilogue (FspMatrixBase::ActionFused).  Optional; when set, the solvers
+  /// use it where an Action is immediately followed by scaling / inner products (it must compute the same A(t) x).
+  using FusedRhs = std::function<PacmenslErrorCode(PetscReal, Vec, Vec, const fspmat_epilogue &)>;
+  PacmenslErrorCode SetFusedRhs(FusedRhs _rhs) { fused_rhs_ = std::move(_rhs); return 0; }
   int SetTolerances(PetscReal _r_tol, PetscReal _abs_tol);
   PacmenslErrorCode SetCurrentTime(PetscReal t);
   PacmenslErrorCode SetStatusOutput(int iprint);
@@ -50,6 +54,7 @@ class PACMENSL_API OdeSolverBase {
 
   Vec *solution_ = nullptr;
   std::function<int(PetscReal t, Vec x, Vec y)> rhs_;
+  FusedRhs fused_rhs_;
   int            rhs_cost_loc_ = 0;
   FspMatrixBase *fspmat_ = nullptr;
 

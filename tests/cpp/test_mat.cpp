@@ -4,6 +4,7 @@
 //   KAT-M2  FspMatrixConstrained: sum(A * 1) == 0                          (:199-238)
 //   KAT-M3/4 the same through CreateRHSJacobian/ComputeRHSJacobian + MatMult (:153-197, 240-287)
 //   KAT-M5  Action(t, x) == J(t) x for time-varying coefficients at five times (:289-341)
+#include "fsp_models.h"
 #include "pacmensl_test_env.h"
 
 using namespace pacmensl;
@@ -194,4 +195,90 @@ TEST_F(MatrixTest, action_before_generate_is_zero_and_destroy_allows_regeneratio
   ASSERT_EQ(B.GenerateValues(plain, stoichiometry, std::vector<int>(), t_fun, propensity, std::vector<int>(), nullptr, nullptr), -1);
   VecDestroy(&x);
   VecDestroy(&y);
+}
+
+
+// Extension test: ActionFused (operator + solver epilogue in one kernel) against Action followed by separate vector
+// passes, through the host classes exactly as the FSP driver uses them: hog1p (time-varying reaction, K = 5 sinks),
+// incremental regeneration after a bound expansion, work vectors carved from one block (VecDuplicateVecs).
+TEST(FusedAction, matches_action_plus_vector_passes_on_hog1p_with_expansion) {
+  int rank, size;
+  MPI_Comm_rank(PETSC_COMM_WORLD, &rank);
+  MPI_Comm_size(PETSC_COMM_WORLD, &size);
+  fsp_fixture f;
+  ASSERT_EQ(fsp_fixture_get("hog1p", &f), 0);
+  arma::Mat<int> SM(f.SM, f.num_species, f.num_reactions);
+  Model          model(SM, f.prop_t, f.prop_x, nullptr, nullptr, std::vector<int>(f.tv_reactions, f.tv_reactions + f.num_tv));
+  StateSetConstrained fss(PETSC_COMM_WORLD);
+  arma::Row<int>      bounds(f.bounds, f.num_constr);
+  fss.SetStoichiometryMatrix(SM);
+  fss.SetShapeBounds(bounds);
+  fss.SetUp();
+  arma::Mat<int> X0(f.x0, f.num_species, 1);
+  fss.AddStates(X0);
+  ASSERT_FALSE(fss.Expand());
+  FspMatrixConstrained A(PETSC_COMM_WORLD);
+  A.SetIncrementalGeneration(true);
+  for (int round = 0; round < 2; ++round) {
+    if (round == 1) {  // the driver's expansion step
+      for (arma::uword k = 1; k < bounds.n_elem; ++k) bounds[k] = (int) std::round(bounds[k] * 1.25 + 0.5);
+      fss.SetShapeBounds(bounds);
+      ASSERT_FALSE(fss.Expand());
+      A.Destroy();
+    }
+    ASSERT_FALSE(A.GenerateValues(fss, model));
+    const int n_loc = A.GetNumLocalRows();
+    Vec proto;
+    VecCreate(PETSC_COMM_WORLD, &proto);
+    VecSetSizes(proto, n_loc, PETSC_DECIDE);
+    VecSetUp(proto);
+    Vec *W = nullptr;
+    ASSERT_FALSE(VecDuplicateVecsUninitialized(proto, 6, &W));
+    Vec x = W[0], y = W[1], z = W[2], v0 = W[3], ewt = W[4], tmp = W[5];
+    PetscRandom prand;
+    PetscRandomCreate(PETSC_COMM_WORLD, &prand);
+    VecSetRandom(x, prand);
+    VecSetRandom(v0, prand);
+    VecSetRandom(ewt, prand);
+    VecScale(ewt, 100.0);
+    DeviceBuffer<double> out(2);
+    for (double t : {0.0, 30.0}) {
+      // Krylov form: y = A x, <y, v0>
+      fspmat_epilogue ep{};
+      ep.alpha = 1.0; ep.beta = 0.0; ep.scale_dev = nullptr; ep.n_dots = 1;
+      ep.dot_vec_dev[0] = v0->d_data; ep.dot_out_dev = out.get();
+      ASSERT_FALSE(A.ActionFused(t, x, y, ep));
+      ASSERT_FALSE(A.Action(t, x, z));
+      double dot_ref, ynorm, gap, dots[2];
+      VecDot(z, v0, &dot_ref);
+      VecNorm(z, NORM_2, &ynorm);
+      VecAXPY(z, -1.0, y);
+      VecNorm(z, NORM_2, &gap);
+      ASSERT_LE(gap, 1e-14 * ynorm);
+      out.download(dots, 2);
+      if (size > 1) pacmensl_allreduce_sum(PETSC_COMM_WORLD, dots, 1);
+      ASSERT_LE(std::fabs(dots[0] - dot_ref), 1e-11 * ynorm);
+      // GMRES form: y = ewt .* (x - gamma A x), <y, v0>, <y, y>
+      const double gamma = 0.37;
+      ep.alpha = -gamma; ep.beta = 1.0; ep.scale_dev = ewt->d_data; ep.n_dots = 2; ep.dot_vec_dev[1] = nullptr;
+      ASSERT_FALSE(A.ActionFused(t, x, y, ep));
+      ASSERT_FALSE(A.Action(t, x, z));
+      fspvec_wlincomb(tmp->d_data, ewt->d_data, 1.0, x->d_data, -gamma, z->d_data, n_loc, nullptr);
+      double d0, d1;
+      VecDot(tmp, v0, &d0);
+      VecDot(tmp, tmp, &d1);
+      VecNorm(tmp, NORM_2, &ynorm);
+      VecAXPY(tmp, -1.0, y);
+      VecNorm(tmp, NORM_2, &gap);
+      ASSERT_LE(gap, 1e-14 * ynorm);
+      out.download(dots, 2);
+      if (size > 1) pacmensl_allreduce_sum(PETSC_COMM_WORLD, dots, 2);
+      ASSERT_LE(std::fabs(dots[0] - d0), 1e-11 * ynorm * ynorm);
+      ASSERT_LE(std::fabs(dots[1] - d1), 1e-11 * d1);
+    }
+    std::printf("    round %d: %d local rows, fused == separate passes\n", round, n_loc);
+    PetscRandomDestroy(&prand);
+    VecDestroyVecs(6, &W);
+    VecDestroy(&proto);
+  }
 }

@@ -186,3 +186,75 @@ def test_zero_operator_before_generate(cuda):
     y = torch.ones(5, dtype=torch.float64, device="cuda")
     M.action(np.ones(2), torch.ones(5, dtype=torch.float64, device="cuda"), y)  # no values: y untouched by kernel
     assert M.flops() == 0
+
+
+@pytest.mark.parametrize("name,bounds,t", [("random_walk_1d_tv", None, 1.0), ("toggle_custom", [30, 30, 200], 0.0),
+                                           ("hog1p", [3, 6, 6, 5, 5], 25.0), ("birth_death_3d_tv", [21, 17, 13], 4.0)])
+def test_fused_epilogue_matches_separate_passes(cuda, oracle, name, bounds, t):
+    """fspmat_action_fused: y = scale .* (beta x + alpha A x) and <y, v0>, <y, y> in one kernel (the BDF/GMRES and
+    Krylov forms), against the oracle Action followed by numpy; sink rows included."""
+    torch, O = cuda, oracle
+    st = O.StateSet(fixture=name, bounds=bounds) if bounds is not None else O.StateSet(fixture=name)
+    st.expand()
+    A = O.FspMatrix(constrained=True)
+    assert A.generate_fixture(st, name) == 0
+    M = device_matrix_from_oracle(A, st.R)
+    rng = np.random.default_rng(11)
+    x, v0 = rng.random(A.nrows), rng.random(A.nrows)
+    scale = 1.0 / (1e-6 * rng.random(A.nrows) + 1e-3)
+    ierr, ax = A.action(t, x)
+    coef = O.fixture_tcoef(name, t, st.R)[1]
+    xd, vd, sd = _dev(torch, x), _dev(torch, v0), _dev(torch, scale)
+    for alpha, beta, sc, vecs in ((-0.37, 1.0, sd, (vd, None)), (1.0, 0.0, None, (vd,)), (1.0, 0.0, None, ())):
+        yd = torch.full((A.nrows,), np.nan, dtype=torch.float64, device="cuda")
+        out = torch.full((2,), np.nan, dtype=torch.float64, device="cuda")
+        M.action_fused(coef, xd, yd, alpha=alpha, beta=beta, scale=sc, dot_vecs=vecs, dot_out=out)
+        torch.cuda.synchronize()
+        yref = (beta * x + alpha * ax) * (scale if sc is not None else 1.0)
+        y = yd.cpu().numpy()
+        assert rel_err(y, yref) <= TOL
+        o = out.cpu().numpy()
+        if len(vecs) >= 1:
+            assert abs(o[0] - yref @ v0) <= 1e-12 * np.abs(yref * v0).sum()
+        if len(vecs) == 2:
+            assert abs(o[1] - yref @ yref) <= 1e-12 * (yref @ yref)
+    # repeated calls reuse the partial buffers / counter correctly and are deterministic
+    outs = []
+    for _ in range(3):
+        out = torch.zeros(2, dtype=torch.float64, device="cuda")
+        M.action_fused(coef, xd, yd, alpha=-0.37, beta=1.0, scale=sd, dot_vecs=(vd, None), dot_out=out)
+        outs.append(out.cpu().numpy().copy())
+    assert (outs[0] == outs[1]).all() and (outs[1] == outs[2]).all()
+
+
+@pytest.mark.parametrize("bounds", [[3, 10, 10, 10, 10], [3, 17, 36, 13, 22]])
+def test_fused_epilogue_krylov_form_hog1p_sizes(cuda, oracle, bounds):
+    """The Krylov form (alpha = 1, beta = 0, one dot) on the hog1p sets of examples/hog1p.cpp: the initial 58 564-state
+    set and the 857 808-state set of the last expansion (more rows than 8 CTAs/SM x 256: the grid-stride path), with a
+    delta vector (first Krylov step) and a random one, t = 0 (coefficient of the time-varying reaction: 3200)."""
+    torch, O = cuda, oracle
+    st = O.StateSet(fixture="hog1p", bounds=bounds)
+    st.expand()
+    A = O.FspMatrix(constrained=True)
+    assert A.generate_fixture(st, "hog1p") == 0
+    M = device_matrix_from_oracle(A, st.R)
+    coef = O.fixture_tcoef("hog1p", 0.0, st.R)[1]
+    rng = np.random.default_rng(5)
+    delta = np.zeros(A.nrows)
+    delta[0] = 1.0
+    for x in (delta, rng.random(A.nrows)):
+        v0 = rng.random(A.nrows)
+        ierr, ax = A.action(0.0, x)
+        xd, vd = _dev(torch, x), _dev(torch, v0)
+        yd = torch.full((A.nrows,), np.nan, dtype=torch.float64, device="cuda")
+        out = torch.full((2,), np.nan, dtype=torch.float64, device="cuda")
+        M.action_fused(coef, xd, yd, alpha=1.0, beta=0.0, scale=None, dot_vecs=(vd,), dot_out=out)
+        yp = torch.full((A.nrows,), np.nan, dtype=torch.float64, device="cuda")
+        M.action(coef, xd, yp)
+        torch.cuda.synchronize()
+        y = yd.cpu().numpy()
+        assert np.isfinite(y).all()
+        assert rel_err(y, ax) <= TOL
+        assert rel_err(y, yp.cpu().numpy()) <= 1e-15
+        o = out.cpu().numpy()
+        assert abs(o[0] - ax @ v0) <= 1e-12 * max(np.abs(ax * v0).sum(), 1e-300)
