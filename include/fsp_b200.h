@@ -128,6 +128,14 @@ FSP_API int fspvec_lincomb3_wprod_sqsum(double *b_dev, double *v_dev, double c0,
                                         double *out_dev, long n, void *stream);
 /* v *= a ; t = v ./ w */
 FSP_API int fspvec_scale_div(double *v_dev, double a, double *t_dev, const double *w_dev, long n, void *stream);
+/* v *= a ; t = v .* winv   (winv = 1 ./ w from fspvec_ewt_pair: fp64 division halves the bandwidth of such a pass) */
+FSP_API int fspvec_scale_mul(double *v_dev, double a, double *t_dev, const double *winv_dev, long n, void *stream);
+/* d = x .* winv ; acor += d ; ycur = zn0 + acor ; out = sum x_i^2 (== sum (d_i ewt_i)^2 since winv .* ewt == 1) */
+FSP_API int fspvec_newton_update_mul(const double *x_dev, const double *winv_dev, double *acor_dev, const double *zn0_dev,
+                                     double *ycur_dev, double *out_dev, long n, void *stream);
+/* fspvec_ewt that also stores the denominators winv_i = rtol |y_i| + atol = 1 / w_i */
+FSP_API int fspvec_ewt_pair(double *w_dev, double *winv_dev, const double *y_dev, double rtol, double atol, long n,
+                            double *min_out_dev, void *stream);
 /* d = dw ? x ./ dw : x ; acor += d ; ycur = zn0 + acor ; out = sum (d_i ewt_i)^2   (end of a Newton iteration) */
 FSP_API int fspvec_newton_update(const double *x_dev, const double *dw_dev, const double *ewt_dev, double *acor_dev,
                                  const double *zn0_dev, double *ycur_dev, double *out_dev, long n, void *stream);

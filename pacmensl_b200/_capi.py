@@ -89,6 +89,9 @@ SIGNATURES = {
     "fspvec_scale_rsqrt": (ci, [vp, vp, cl, vp]),
     "fspvec_lincomb3_wprod_sqsum": (ci, [vp, vp, cd, vp, cd, vp, cd, vp, vp, vp, cl, vp]),
     "fspvec_scale_div": (ci, [vp, cd, vp, vp, cl, vp]),
+    "fspvec_scale_mul": (ci, [vp, cd, vp, vp, cl, vp]),
+    "fspvec_newton_update_mul": (ci, [vp, vp, vp, vp, vp, vp, cl, vp]),
+    "fspvec_ewt_pair": (ci, [vp, vp, vp, cd, cd, cl, vp, vp]),
     "fspvec_newton_update": (ci, [vp, vp, vp, vp, vp, vp, vp, cl, vp]),
     "fspvec_nordsieck": (ci, [vp, ci, vp, ci, cl, vp]),
     "fspvec_multi_axpy": (ci, [vp, ci, vp, vp, cl, vp]),

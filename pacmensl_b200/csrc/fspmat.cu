@@ -77,9 +77,9 @@ struct Epi {
   int           n_dots;
   const double *vec[2];
   double       *out;
-  double       *partials;  // [(G + 1) * 2]: G main CTAs + one slot for the sink rows
-  unsigned     *counter;
-  int           G;
+  double       *partials;  // [2][pstride]: one slot per main CTA + one slot (index G) for the sink rows
+  long          pstride;
+  int           G;         // number of main CTAs
 };
 
 struct P2PWait {
@@ -319,14 +319,15 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_lean(MatView m, Coefs 
   y[i] = fma(-d, __ldg(x + i), acc);
 }
 
-// Action with fused epilogue (solver hot loops): grid-stride over the rows with G CTAs so that the per-CTA partial
-// inner products stay few; the K sink rows get the same epilogue in the last-arriving sink CTA.
+// Action with fused epilogue (solver hot loops).  Same shape as the lean kernel (1 row per thread, 32 registers, 8
+// CTAs/SM -- a grid-stride variant with few CTAs measured 1.6x slower, profiles/r01_solve_launches_summary.md); every
+// CTA leaves one partial per inner product, the last-arriving sink CTA finishes the K sink rows with the same
+// epilogue and leaves the partial of those rows in the extra slot; a fixed-shape reduction over the partials follows
+// (fspvec_sum), so the results are deterministic.
 template <int P>
-__global__ void __launch_bounds__(kThreads) fsp_action_epi(MatView m, Coefs cf, Epi e, const double *__restrict__ x,
-                                                           double *__restrict__ y) {
+__global__ void __launch_bounds__(kThreads, 8) fsp_action_epi(MatView m, Coefs cf, Epi e, const double *__restrict__ x,
+                                                              double *__restrict__ y) {
   __shared__ double red[32];
-  __shared__ bool   last_cta;
-  double            d0 = 0.0, d1 = 0.0;
   if ((int) blockIdx.x >= m.main_blocks) {
     // ---- sink rows: partial sums per chunk, then the last sink CTA finishes rows n..n+K-1 with the epilogue ----
     __shared__ bool is_last;
@@ -342,84 +343,69 @@ __global__ void __launch_bounds__(kThreads) fsp_action_epi(MatView m, Coefs cf, 
     __threadfence();
     if (threadIdx.x == 0) is_last = (atomicAdd(m.sink_counter, 1u) == (unsigned) m.sink_blocks - 1u);
     __syncthreads();
-    if (is_last) {
-      __threadfence();
-      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-      for (int k = warp; k < m.K; k += nw) {
-        double s = 0.0;
-        for (int b = lane; b < m.sink_blocks; b += 32) {
-          const int seg = m.sb_seg[b];
-          if (seg >= 0 && seg % m.K == k) s = fma(cf.cd[seg / m.K], __ldcg(m.sink_partials + b), s);
-        }
-        s = warp_sum(s);
-        if (lane == 0) {
-          const long i = (long) m.n_rows_main + k;
-          double     v = fma(e.alpha, s, e.beta * __ldg(x + i));
-          if (e.scale) v *= __ldg(e.scale + i);
-          y[i] = v;
-        }
+    if (!is_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = warp; k < m.K; k += nw) {
+      double s = 0.0;
+      for (int b = lane; b < m.sink_blocks; b += 32) {
+        const int seg = m.sb_seg[b];
+        if (seg >= 0 && seg % m.K == k) s = fma(cf.cd[seg / m.K], __ldcg(m.sink_partials + b), s);
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        *m.sink_counter = 0u;
-        for (int k = 0; k < m.K; ++k) {  // fixed order
-          const long   i = (long) m.n_rows_main + k;
-          const double v = y[i];
-          if (e.n_dots > 0) d0 = fma(v, e.vec[0] ? __ldg(e.vec[0] + i) : v, d0);
-          if (e.n_dots > 1) d1 = fma(v, e.vec[1] ? __ldg(e.vec[1] + i) : v, d1);
-        }
-        e.partials[2 * e.G] = d0;
-        e.partials[2 * e.G + 1] = d1;
+      s = warp_sum(s);
+      if (lane == 0) {
+        const long i = (long) m.n_rows_main + k;
+        double     v = fma(e.alpha, s, e.beta * __ldg(x + i));
+        if (e.scale) v *= __ldg(e.scale + i);
+        y[i] = v;
       }
     }
-  } else {
-    const long stride = (long) m.main_blocks * kThreads;
-    for (long i = (long) blockIdx.x * kThreads + threadIdx.x; i < m.n; i += stride) {
-      const int    *cp = m.col + i;
-      const double *op = m.off + i;
-      double        acc = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *m.sink_counter = 0u;
+      double d0 = 0.0, d1 = 0.0;
+      for (int k = 0; k < m.K; ++k) {  // fixed order
+        const long   i = (long) m.n_rows_main + k;
+        const double v = y[i];
+        if (e.n_dots > 0) d0 = fma(v, e.vec[0] ? __ldg(e.vec[0] + i) : v, d0);
+        if (e.n_dots > 1) d1 = fma(v, e.vec[1] ? __ldg(e.vec[1] + i) : v, d1);
+      }
+      if (e.n_dots > 0) e.partials[e.G] = d0;
+      if (e.n_dots > 1) e.partials[(size_t) e.pstride + e.G] = d1;
+    }
+    return;
+  }
+  const int i = (int) blockIdx.x * kThreads + (int) threadIdx.x;
+  double    d0 = 0.0, d1 = 0.0;
+  if (i < m.n) {
+    const int    *cp = m.col + i;
+    const double *op = m.off + i;
+    double        acc = 0.0;
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const int    c = ld_stream(cp + (size_t) p * m.ld);
-        const double o = ld_stream(op + (size_t) p * m.ld);
-        const double xs = c >= 0 ? __ldg(x + c) : 0.0;
-        acc = fma(cf.c[p] * o, xs, acc);
-      }
-      double        d = 0.0;
-      const double *dp = m.diag + i;
-      for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
-      const double xi = __ldg(x + i);
-      double       v = fma(e.alpha, fma(-d, xi, acc), e.beta * xi);
-      if (e.scale) v *= __ldg(e.scale + i);
-      y[i] = v;
-      if (e.n_dots > 0) d0 = fma(v, e.vec[0] ? __ldg(e.vec[0] + i) : v, d0);
-      if (e.n_dots > 1) d1 = fma(v, e.vec[1] ? __ldg(e.vec[1] + i) : v, d1);
+    for (int p = 0; p < P; ++p) {
+      const int    c = ld_stream(cp + (size_t) p * m.ld);
+      const double o = ld_stream(op + (size_t) p * m.ld);
+      const double xs = c >= 0 ? __ldg(x + c) : 0.0;
+      acc = fma(cf.c[p] * o, xs, acc);
     }
-    if (e.n_dots > 0) {
-      const double r0 = block_sum(d0, red);
-      const double r1 = e.n_dots > 1 ? block_sum(d1, red) : 0.0;
-      if (threadIdx.x == 0) {
-        e.partials[2 * blockIdx.x] = r0;
-        e.partials[2 * blockIdx.x + 1] = r1;
-      }
-    }
+    double        d = 0.0;
+    const double *dp = m.diag + i;
+    for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
+    const double xi = __ldg(x + i);
+    double       v = fma(e.alpha, fma(-d, xi, acc), e.beta * xi);
+    if (e.scale) v *= __ldg(e.scale + i);
+    y[i] = v;
+    if (e.n_dots > 0) d0 = v * (e.vec[0] ? __ldg(e.vec[0] + i) : v);
+    if (e.n_dots > 1) d1 = v * (e.vec[1] ? __ldg(e.vec[1] + i) : v);
   }
-  if (e.n_dots == 0) return;
-  // ---- last CTA of the whole grid: fixed-order sum of the partials ----
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last_cta = (atomicAdd(e.counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!last_cta) return;
-  __threadfence();
-  const int slots = e.G + (m.sink_blocks > 0 ? 1 : 0);
-  for (int k = 0; k < e.n_dots; ++k) {
-    double v = 0.0;
-    for (int b = threadIdx.x; b < slots; b += blockDim.x) v += __ldcg(e.partials + 2 * b + k);
-    const double r = block_sum(v, red);
-    if (threadIdx.x == 0) e.out[k] = r;
+  if (e.n_dots > 0) {
+    const double r0 = block_sum(d0, red);
+    if (threadIdx.x == 0) e.partials[blockIdx.x] = r0;
   }
-  if (threadIdx.x == 0) *e.counter = 0u;
+  if (e.n_dots > 1) {
+    const double r1 = block_sum(d1, red);
+    if (threadIdx.x == 0) e.partials[(size_t) e.pstride + blockIdx.x] = r1;
+  }
 }
 
 typedef void (*epi_fn)(MatView, Coefs, Epi, const double *, double *);
@@ -690,7 +676,6 @@ struct fspmat_s {
   int     *d_cta_order = nullptr;      // CTA issue order of the single-kernel peer-memory action
   int      n_ctas = 0, n_interior_ctas = 0;
   double  *d_epi_partials = nullptr;   // fused-epilogue inner-product partials (allocated on first use)
-  unsigned *d_epi_counter = nullptr;
   int     *d_boundary_rows = nullptr;  // rows referencing ghost entries (multi-GPU)
   long     n_boundary = 0;
 };
@@ -700,7 +685,7 @@ static int free_values(fspmat_s *h) {
   pfree(h->d_sink_idx); pfree(h->d_sink_val);
   pfree(h->d_sb_seg); pfree(h->d_sb_begin); pfree(h->d_sb_end);
   pfree(h->d_sink_partials); pfree(h->d_sink_counter); pfree(h->d_boundary_rows);
-  pfree(h->d_epi_partials); pfree(h->d_epi_counter); pfree(h->d_cta_order);
+  pfree(h->d_epi_partials); pfree(h->d_cta_order);
   int variant = h->variant;
   *h = fspmat_s();
   h->variant = variant;
@@ -999,24 +984,24 @@ int fspmat_action_fused(fspmat_t h, const double *coef_host, const double *x, do
                         void *stream) {
   if (!fspmat_fused_supported(h)) { set_error("fspmat_action_fused: not available for this operator (ghost columns, no values or > 16 reactions)"); return -1; }
   if (ep->n_dots < 0 || ep->n_dots > 2) { set_error("fspmat_action_fused: n_dots must be 0, 1 or 2"); return -1; }
-  const int maxG = sm_count() * 8;
-  if (!h->d_epi_partials) {
-    FSP_CUDA_CHECK(pmalloc(&h->d_epi_partials, sizeof(double) * 2 * (size_t) (maxG + 1)));
-    FSP_CUDA_CHECK(pmalloc(&h->d_epi_counter, sizeof(unsigned)));
-    FSP_CUDA_CHECK(cudaMemsetAsync(h->d_epi_counter, 0, sizeof(unsigned), (cudaStream_t) 0));
-    FSP_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t) 0));
-  }
+  const int  n_ctas = (int) std::max<long>(1, ((long) h->n + kThreads - 1) / kThreads);
+  const long pstride = ((long) n_ctas + 1 + 31) / 32 * 32;
+  if (!h->d_epi_partials) FSP_CUDA_CHECK(pmalloc(&h->d_epi_partials, sizeof(double) * 2 * (size_t) pstride));
   Coefs cf; MatView m;
   fill_coefs_view(h, coef_host, cf, m);
   m.sink_blocks = (h->K > 0 && h->owns_sinks) ? h->sink_blocks : 0;
-  m.main_blocks = (int) std::min<long>(maxG, std::max<long>(1, ((long) h->n + kThreads - 1) / kThreads));
+  m.main_blocks = n_ctas;
   Epi e;
   e.alpha = ep->alpha; e.beta = ep->beta; e.scale = ep->scale_dev; e.n_dots = ep->n_dots;
   e.vec[0] = ep->dot_vec_dev[0]; e.vec[1] = ep->dot_vec_dev[1];
-  e.out = ep->dot_out_dev; e.partials = h->d_epi_partials; e.counter = h->d_epi_counter; e.G = m.main_blocks;
+  e.out = ep->dot_out_dev; e.partials = h->d_epi_partials; e.pstride = pstride; e.G = n_ctas;
   epi_fn fn = pick_epi(h->P);
   fn<<<m.main_blocks + m.sink_blocks, kThreads, 0, resolve_stream(stream)>>>(m, cf, e, x, y);
   FSP_LAUNCH_CHECK();
+  // fixed-shape reduction of the per-CTA partials (+ the sink-row slot)
+  const long slots = (long) n_ctas + (m.sink_blocks > 0 ? 1 : 0);
+  for (int k = 0; k < ep->n_dots; ++k)
+    if (fspvec_sum(ep->dot_out_dev + k, h->d_epi_partials + (size_t) k * pstride, slots, stream)) return -1;
   return 0;
 }
 

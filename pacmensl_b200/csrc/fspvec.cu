@@ -137,10 +137,6 @@ struct LinComb3F {
     z[i] = v;
   }
 };
-struct ScaleRsqrtF {
-  double *w; const double *nsq;
-  __device__ void operator()(long i) const { w[i] *= 1.0 / sqrt(*nsq); }
-};
 struct ScatterF {
   double *pn; const double *po; const int *idx;
   __device__ void operator()(long i) const { int j = idx[i]; if (j >= 0) pn[j] = po[i]; }
@@ -283,10 +279,11 @@ struct MdotF {
   }
 };
 struct EwtF {
-  double *w; const double *y; double rtol, atol;
+  double *w; const double *y; double rtol, atol; double *winv;
   __device__ void operator()(long i, double (&acc)[1]) const {
     double t = rtol * fabs(y[i]) + atol;
     w[i] = 1.0 / t;
+    if (winv) winv[i] = t;  // the un-scaling x ./ w of the GMRES loop becomes a multiplication
     acc[0] = fmin(acc[0], t);
   }
 };
@@ -323,6 +320,26 @@ struct ScaleDivF {
     const double vi = v[i] * a;
     v[i] = vi;
     t[i] = vi / w[i];
+  }
+};
+// v *= a ; t = v .* winv    (the same with the reciprocal weights: fp64 division halves the bandwidth of these passes)
+struct ScaleMulF {
+  double *v; double a; double *t; const double *winv;
+  __device__ void operator()(long i) const {
+    const double vi = v[i] * a;
+    v[i] = vi;
+    t[i] = vi * winv[i];
+  }
+};
+// d = x .* winv ; acor += d ; ycur = zn0 + acor ; acc = sum x^2  (== sum (d .* ewt)^2 because winv .* ewt == 1)
+struct NewtonUpdateMulF {
+  const double *x, *winv; double *acor; const double *zn0; double *ycur;
+  __device__ void operator()(long i, double (&acc)[1]) const {
+    const double xi = x[i];
+    const double a = fma(xi, winv[i], acor[i]);
+    acor[i] = a;
+    ycur[i] = zn0[i] + a;
+    acc[0] = fma(xi, xi, acc[0]);
   }
 };
 // d = dw ? x ./ dw : x ; acor += d ; ycur = zn0 + acor ; acc = sum (d .* ewt)^2     (end of a Newton iteration)
@@ -383,6 +400,26 @@ __global__ void __launch_bounds__(kThreads) multi_axpy_kernel(NordArgs a, const 
     const double xi = x[i];
 #pragma unroll
     for (int j = 0; j < L; ++j) a.Z[j][i] = __fma_rn(a.f[j], xi, a.Z[j][i]);
+  }
+}
+
+// w *= 1/sqrt(*nsq): the factor is formed once per thread (not once per element: fp64 sqrt + division), 128-bit
+// accesses when the vector allows it
+__global__ void __launch_bounds__(kThreads) scale_rsqrt_kernel(double *__restrict__ w, const double *__restrict__ nsq, long n,
+                                                               int vec2) {
+  const double s = 1.0 / sqrt(*nsq);
+  const long   stride = (long) gridDim.x * blockDim.x;
+  if (vec2) {
+    double2 *w2 = reinterpret_cast<double2 *>(w);
+    const long n2 = n >> 1;
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+      double2 v = w2[i];
+      v.x *= s; v.y *= s;
+      w2[i] = v;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) w[n - 1] *= s;
+  } else {
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] *= s;
   }
 }
 
@@ -500,7 +537,12 @@ int fspvec_wsqsum(double *out, const double *x, const double *w, long n, void *s
 int fspvec_ewt(double *w, const double *y, double rtol, double atol, long n, double *min_out, void *s) {
   double *tmp = min_out;
   if (!tmp && tmp_scalar(&tmp)) return -1;
-  return launch_reduce<1, RED_MIN>(EwtF{w, y, rtol, atol}, n, tmp, s);
+  return launch_reduce<1, RED_MIN>(EwtF{w, y, rtol, atol, nullptr}, n, tmp, s);
+}
+int fspvec_ewt_pair(double *w, double *winv, const double *y, double rtol, double atol, long n, double *min_out, void *s) {
+  double *tmp = min_out;
+  if (!tmp && tmp_scalar(&tmp)) return -1;
+  return launch_reduce<1, RED_MIN>(EwtF{w, y, rtol, atol, winv}, n, tmp, s);
 }
 int fspvec_ratio_absmax(double *out, const double *x, const double *y, double a, double b, long n, void *s) {
   if (launch_reduce<1, RED_MIN>(RatioAbsMaxF{x, y, a, b}, n, out, s)) return -1;
@@ -512,7 +554,13 @@ int fspvec_axpy_dot(double *w, const double *h, double sign, const double *v, co
                     void *s) {
   return launch_reduce<1, RED_SUM>(AxpyDotF{w, h, sign, v, u}, n, out, s);
 }
-int fspvec_scale_rsqrt(double *w, const double *nsq, long n, void *s) { return launch_map(ScaleRsqrtF{w, nsq}, n, s); }
+int fspvec_scale_rsqrt(double *w, const double *nsq, long n, void *s) {
+  if (n <= 0) return 0;
+  const int vec2 = aligned16(w) ? 1 : 0;
+  scale_rsqrt_kernel<<<grid_for(vec2 ? n / 2 : n, 2), kThreads, 0, resolve_stream(s)>>>(w, nsq, n, vec2);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
 
 int fspvec_lincomb3_wprod_sqsum(double *b, double *v, double c0, const double *x0, double c1, const double *x1, double c2,
                                 const double *x2, const double *w, double *out, long n, void *s) {
@@ -520,6 +568,13 @@ int fspvec_lincomb3_wprod_sqsum(double *b, double *v, double c0, const double *x
 }
 int fspvec_scale_div(double *v, double a, double *t, const double *w, long n, void *s) {
   return launch_map(ScaleDivF{v, a, t, w}, n, s);
+}
+int fspvec_scale_mul(double *v, double a, double *t, const double *winv, long n, void *s) {
+  return launch_map(ScaleMulF{v, a, t, winv}, n, s);
+}
+int fspvec_newton_update_mul(const double *x, const double *winv, double *acor, const double *zn0, double *ycur,
+                             double *out, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(NewtonUpdateMulF{x, winv, acor, zn0, ycur}, n, out, s);
 }
 int fspvec_newton_update(const double *x, const double *dw, const double *ewt, double *acor, const double *zn0,
                          double *ycur, double *out, long n, void *s) {

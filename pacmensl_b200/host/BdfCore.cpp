@@ -37,12 +37,12 @@ BdfCore::~BdfCore() { Free(); }
 
 void BdfCore::Free() {
   for (auto &z : zn_) if (z) VecDestroy(&z);
-  for (Vec *v : {&ewt_, &y_, &acor_, &tempv_, &ftemp_, &xcor_, &vtemp_, &delta_}) if (*v) VecDestroy(v);
+  for (Vec *v : {&ewt_, &ewt_inv_, &y_, &acor_, &tempv_, &ftemp_, &xcor_, &vtemp_, &delta_}) if (*v) VecDestroy(v);
   for (auto &v : V_) if (v) VecDestroy(&v);
   V_.clear();
   for (auto &zs : znS_) for (auto &v : zs) if (v) VecDestroy(&v);
   znS_.clear();
-  for (auto *vv : {&ewtS_, &acorS_, &yS_, &ftempS_}) { for (auto &v : *vv) if (v) VecDestroy(&v); vv->clear(); }
+  for (auto *vv : {&ewtS_, &ewtS_inv_, &acorS_, &yS_, &ftempS_}) { for (auto &v : *vv) if (v) VecDestroy(&v); vv->clear(); }
   ns_ = 0;
 }
 
@@ -59,15 +59,23 @@ int BdfCore::wrms(Vec v, Vec w, double *out) {
   return 0;
 }
 
-int BdfCore::ewt_set(Vec y, Vec ewt) {
-  // cvEwtSetSS: ewt_i = 1 / (rtol |y_i| + atol); fails if any denominator is <= 0
+int BdfCore::ewt_set(Vec y, Vec ewt, Vec ewt_inv) {
+  // cvEwtSetSS: ewt_i = 1 / (rtol |y_i| + atol); fails if any denominator is <= 0.  The denominators are kept too
+  // (ewt_inv): every "./ ewt" of the scaled GMRES loop becomes a multiplication.
   double *tmp = hdev_.get();
-  VCHK(fspvec_ewt(ewt->d_data, y->d_data, rtol_, atol_, n_local_, tmp, stream_));
+  VCHK(fspvec_ewt_pair(ewt->d_data, ewt_inv->d_data, y->d_data, rtol_, atol_, n_local_, tmp, stream_));
   double mn = 0.0;
   VCHK(fsp_memcpy_d2h(&mn, tmp, sizeof(double), stream_));
   double neg = -mn;
   if (pacmensl_allreduce_max(comm_, &neg, 1)) return BDF_MEM_FAIL;
   return (-neg) > 0.0 ? 0 : BDF_ILL_EWT;
+}
+
+Vec BdfCore::inv_of(Vec ewt) const {
+  if (ewt == ewt_) return ewt_inv_;
+  for (size_t is = 0; is < ewtS_.size(); ++is)
+    if (ewt == ewtS_[is]) return ewtS_inv_[is];
+  return nullptr;
 }
 
 int BdfCore::rhs(double t, Vec y, Vec ydot) {
@@ -85,7 +93,7 @@ int BdfCore::Init(double t0, Vec y0, RhsFn f, JtvFn jtv, double tout_hint) {
   n_global_ = (double) ng;
   tout_hint_ = tout_hint;
   for (int j = 0; j <= QMAX; ++j) if (alloc_like(y0, &zn_[j])) return BDF_MEM_FAIL;
-  for (Vec *v : {&ewt_, &y_, &acor_, &tempv_, &ftemp_, &xcor_, &vtemp_, &delta_}) if (alloc_like(y0, v)) return BDF_MEM_FAIL;
+  for (Vec *v : {&ewt_, &ewt_inv_, &y_, &acor_, &tempv_, &ftemp_, &xcor_, &vtemp_, &delta_}) if (alloc_like(y0, v)) return BDF_MEM_FAIL;
   if (hdev_.resize((size_t) (maxl_ + 8) * 2)) return BDF_MEM_FAIL;
   VCHK(VecCopy(y0, zn_[0]));
   q_ = 1; L_ = 2; qprime_ = 1; qwait_ = L_; qu_ = 0; nscon_ = 0; indx_acor_ = QMAX;
@@ -105,11 +113,11 @@ int BdfCore::InitSens(int ns, Vec *s0, SensRhsFn fs, bool errcon) {
   errcon_ = errcon;
   fs_ = std::move(fs);
   znS_.assign(ns, std::vector<Vec>(QMAX + 1, nullptr));
-  ewtS_.assign(ns, nullptr); acorS_.assign(ns, nullptr); yS_.assign(ns, nullptr); ftempS_.assign(ns, nullptr);
+  ewtS_.assign(ns, nullptr); ewtS_inv_.assign(ns, nullptr); acorS_.assign(ns, nullptr); yS_.assign(ns, nullptr); ftempS_.assign(ns, nullptr);
   acnrmS_.assign(ns, 0.0);
   for (int is = 0; is < ns; ++is) {
     for (int j = 0; j <= QMAX; ++j) if (alloc_like(zn_[0], &znS_[is][j])) return BDF_MEM_FAIL;
-    if (alloc_like(zn_[0], &ewtS_[is]) || alloc_like(zn_[0], &acorS_[is]) || alloc_like(zn_[0], &yS_[is]) ||
+    if (alloc_like(zn_[0], &ewtS_inv_[is]) || alloc_like(zn_[0], &ewtS_[is]) || alloc_like(zn_[0], &acorS_[is]) || alloc_like(zn_[0], &yS_[is]) ||
         alloc_like(zn_[0], &ftempS_[is])) return BDF_MEM_FAIL;
     VCHK(VecCopy(s0[is], znS_[is][0]));
   }
@@ -363,11 +371,12 @@ int BdfCore::lin_solve(Vec b, Vec ewt, double ss_b, double tn, bool first_newton
   }
   const double delta = deltar * std::sqrt(n_global_);
   const bool   multi = comm_ && comm_->size > 1;
+  Vec          ewt_inv = inv_of(ewt);  // 1 ./ ewt: the un-scalings "./ s2" are multiplications
   const double beta = std::sqrt(ss_b);
   double       rho = beta;
   if (rho <= delta) { *converged = 1; return 0; }
   // V0 /= beta and vtemp = V0 ./ s2 in one pass
-  VCHK(fspvec_scale_div(V_[0]->d_data, 1.0 / beta, vtemp_->d_data, ewt->d_data, n_local_, stream_));
+  VCHK(fspvec_scale_mul(V_[0]->d_data, 1.0 / beta, vtemp_->d_data, ewt_inv->d_data, n_local_, stream_));
 
   const int lmax = maxl_;
   std::vector<std::vector<double>> Hes((size_t) lmax + 1, std::vector<double>((size_t) lmax, 0.0));
@@ -464,9 +473,9 @@ int BdfCore::lin_solve(Vec b, Vec ewt, double ss_b, double tn, bool first_newton
     // another iteration follows: normalise V_{l+1} and form its unscaled copy vtemp = V_{l+1} ./ s2 in one pass (the
     // last basis vector of a finished solve is never read, so it is neither normalised nor divided)
     if (l + 1 < lmax && new_norm > 0.0)
-      VCHK(fspvec_scale_div(w, 1.0 / new_norm, vtemp_->d_data, ewt->d_data, n_local_, stream_));
+      VCHK(fspvec_scale_mul(w, 1.0 / new_norm, vtemp_->d_data, ewt_inv->d_data, n_local_, stream_));
     else if (l + 1 < lmax)
-      VCHK(fspvec_div(vtemp_->d_data, w, ewt->d_data, n_local_, stream_));
+      VCHK(fspvec_prod(vtemp_->d_data, w, ewt_inv->d_data, n_local_, stream_));
   }
   // least-squares solution: yg = beta * Q e1 ; solve R yg = .
   const int lp1 = l_used + 1;
@@ -534,8 +543,12 @@ int BdfCore::nls(Vec zn0, Vec zn1, Vec ewt, Vec acor, Vec ycur, Vec ftemp, int s
     if (r > 0 || !conv) return CONV_FAIL;
     // delta = xsrc (./ ewt) ; acor += delta ; ycur = zn0 + acor ; del = wrms(delta) -- one pass
     if (!xsrc) { VCHK(fspvec_set(delta_->d_data, 0.0, n_local_, stream_)); xsrc = delta_; divide = false; }
-    VCHK(fspvec_newton_update(xsrc->d_data, divide ? ewt->d_data : nullptr, ewt->d_data, acor->d_data, zn0->d_data,
-                              ycur->d_data, red, n_local_, stream_));
+    if (divide)
+      VCHK(fspvec_newton_update_mul(xsrc->d_data, inv_of(ewt)->d_data, acor->d_data, zn0->d_data, ycur->d_data, red,
+                                    n_local_, stream_));
+    else
+      VCHK(fspvec_newton_update(xsrc->d_data, nullptr, ewt->d_data, acor->d_data, zn0->d_data, ycur->d_data, red,
+                                n_local_, stream_));
     double ss_d = 0.0;
     if (global_sum(red, &ss_d)) return BDF_MEM_FAIL;
     del = std::sqrt(ss_d / n_global_);
@@ -738,11 +751,11 @@ void BdfCore::prepare_next_step(double dsm) {
 int BdfCore::Step(double *t_reached, Vec yout, Vec *sout) {
   vec_status_ = 0;
   if (first_) {
-    if (ewt_set(zn_[0], ewt_)) return BDF_ILL_EWT;
+    if (ewt_set(zn_[0], ewt_, ewt_inv_)) return BDF_ILL_EWT;
     int r = rhs(tn_, zn_[0], zn_[1]);
     if (r != 0) return BDF_RHS_FAIL;
     for (int is = 0; is < ns_; ++is) {
-      if (ewt_set(znS_[is][0], ewtS_[is])) return BDF_ILL_EWT;
+      if (ewt_set(znS_[is][0], ewtS_[is], ewtS_inv_[is])) return BDF_ILL_EWT;
       r = fs_(is, tn_, zn_[0], zn_[1], znS_[is][0], znS_[is][1]);
       if (r != 0) return BDF_RHS_FAIL;
     }
@@ -755,8 +768,8 @@ int BdfCore::Step(double *t_reached, Vec yout, Vec *sout) {
     for (int is = 0; is < ns_; ++is) VCHK(fspvec_scale(znS_[is][1]->d_data, h_, n_local_, stream_));
     first_ = false;
   } else {
-    if (ewt_set(zn_[0], ewt_)) return BDF_ILL_EWT;
-    for (int is = 0; is < ns_; ++is) if (ewt_set(znS_[is][0], ewtS_[is])) return BDF_ILL_EWT;
+    if (ewt_set(zn_[0], ewt_, ewt_inv_)) return BDF_ILL_EWT;
+    for (int is = 0; is < ns_; ++is) if (ewt_set(znS_[is][0], ewtS_[is], ewtS_inv_[is])) return BDF_ILL_EWT;
   }
 
   const double saved_t = tn_;

@@ -80,6 +80,7 @@ class BdfCore {
 
   // Nordsieck history and work vectors
   Vec zn_[LMAX + 1] = {nullptr};
+  Vec ewt_inv_ = nullptr;  ///< rtol |y| + atol = 1 ./ ewt_
   Vec ewt_ = nullptr, y_ = nullptr, acor_ = nullptr, tempv_ = nullptr, ftemp_ = nullptr;
   // GMRES workspace (basis allocated on demand up to maxl_ + 1)
   std::vector<Vec> V_;
@@ -91,7 +92,7 @@ class BdfCore {
   int  ns_ = 0;
   bool errcon_ = false;
   std::vector<std::vector<Vec>> znS_;  // [is][j]
-  std::vector<Vec> ewtS_, acorS_, yS_, ftempS_;
+  std::vector<Vec> ewtS_, ewtS_inv_, acorS_, yS_, ftempS_;
   std::vector<double> acnrmS_;
 
   // integrator state (names follow the CVODE literature)
@@ -106,7 +107,8 @@ class BdfCore {
 
   // helpers
   int  alloc_like(Vec proto, Vec *out);
-  int  ewt_set(Vec y, Vec ewt);
+  int  ewt_set(Vec y, Vec ewt, Vec ewt_inv);
+  Vec  inv_of(Vec ewt) const;
   int  wrms(Vec v, Vec w, double *out);
   int  rhs(double t, Vec y, Vec ydot);
   int  initial_step(double tout);

@@ -67,6 +67,36 @@ def _worker(rank, world, port, name, bounds, ret):
     ghost = ghost.numpy()
     assert np.array_equal(ghost, xg[ghost_gids])
 
+    # peer-memory form of the same exchange (fsphalo_*): every sender learns where its segment starts in the receiver's
+    # ghost window (remote_off) and "stores" its values there, two parities, three epochs with changing x
+    from pacmensl_b200.partition import cta_issue_order, window_offsets
+    recv_off = window_offsets(recv_counts)
+    remote_off = torch.zeros(world, dtype=torch.int64)
+    dist.all_to_all_single(remote_off, torch.from_numpy(recv_off[:world].copy()))
+    send_off = window_offsets(send_counts.numpy())
+    window = np.full((2, len(ghost_gids)), np.nan)
+    for epoch in (1, 2, 3):
+        par = epoch & 1
+        xe = x_loc * epoch
+        # what lands in peer p's window: (offset, values); delivered here by an all-to-all of offsets and values
+        offs_in = torch.zeros(world, dtype=torch.int64)
+        dist.all_to_all_single(offs_in, remote_off.clone())
+        vals_in = torch.zeros(len(ghost_gids), dtype=torch.float64)
+        dist.all_to_all_single(vals_in, torch.from_numpy(xe[send_idx]), output_split_sizes=recv_counts.tolist(),
+                               input_split_sizes=send_counts.tolist())
+        pos = 0
+        for p in range(world):
+            cnt = int(recv_counts[p])
+            window[par, int(offs_in[p]): int(offs_in[p]) + cnt] = vals_in[pos: pos + cnt].numpy()
+            pos += cnt
+        assert np.array_equal(window[par], xg[ghost_gids] * epoch)
+    assert send_off[-1] == len(send_idx)
+    order, n_int = cta_issue_order(n_loc, col_local, threads=8)
+    assert sorted(order.tolist()) == list(range((n_loc + 7) // 8))
+    ghost_rows = np.nonzero((col_local <= -2).any(axis=0))[0]
+    assert not set((ghost_rows // 8).tolist()) & set(order[:n_int].tolist())
+    assert set((ghost_rows // 8).tolist()) == set(order[n_int:].tolist())
+
     # local rows of the fused operator
     y_loc = np.zeros(n_loc)
     for p in range(P):
@@ -120,3 +150,20 @@ def test_block_layout_rule():
     assert block_layout(10, 4).tolist() == [0, 3, 6, 8, 10]
     assert block_layout(13, 2).tolist() == [0, 7, 13]
     assert block_layout(3, 8).tolist() == [0, 1, 2, 3, 3, 3, 3, 3, 3]
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_epoch_protocol_two_parities_suffice_under_any_interleaving(world):
+    """The peer-memory halo keeps only TWO ghost buffers per rank.  Randomised interleavings of the ranks' push/consume
+    steps (including ranks racing ahead as far as the protocol lets them) never read overwritten data."""
+    sys.path.insert(0, ROOT)
+    from pacmensl_b200.partition import EpochProtocol
+    rng = np.random.default_rng(world)
+    for trial in range(20):
+        prot = EpochProtocol(world)
+        bias = rng.random(world) + 0.05   # some ranks are much "faster" than others
+        bias /= bias.sum()
+        for _ in range(4000):
+            prot.step(int(rng.choice(world, p=bias)))
+        assert min(prot.consumed) >= 5
+        assert max(prot.consumed) - min(prot.consumed) <= 1   # nobody can run more than one epoch ahead
