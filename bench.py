@@ -296,11 +296,15 @@ def main():
                                    "FspMatrixConstrained::Action(t,x,y)" % ("x".join(str(d) for d in dims), N, "R_tv=3" if args.tv else "time-invariant"),
                        "states": N, "bytes_per_row": lattice_bytes_per_row(args.tv),
                        "l2": "inputs (%.2f GB per Action) exceed the 126 MB L2; no flush needed" % (bytes_total / 1e9),
-                       "partition": "1 block" if world == 1 else "%d contiguous row blocks (BLOCK), NCCL halo exchange + K-double sink all-reduce per Action" % world,
+                       "partition": "1 block" if world == 1 else (
+                           "%d contiguous row blocks (BLOCK); " % world + (
+                               "peer-memory path: fused pack+store+signal halo kernel over CUDA IPC windows (NVLink), interior pass, "
+                               "boundary kernel waiting on peer flags in device code, sink slots summed by the owner; no NCCL call per Action"
+                               if api.p2p_enabled() else "NCCL halo exchange + K-double sink all-reduce per Action")),
                        "kernel_variant": args.variant, "build_seconds": round(t_build, 2)},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "fsp_action_lean<6,*> (pacmensl_b200/csrc/fspmat.cu)" + ("" if world == 1 else " + halo exchange (rank 0 share)"),
+                         "kernel": ("fsp_action_lean<6,0>" if world == 1 else ("fsp_action_lean<6,2> + fsp_action_boundary_p2p_kernel (+ halo_push_kernel, sink kernel)" if api.p2p_enabled() else "fsp_action_lean<6,2> + boundary rows + NCCL halo (rank 0 share)")) + " (pacmensl_b200/csrc/fspmat.cu)",
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_local},
             "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks,
         }

@@ -1022,7 +1022,18 @@ int fspmat_action_sinks_p2p(fspmat_t h, const double *coef_host, const double *x
 int fspmat_action_p2p(fspmat_t h, const double *coef_host, const double *x, double *y, const fsphalo_epoch *e, void *stream) {
   if (!h->has_values) return 0;
   p2p_fn fn = pick_p2p(h->P);
-  if (!fn || !h->d_cta_order) { set_error("fspmat_action_p2p: needs an operator with ghost columns and <= 16 reactions"); return -1; }
+  if (!fn) { set_error("fspmat_action_p2p: supports 1..16 reactions (got %d)", h->P); return -1; }
+  if (!h->d_cta_order) {
+    // this rank references no ghost entry (or owns no state at all): identity order; the last CTA still waits for the
+    // peers' flags -- every rank must, the flag wait is what paces the reuse of the two ghost buffers
+    const int n_ctas = (int) std::max<long>(1, ((long) h->n + kThreads - 1) / kThreads);
+    std::vector<int> order((size_t) n_ctas);
+    for (int q = 0; q < n_ctas; ++q) order[(size_t) q] = q;
+    FSP_CUDA_CHECK(pmalloc(&h->d_cta_order, sizeof(int) * n_ctas));
+    FSP_CUDA_CHECK(cudaMemcpy(h->d_cta_order, order.data(), sizeof(int) * n_ctas, cudaMemcpyHostToDevice));
+    h->n_ctas = n_ctas;
+    h->n_interior_ctas = n_ctas - 1;
+  }
   Coefs cf; MatView m;
   fill_coefs_view(h, coef_host, cf, m);
   m.cta_order = h->d_cta_order;

@@ -277,7 +277,11 @@ int FspMatrixBase::EvaluatePropensitiesHost_(fspset_t dset, int n_species, long 
   const long kSuper = 1L << 18;   // states per pinned buffer
   const int  R = (int) enable_reactions_.size();
   if (count <= 0 || R == 0) return 0;
-  static const bool pipeline = [] { const char *e = std::getenv("FSP_HOST_PIPELINE"); return !(e && e[0] == '0'); }();
+  // Opt-in (FSP_HOST_PIPELINE=1): on the GPU boxes of this pool the pipelined form measured SLOWER than one call per
+  // reaction over all new states (hog1p, 23.9 M states: matrix generation 2.9-3.3 s vs 2.0 s on the same box) --
+  // the pinned buffers are probably NUMA-remote for the calling thread, which costs the callbacks more than the
+  // cache blocking and the copy overlap win.
+  static const bool pipeline = [] { const char *e = std::getenv("FSP_HOST_PIPELINE"); return e && e[0] == '1'; }();
   if (count <= kBlock || !pipeline) {  // small increments: no pipeline needed
     std::vector<int>    st((size_t) count * n_species);
     std::vector<double> vals((size_t) count);
@@ -468,7 +472,11 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
     //   main stream : interior pass; then the boundary kernel waits for the peers' flags in device code, redoes the
     //                 rows with ghost entries and (sink owner) adds the slots in rank order into y[n..n+K)
     fsphalo_epoch ep;
-    static const bool split = [] { const char *e = std::getenv("FSP_P2P_SPLIT"); return e && e[0] == '1'; }();
+    // Default: interior pass + boundary kernel that waits for the peers' flags (validated and measured on 2 and 8
+    // GPUs).  FSP_P2P_SINGLE=1 selects the single-kernel form (ghost-free CTAs first, waiting CTAs last): correct, but
+    // it measured 0.96 ms against 0.74 ms per Action on 2 GPUs (465^3 lattice) -- CTAs are evidently not issued
+    // strictly in blockIdx order, so some waiting CTAs start early and hold SM slots; kept for further work.
+    static const bool split = [] { const char *e = std::getenv("FSP_P2P_SINGLE"); return !(e && e[0] == '1'); }();
     FSPCHKERRQ(fsp_event_record(ev_x_ready_, stream));
     FSPCHKERRQ(fsp_stream_wait_event(comm_stream_, ev_x_ready_));
     FSPCHKERRQ(fsphalo_begin(halo_, x->d_data, comm_stream_, &ep));
@@ -487,8 +495,8 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
       FSPCHKERRQ(fsp_stream_wait_event(stream, ev_comm_done_));
       return 0;
     }
-    // FSP_P2P_SPLIT=1 (A/B diagnostics): interior pass, then a boundary kernel that waits for the flags and redoes the
-    // rows with ghost entries
+    // interior pass over all rows (ghost entries count 0), then a boundary kernel that waits for the peers' flags in
+    // device code and redoes the rows with ghost entries (+ the sink owner's final sum)
     FSPCHKERRQ(fspmat_action_phase(dmat_, coefs, x->d_data, nullptr, y->d_data, nullptr, 1, stream));
     FSPCHKERRQ(fsp_stream_wait_event(stream, ev_comm_done_));
     FSPCHKERRQ(fspmat_action_boundary_p2p(dmat_, coefs, x->d_data, y->d_data, &ep, stream));
