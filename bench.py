@@ -36,6 +36,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-expand", action="store_true", help="skip the Expand() closure check of the lattice set")
+    ap.add_argument("--no-solve", action="store_true", help="skip the solve-to-t_f side measurement (N = 1 only)")
+    ap.add_argument("--solve-lattice", type=int, default=215, help="lattice edge of the GPU solve-to-t_f measurement")
+    ap.add_argument("--cpu-solve-lattice", type=int, default=128, help="lattice edge of the bounded CPU solve sample")
     return ap.parse_args()
 
 
@@ -138,6 +141,40 @@ def cpu_baseline(args, steps=None, warmup=3):
             "sample": "%d^3 = %d-state lattice, median of %d reference-shaped (SpMV+AXPY per matrix) OpenMP Actions; "
                       "oracle/fsp_oracle.c (the PETSc reference cannot be built in this image)" % (L, n, steps),
             "ms_per_step": med * 1e3}
+
+
+def solve_to_tf(args):
+    """Second half of BASELINE's metric: wall time of a KrylovFsp solve to t_f = 1 on the fixed lattice (p0 = delta(0)).
+    GPU: examples/lattice_solve.cpp (the host classes on the CUDA library), best of 2, at --solve-lattice and at the CPU
+    sample size; CPU: the oracle's restatement of KrylovFsp (oracle/krylov_oracle.py) on the bounded sample."""
+    import numpy as np
+    out = {"solver": "KrylovFsp (defaults: IOP q=2, m in [25,60], atol 1e-14)", "t_final": 1.0}
+    exe = os.path.join(ROOT, "build", "examples", "lattice_solve")
+
+    def gpu(edge):
+        r = subprocess.run([exe, "--edge", str(edge), "--solver", "krylov", "--repeat", "2"], capture_output=True, text=True,
+                           timeout=240, env=dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0"))
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"states": j["states"], "wall_s": j["wall_s"], "action_calls": j["action_calls"],
+                "l1_err_vs_poisson": j["l1_err_vs_poisson"]}
+
+    out["gpu"] = gpu(args.solve_lattice)
+    out["gpu_at_cpu_sample_size"] = gpu(args.cpu_solve_lattice)
+    from oracle import oracle as O
+    from oracle.krylov_oracle import KrylovOracle
+    L = args.cpu_solve_lattice
+    st = O.StateSet(fixture="birth_death_3d", bounds=[L - 1] * 3)
+    st.expand()
+    A = O.FspMatrix(constrained=True)
+    assert A.generate_fixture(st, "birth_death_3d") == 0
+    p0 = np.zeros(A.nrows)
+    p0[st.state2index(np.array([[0, 0, 0]], dtype=np.int32))[0]] = 1.0
+    kry = KrylovOracle(A)
+    t0 = time.perf_counter()
+    p = kry.solve(p0, 1.0)
+    out["cpu"] = {"states": st.n, "wall_s": time.perf_counter() - t0, "action_calls": kry.num_rhs, "cores": O.num_threads(),
+                  "kind": "port", "sum_p": float(p.sum())}
+    return out
 
 
 def run_reference(args):
@@ -276,6 +313,7 @@ def main():
                "call": "pfsp_mat_action_host (include/pacmensl_b200_host.h) with pinned host x, y"}
         del xh, yh
 
+    pending_line = {}
     if rank == 0:
         peak, peak_src = measured_peak()
         ach = bytes_local / (kms * 1e-3) / 1e9
@@ -311,13 +349,27 @@ def main():
         if not args.no_cpu_baseline:
             cb = cpu_baseline(args)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        line["_solve_pending"] = world == 1 and not args.no_solve
+        pending_line = line
+        print_now = not line["_solve_pending"]
+        if print_now:
+            del line["_solve_pending"]
+            print(json.dumps(line))
     if dist is not None:
         dist.barrier()
-    del lat
+    del lat, x, y
     api.finalize()
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0 and pending_line.get("_solve_pending"):
+        # side measurement after the device memory of the Action workload has been released; never fatal
+        del pending_line["_solve_pending"]
+        try:
+            torch.cuda.empty_cache()
+            pending_line["solve_to_tf"] = solve_to_tf(args)
+        except Exception as e:  # noqa: BLE001
+            pending_line["solve_to_tf"] = {"unavailable": repr(e)[:200]}
+        print(json.dumps(pending_line))
 
 
 if __name__ == "__main__":

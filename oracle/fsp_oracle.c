@@ -701,6 +701,39 @@ ORC_API int orc_fixture_tcoef(const char *name, double t, double *out) {
   return f.prop_t(t, f.num_reactions, out, NULL);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * BLAS-1 kernels of the CPU restatement of KrylovFsp (oracle/krylov_oracle.py): the PETSc calls of
+ * src/OdeSolver/KrylovFsp.cpp:280-309 (VecDot, VecAXPY, VecNorm, VecScale) and :244-252 (VecMAXPY),
+ * OpenMP over the host cores.
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API double orc_vec_dot(long n, const double *x, const double *y) {
+  double s = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : s)
+  for (long i = 0; i < n; ++i) s += x[i] * y[i];
+  return s;
+}
+ORC_API void orc_vec_axpy(long n, double a, const double *x, double *y) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) y[i] += a * x[i];
+}
+ORC_API void orc_vec_scale(long n, double a, double *y) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) y[i] *= a;
+}
+ORC_API void orc_vec_copy(long n, const double *x, double *y) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) y[i] = x[i];
+}
+/* y = sum_k c[k] X[k]  (X: m rows of leading dimension ld) */
+ORC_API void orc_vec_maxpy(long n, int m, const double *c, const double *X, long ld, double *y) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < n; ++i) {
+    double acc = 0.0;
+    for (int k = 0; k < m; ++k) acc += c[k] * X[(size_t) k * ld + i];
+    y[i] = acc;
+  }
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

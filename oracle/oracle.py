@@ -75,6 +75,11 @@ def lib():
             "orc_mat_generate_fixture": (ci, [vp, vp, C.c_char_p]),
             "orc_fixture_tcoef": (ci, [C.c_char_p, cd, dp]),
             "orc_num_threads": (ci, []),
+            "orc_vec_dot": (cd, [C.c_long, dp, dp]),
+            "orc_vec_axpy": (None, [C.c_long, cd, dp, dp]),
+            "orc_vec_scale": (None, [C.c_long, cd, dp]),
+            "orc_vec_copy": (None, [C.c_long, dp, dp]),
+            "orc_vec_maxpy": (None, [C.c_long, ci, dp, dp, C.c_long, dp]),
         }
         for name, (res, args) in sigs.items():
             f = getattr(L, name)
