@@ -95,15 +95,21 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// spin until *flag >= epoch; false (and *err = 1) after kSpinTimeoutNs so that a lost peer cannot hang the GPU
+// spin until *flag >= epoch; false (and *err = 1) after kSpinTimeoutNs so that a lost peer cannot hang the GPU.  Once
+// the error flag is up (an earlier wait timed out) every later wait gives up after ~1000 polls instead of another
+// 20 s, so a failed rank costs its peers one time-out, not one per kernel.
 __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long epoch, unsigned int *err) {
   if (ld_acquire_sys(flag) >= epoch) return true;
   const unsigned long long t0 = global_ns();
+  unsigned                 polls = 0;
   while (ld_acquire_sys(flag) < epoch) {
     __nanosleep(64);
-    if (global_ns() - t0 > kSpinTimeoutNs) {
-      if (err) *(volatile unsigned int *) err = 1u;
-      return false;
+    if ((++polls & 1023u) == 0u) {
+      if (err && *(volatile unsigned int *) err) return false;
+      if (global_ns() - t0 > kSpinTimeoutNs) {
+        if (err) *(volatile unsigned int *) err = 1u;
+        return false;
+      }
     }
   }
   return true;
