@@ -291,6 +291,12 @@ FSP_API int fspmat_action_fused(fspmat_t h, const double *coef_host, const doubl
  *   phase 0  == fspmat_action (everything in one launch) */
 FSP_API int fspmat_action_phase(fspmat_t h, const double *coef_host, const double *x_dev, const double *ghost_dev,
                                 double *y_dev, double *sink_out_dev, int phase, void *stream);
+/* Host-vector pipeline (single GPU): rows [row_begin, row_end) of y = A(t) x; with_sinks != 0 adds the K sink rows
+ * (which need all of x).  fspmat_chunk_max_columns tells which prefix of x every chunk of rows references, so a chunk
+ * can run as soon as that prefix has been uploaded while its part of y is downloaded behind it. */
+FSP_API int fspmat_action_rows(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev, long row_begin,
+                               long row_end, int with_sinks, void *stream);
+FSP_API int fspmat_chunk_max_columns(fspmat_t h, long chunk_rows, int n_chunks, int *chunk_max_host);
 FSP_API int fspmat_num_boundary_rows(fspmat_t h, long *n);
 /* Peer-memory variants (see fsphalo_* below).  sinks: the K partial sink sums go straight into the sink owner's slot
  * row (e->sink_slot_remote) followed by the flag; boundary: waits in device code for every peer's halo flag, redoes

@@ -125,6 +125,8 @@ SIGNATURES = {
     "fspmat_clear": (ci, [vp]),
     "fspmat_action": (ci, [vp, dp, vp, vp, vp, vp, vp]),
     "fspmat_action_phase": (ci, [vp, dp, vp, vp, vp, vp, ci, vp]),
+    "fspmat_action_rows": (ci, [vp, dp, vp, vp, cl, cl, ci, vp]),
+    "fspmat_chunk_max_columns": (ci, [vp, cl, ci, ip]),
     "fspmat_num_boundary_rows": (ci, [vp, lp]),
     "fspmat_fused_supported": (ci, [vp]),
     "fspmat_action_fused": (ci, [vp, dp, vp, vp, vp, vp]),

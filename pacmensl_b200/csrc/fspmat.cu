@@ -62,6 +62,7 @@ struct MatView {
   int           ghost_zero;    // 1: ghost entries contribute 0 (interior pass, halo still in flight)
   const int    *row_list;      // non-null: process only these rows (boundary pass); n = list length
   int           write_y_sinks; // 0: sink role writes only sink_out (the owner copies the reduced values later)
+  int           row0;          // row-range variant (GHOST == 3): first row of this launch; n = one past the last
   const int    *cta_order;     // single-kernel peer-memory action: CTAs without ghost rows first, the others last
   int           n_interior_ctas;
   // peer-memory mode: sink_out is the sink owner's slot row of this rank; publish this flag after writing it
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(kThreads) fsp_action_generic(MatView m, Coefs 
 
 // Lean hot kernel: 1 row per thread, 32 registers -> 8 CTAs of 256 threads per SM (full occupancy), which matters
 // because every thread does TWO dependent memory round trips (column index, then the gathered x entry).
-// GHOST: 0 = no ghost columns exist (single GPU), 1 = ghost buffer valid, 2 = interior pass (ghost entries count 0).
+// GHOST: 0 = no ghost columns exist (single GPU), 1 = ghost buffer valid, 2 = interior pass (ghost entries count 0),
+//        3 = no ghost columns, rows [m.row0, m.n) only (chunks of the host-vector pipeline, fspmat_action_rows).
 template <int P, int GHOST>
 __global__ void __launch_bounds__(kThreads, 8) fsp_action_lean(MatView m, Coefs cf, const double *__restrict__ x,
                                                                 const double *__restrict__ ghost,
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_lean(MatView m, Coefs 
     sink_role(m, cf, x, y, sink_out);
     return;
   }
-  const int i = (int) blockIdx.x * kThreads + (int) threadIdx.x;
+  const int i = (GHOST == 3 ? m.row0 : 0) + (int) blockIdx.x * kThreads + (int) threadIdx.x;
   if (i >= m.n) return;
   const int    *cp = m.col + i;
   const double *op = m.off + i;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_lean(MatView m, Coefs 
     const int    c = ld_stream(cp + (size_t) p * m.ld);
     const double o = ld_stream(op + (size_t) p * m.ld);
     double xs;
-    if (GHOST == 0) xs = c >= 0 ? __ldg(x + c) : 0.0;
+    if (GHOST == 0 || GHOST == 3) xs = c >= 0 ? __ldg(x + c) : 0.0;
     else if (GHOST == 2) xs = c >= 0 ? __ldg(x + c) : 0.0;
     else xs = c >= 0 ? __ldg(x + c) : (c == -1 ? 0.0 : __ldg(ghost + (-(c + 2))));
     acc = fma(cf.c[p] * o, xs, acc);
@@ -533,6 +535,7 @@ action_fn pick_variant(int rows_per_thread) {
     case 10: return fsp_action_lean<P, 0>;
     case 11: return fsp_action_lean<P, 1>;
     case 12: return fsp_action_lean<P, 2>;
+    case 13: return fsp_action_lean<P, 3>;
     case 1: return fsp_action_rows1<P, 1>;
     case 3: return fsp_action_rows1<P, 8>;  // register-capped (32 regs, full occupancy, may spill for P >= 5)
     case 4: return fsp_action_rows4<P>;
@@ -636,6 +639,23 @@ struct CtaIsInterior {
   const int *flag;
   __host__ __device__ bool operator()(const int &c) const { return flag[c] == 0; }
 };
+// per row-chunk maximum of the referenced column indices (what part of x a chunk of rows needs): one atomicMax per warp
+__global__ void chunk_max_col_kernel(int n, int P, long ld, const int *__restrict__ col, int chunk_rows, int *__restrict__ chunk_max) {
+  const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  int        mx = -1;
+  if (i < n) {
+    mx = (int) i;  // the diagonal term reads x_i
+    for (int p = 0; p < P; ++p) mx = max(mx, col[p * ld + i]);
+  }
+  const int c0 = (int) (min((long) n - 1, (long) blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / chunk_rows);
+  const int c1 = (int) (min((long) n - 1, (long) blockIdx.x * blockDim.x + (threadIdx.x | 31)) / chunk_rows);
+  if (c0 == c1) {
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx >= 0) atomicMax(chunk_max + c0, mx);
+  } else if (i < n) {
+    atomicMax(chunk_max + (int) (i / chunk_rows), mx);
+  }
+}
 struct RowHasGhost {
   const int *col; long ld; int P;
   __host__ __device__ bool operator()(const int &i) const {
@@ -914,7 +934,7 @@ static int launch_action(fspmat_t h, const double *coef_host, const double *x, c
   m.owns_sinks = h->owns_sinks;
   m.ghost_zero = 0; m.row_list = nullptr; m.write_y_sinks = 1;
   m.sink_flag_remote = nullptr; m.sink_epoch = 0;
-  m.cta_order = nullptr; m.n_interior_ctas = 0;
+  m.cta_order = nullptr; m.n_interior_ctas = 0; m.row0 = 0;
 
   // Kernel selection.  variant 0 (default) = lean kernel: 1 row per thread, 32 registers, 8 CTAs/SM.  Measured on
   // one B200 (465^3 lattice, same GPU, profiles/r01_variants.md): lean 6.77 TB/s, 2 rows/thread (64 regs) 6.15 TB/s,
@@ -974,8 +994,46 @@ static void fill_coefs_view(fspmat_t h, const double *coef_host, Coefs &cf, MatV
   m.owns_sinks = h->owns_sinks;
   m.ghost_zero = 0; m.row_list = nullptr; m.write_y_sinks = 0;
   m.sink_flag_remote = nullptr; m.sink_epoch = 0;
-  m.cta_order = nullptr; m.n_interior_ctas = 0;
+  m.cta_order = nullptr; m.n_interior_ctas = 0; m.row0 = 0;
   m.main_blocks = 0;
+}
+
+// Rows [row_begin, row_end) of y = A(t) x (no ghost columns); with_sinks != 0 also computes the K sink rows (needs all
+// of x).  Building block of the host-vector pipeline: chunks of rows run as soon as the part of x they reference has
+// been uploaded, and their part of y goes back while later chunks compute.
+int fspmat_action_rows(fspmat_t h, const double *coef_host, const double *x, double *y, long row_begin, long row_end,
+                       int with_sinks, void *stream) {
+  if (!h->has_values) return 0;
+  if (h->n_ghost != 0) { set_error("fspmat_action_rows: operator has ghost columns"); return -1; }
+  if (row_begin < 0 || row_end > h->n || row_begin > row_end) { set_error("fspmat_action_rows: bad row range"); return -1; }
+  action_fn fn = pick_kernel(h->P, 13);
+  if (!fn) { set_error("fspmat_action_rows: supports 1..16 reactions (got %d)", h->P); return -1; }
+  Coefs cf; MatView m;
+  fill_coefs_view(h, coef_host, cf, m);
+  m.row0 = (int) row_begin;
+  m.n = (int) row_end;
+  m.write_y_sinks = 1;
+  m.sink_blocks = (with_sinks && h->K > 0 && h->owns_sinks) ? h->sink_blocks : 0;
+  m.main_blocks = (int) ((row_end - row_begin + kThreads - 1) / kThreads);
+  const int grid = m.main_blocks + m.sink_blocks;
+  if (grid == 0) return 0;
+  fn<<<grid, kThreads, 0, resolve_stream(stream)>>>(m, cf, x, nullptr, y, nullptr);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+// chunk_max_host[c] = largest index of x referenced by rows [c*chunk_rows, (c+1)*chunk_rows) (their own index included)
+int fspmat_chunk_max_columns(fspmat_t h, long chunk_rows, int n_chunks, int *chunk_max_host) {
+  if (!h->has_values || h->n <= 0) { for (int c = 0; c < n_chunks; ++c) chunk_max_host[c] = -1; return 0; }
+  if (chunk_rows <= 0 || (long) n_chunks * chunk_rows < h->n) { set_error("fspmat_chunk_max_columns: chunks do not cover the rows"); return -1; }
+  int *d = nullptr;
+  FSP_CUDA_CHECK(pmalloc(&d, sizeof(int) * n_chunks));
+  FSP_CUDA_CHECK(cudaMemsetAsync(d, 0xff, sizeof(int) * n_chunks, (cudaStream_t) 0));  // -1
+  chunk_max_col_kernel<<<(unsigned) ((h->n + 255) / 256), 256, 0, (cudaStream_t) 0>>>(h->n, h->P, h->ld, h->d_col, (int) chunk_rows, d);
+  FSP_LAUNCH_CHECK();
+  FSP_CUDA_CHECK(cudaMemcpy(chunk_max_host, d, sizeof(int) * n_chunks, cudaMemcpyDeviceToHost));
+  pfree(d);
+  return 0;
 }
 
 int fspmat_fused_supported(fspmat_t h) { return (h->has_values && h->n_ghost == 0 && h->P >= 1 && h->P <= 16) ? 1 : 0; }

@@ -46,6 +46,9 @@ FspMatrixBase::~FspMatrixBase() {
   if (dmat_) fspmat_destroy(dmat_);
   dmat_ = nullptr;
   FreePinned_();
+  for (void *e : ev_up_) fsp_event_destroy(e);
+  for (void *e : ev_cmp_) fsp_event_destroy(e);
+  for (void *s : {up_stream_, down_stream_, host_compute_stream_}) if (s) { fsp_stream_sync(s); fsp_stream_destroy(s); }
   comm_ = MPI_COMM_NULL;
 }
 
@@ -57,6 +60,8 @@ int FspMatrixBase::Destroy() {
   if (comm_stream_) fsp_stream_sync(comm_stream_);  // side-stream kernels may still read the halo buffers
   if (dmat_) fspmat_clear(dmat_);
   if (halo_) { fsphalo_destroy(halo_); halo_ = nullptr; }
+  host_chunk_need_.clear();
+  host_chunk_rows_ = 0;
   ghost_buf_.release();
   send_buf_.release();
   send_idx_.release();
@@ -541,6 +546,81 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
       printf("[trace] pack %.3f | halo %.3f | sinks %.3f | allreduce %.3f || interior %.3f | end %.3f ms\n", t[1], t[2], t[3],
              t[4], t[5], t[6]);
   }
+  return 0;
+}
+
+// y_host = A(t) x_host with HOST vectors (what a caller with host-resident PETSc vectors gets; bench.py's e2e number).
+// Single GPU: a three-stage pipeline over row chunks -- x goes up in chunks on one copy stream, a chunk of rows runs as
+// soon as the prefix of x it references has arrived (fspmat_chunk_max_columns, cached per generation), and its part of
+// y goes down on a second copy stream while later chunks upload and compute -- so the PCIe link is used in both
+// directions at once instead of H2D, Action, D2H one after the other.
+PacmenslErrorCode FspMatrixBase::ActionHost(PetscReal t, const double *x_host, double *y_host) {
+  const long n = num_rows_local_, ns = num_states_local_;
+  if (hx_.resize((size_t) std::max<long>(n, 1)) || hy_.resize((size_t) std::max<long>(n, 1))) PACMENSLCHKERRQ(-1);
+  static const int n_chunks_env = [] { const char *e = std::getenv("FSP_HOST_CHUNKS"); return e ? std::atoi(e) : 32; }();
+  const bool pipelined = has_values_ == PETSC_TRUE && comm_size_ == 1 && n_chunks_env > 1 && ns >= 64L * 256 * n_chunks_env &&
+                         (int) (tv_reactions_.size() + ti_reactions_.size()) <= 16;
+  if (!pipelined) {
+    FSPCHKERRQ(fsp_memcpy_h2d(hx_.get(), x_host, sizeof(double) * n, nullptr));
+    _p_Vec x, y;
+    x.comm = y.comm = comm_;
+    x.n_local = y.n_local = (PetscInt) n;
+    x.d_data = hx_.get();
+    y.d_data = hy_.get();
+    x.owns_data = y.owns_data = false;
+    PacmenslErrorCode ierr = Action(t, &x, &y);
+    PACMENSLCHKERRQ(ierr);
+    FSPCHKERRQ(fsp_memcpy_d2h(y_host, hy_.get(), sizeof(double) * n, nullptr));
+    return 0;
+  }
+  if (!tv_reactions_.empty()) {
+    int ierr = t_fun_(t, num_reactions_, time_coefficients_.memptr(), t_fun_args_);
+    PACMENSLCHKERRQ(ierr);
+  }
+  FSPCHKERRQ(fsp_stream_sync(nullptr));  // hx_/hy_ come from the stream-ordered pool of the main stream
+  const int  C = n_chunks_env;
+  const long chunk = ((ns + C - 1) / C + 255) / 256 * 256;
+  if (host_chunk_need_.empty() || host_chunk_rows_ != chunk) {
+    host_chunk_need_.assign((size_t) C, -1);
+    FSPCHKERRQ(fspmat_chunk_max_columns(dmat_, chunk, C, host_chunk_need_.data()));
+    host_chunk_rows_ = chunk;
+  }
+  if (!up_stream_) {
+    FSPCHKERRQ(fsp_stream_create(&up_stream_));
+    FSPCHKERRQ(fsp_stream_create(&down_stream_));
+    FSPCHKERRQ(fsp_stream_create(&host_compute_stream_));
+  }
+  while ((int) ev_up_.size() < C + 1) { void *e = nullptr; FSPCHKERRQ(fsp_event_create(&e)); ev_up_.push_back(e); }
+  while ((int) ev_cmp_.size() < C + 1) { void *e = nullptr; FSPCHKERRQ(fsp_event_create(&e)); ev_cmp_.push_back(e); }
+  const double *coefs = time_coefficients_.memptr();
+  // stage 1: all uploads, in order (chunk k of x, the sink entries ride with the last chunk)
+  for (int k = 0; k < C; ++k) {
+    const long b = std::min<long>(ns, (long) k * chunk), e = (k == C - 1) ? n : std::min<long>(ns, (long) (k + 1) * chunk);
+    if (e > b) FSPCHKERRQ(fsp_memcpy_h2d_async(hx_.get() + b, x_host + b, sizeof(double) * (e - b), up_stream_));
+    FSPCHKERRQ(fsp_event_record(ev_up_[k], up_stream_));
+  }
+  // stages 2 + 3: rows of chunk c as soon as x[0 .. need_c] is on the device; its y right behind it
+  for (int c = 0; c < C; ++c) {
+    const long b = std::min<long>(ns, (long) c * chunk), e = std::min<long>(ns, (long) (c + 1) * chunk);
+    if (e <= b) continue;
+    const long need = std::max<long>(host_chunk_need_[c], e - 1);
+    const int  k_need = (int) std::min<long>(C - 1, need / chunk);
+    FSPCHKERRQ(fsp_stream_wait_event(host_compute_stream_, ev_up_[k_need]));
+    FSPCHKERRQ(fspmat_action_rows(dmat_, coefs, hx_.get(), hy_.get(), b, e, 0, host_compute_stream_));
+    FSPCHKERRQ(fsp_event_record(ev_cmp_[c], host_compute_stream_));
+    FSPCHKERRQ(fsp_stream_wait_event(down_stream_, ev_cmp_[c]));
+    FSPCHKERRQ(fsp_memcpy_d2h_async(y_host + b, hy_.get() + b, sizeof(double) * (e - b), down_stream_));
+  }
+  if (n > ns) {  // sink rows need all of x
+    FSPCHKERRQ(fsp_stream_wait_event(host_compute_stream_, ev_up_[C - 1]));
+    FSPCHKERRQ(fspmat_action_rows(dmat_, coefs, hx_.get(), hy_.get(), ns, ns, 1, host_compute_stream_));
+    FSPCHKERRQ(fsp_event_record(ev_cmp_[C], host_compute_stream_));
+    FSPCHKERRQ(fsp_stream_wait_event(down_stream_, ev_cmp_[C]));
+    FSPCHKERRQ(fsp_memcpy_d2h_async(y_host + ns, hy_.get() + ns, sizeof(double) * (n - ns), down_stream_));
+  }
+  FSPCHKERRQ(fsp_stream_sync(down_stream_));
+  FSPCHKERRQ(fsp_stream_sync(host_compute_stream_));
+  FSPCHKERRQ(fsp_stream_sync(up_stream_));
   return 0;
 }
 

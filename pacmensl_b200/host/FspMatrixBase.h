@@ -45,6 +45,9 @@ class PACMENSL_API FspMatrixBase {
   /// Extension: y = scale .* (beta x + alpha A(t) x) with up to two inner products of y fused into the same kernel
   /// (include/fsp_b200.h: fspmat_epilogue) -- what the Krylov and BDF/GMRES loops need right after every Action.
   virtual PacmenslErrorCode ActionFused(PetscReal t, Vec x, Vec y, const fspmat_epilogue &ep);
+  /// Extension: the same operator on HOST vectors (n local rows each): chunked upload / compute / download pipeline
+  /// on a single GPU, plain H2D + Action + D2H otherwise.  FSP_HOST_CHUNKS (default 32; <= 1 disables the pipeline).
+  PacmenslErrorCode ActionHost(PetscReal t, const double *x_host, double *y_host);
   /// y = (sum_r coef[r] A_r) x with the coefficient vector supplied directly (used by SensFspMatrix).
   PacmenslErrorCode ActionWithCoefficients(const double *coefs, Vec x, Vec y);
 
@@ -91,6 +94,12 @@ class PACMENSL_API FspMatrixBase {
   long                 cache_n_ = 0, cache_ld_ = 0;
   int                  cache_R_ = 0;
   std::vector<int>     cache_enabled_;
+  // host-vector pipeline (ActionHost)
+  DeviceBuffer<double> hx_, hy_;
+  std::vector<int>     host_chunk_need_;
+  long                 host_chunk_rows_ = 0;
+  void                *up_stream_ = nullptr, *down_stream_ = nullptr, *host_compute_stream_ = nullptr;
+  std::vector<void *>  ev_up_, ev_cmp_;
   // pinned double buffers + copy stream of the pipelined host-callback evaluation
   int    *pin_states_[2] = {nullptr, nullptr};
   double *pin_vals_[2] = {nullptr, nullptr};

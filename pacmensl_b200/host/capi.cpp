@@ -189,14 +189,7 @@ int pfsp_mat_action(void *mat, double t, const double *x_dev, double *y_dev) {
 }
 int pfsp_mat_action_host(void *mat, double t, const double *x_host, double *y_host) {
   PFSP_TRY
-  auto *A = static_cast<FspMatrixBase *>(mat);
-  const size_t n = (size_t) A->GetNumLocalRows();
-  static thread_local DeviceBuffer<double> xd, yd;
-  if (xd.resize(n) || yd.resize(n)) return -1;
-  if (fsp_memcpy_h2d(xd.get(), x_host, sizeof(double) * n, nullptr)) return -1;
-  int ierr = pfsp_mat_action(mat, t, xd.get(), yd.get());
-  if (ierr) return ierr;
-  return fsp_memcpy_d2h(y_host, yd.get(), sizeof(double) * n, nullptr);
+  return static_cast<FspMatrixBase *>(mat)->ActionHost(t, x_host, y_host);
   PFSP_CATCH
 }
 

@@ -258,3 +258,30 @@ def test_fused_epilogue_krylov_form_hog1p_sizes(cuda, oracle, bounds):
         assert rel_err(y, yp.cpu().numpy()) <= 1e-15
         o = out.cpu().numpy()
         assert abs(o[0] - ax @ v0) <= 1e-12 * max(np.abs(ax * v0).sum(), 1e-300)
+
+
+@pytest.mark.parametrize("upper,tv", [([127, 127, 63], False), ([127, 95, 63], True), ([21, 17, 13], False)])
+def test_action_host_pipeline_equals_device_action(cuda, upper, tv):
+    """pfsp_mat_action_host (host vectors; chunked upload / compute / download pipeline above 524 288 rows, plain
+    H2D + Action + D2H below) returns exactly what Action returns on device vectors -- same arithmetic per row."""
+    torch = cuda
+    from pacmensl_b200 import api
+    from pacmensl_b200.lattice import Lattice
+    api.init(0)
+    lat = Lattice(upper, tv=tv)
+    n = lat.n_rows
+    rng = np.random.default_rng(21)
+    x = rng.random(n)
+    for pinned in (True, False):
+        xh = torch.from_numpy(x.copy())
+        yh = torch.full((n,), float("nan"), dtype=torch.float64)
+        if pinned:
+            xh, yh = xh.pin_memory(), yh.pin_memory()
+        for t in (0.0, 7.0):
+            yh.fill_(float("nan"))
+            assert lat.mat.action_host(t, xh, yh) == 0
+            xd = torch.from_numpy(x).cuda()
+            yd = torch.empty_like(xd)
+            lat.action(t, xd, yd)
+            torch.cuda.synchronize()
+            assert torch.equal(yh, yd.cpu()), (upper, tv, pinned, t)
