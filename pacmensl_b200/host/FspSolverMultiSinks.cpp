@@ -241,9 +241,9 @@ PacmenslErrorCode FspSolverMultiSinks::SetUp() {
         }
         break;
       default:
-        // ODESolverType::PETSC (TsFsp, PETSc TS with assembled Jacobians) is outside this build's scope;
-        // the BDF integrator takes its place so that callers selecting it still get a solution.
-        ode_solver_ = std::make_shared<CvodeFsp>(comm_);
+        // ODESolverType::PETSC: TsFsp keeps the reference's interface and integrates with the matrix-free BDF
+        // integrator (PETSc TS with assembled Jacobians is outside this build's scope), see TsFsp.h
+        ode_solver_ = std::make_shared<TsFsp>(comm_);
     }
     ode_solver_->SetFspMatPtr(A_.get());
     if (logging_enabled) ode_solver_->EnableLogging();

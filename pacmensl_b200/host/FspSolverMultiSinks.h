@@ -14,6 +14,7 @@
 #include "KrylovFsp.h"
 #include "Model.h"
 #include "OdeSolverBase.h"
+#include "TsFsp.h"
 #include "PetscWrap.h"
 #include "StateSetBase.h"
 #include "StateSetConstrained.h"

@@ -112,6 +112,27 @@ TEST_F(OdeTest, use_krylov) {
   VecDestroy(&P);
 }
 
+// KAT-O3 (reference tests/test_ode.cpp:297-330): the TsFsp interface (ODESolverType::PETSC)
+TEST_F(OdeTest, use_ts) {
+  auto AV = [&](PetscReal t, Vec x, Vec y) { return A->Action(t, x, y); };
+  Vec  P = initial_vec();
+  TsFsp ts(PETSC_COMM_WORLD);
+  ASSERT_EQ(ts.SetFinalTime(100.0), 0);
+  ASSERT_EQ(ts.SetInitialSolution(&P), 0);
+  ASSERT_EQ(ts.SetRhs(AV), 0);
+  ASSERT_EQ(ts.SetStatusOutput(0), 0);
+  ASSERT_EQ(ts.SetFspMatPtr(A), 0);
+  ASSERT_EQ(ts.SetTsType(TSROSW), 0);
+  ASSERT_EQ(ts.SetUp(), 0);
+  PetscInt solver_stat = ts.Solve();
+  ASSERT_FALSE(solver_stat);
+  PetscReal Psum;
+  VecSum(P, &Psum);
+  ASSERT_LE(Psum, 1.0 + 1.0e-8);
+  ASSERT_GE(Psum, 1.0 - 1.0e-8);
+  VecDestroy(&P);
+}
+
 TEST_F(OdeTest, krylov_handling_bad_mat_vec) {
   auto AV = [&](PetscReal, Vec, Vec) { return -1; };
   Vec  P = initial_vec();
