@@ -380,6 +380,12 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_epi(MatView m, Coefs c
   const int i = (int) blockIdx.x * kThreads + (int) threadIdx.x;
   double    d0 = 0.0, d1 = 0.0;
   if (i < m.n) {
+    // the epilogue operands are requested FIRST, together with the matrix planes: issued after the gathers they would
+    // add a third dependent memory round trip per row (measured: 212 us instead of ~172 us on 9.9 M rows)
+    const double sc = e.scale ? __ldg(e.scale + i) : 1.0;
+    const double w0 = (e.n_dots > 0 && e.vec[0]) ? __ldg(e.vec[0] + i) : 0.0;
+    const double w1 = (e.n_dots > 1 && e.vec[1]) ? __ldg(e.vec[1] + i) : 0.0;
+    const double xi = __ldg(x + i);
     const int    *cp = m.col + i;
     const double *op = m.off + i;
     double        acc = 0.0;
@@ -393,12 +399,10 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_epi(MatView m, Coefs c
     double        d = 0.0;
     const double *dp = m.diag + i;
     for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
-    const double xi = __ldg(x + i);
-    double       v = fma(e.alpha, fma(-d, xi, acc), e.beta * xi);
-    if (e.scale) v *= __ldg(e.scale + i);
+    const double v = fma(e.alpha, fma(-d, xi, acc), e.beta * xi) * sc;
     y[i] = v;
-    if (e.n_dots > 0) d0 = v * (e.vec[0] ? __ldg(e.vec[0] + i) : v);
-    if (e.n_dots > 1) d1 = v * (e.vec[1] ? __ldg(e.vec[1] + i) : v);
+    if (e.n_dots > 0) d0 = v * (e.vec[0] ? w0 : v);
+    if (e.n_dots > 1) d1 = v * (e.vec[1] ? w1 : v);
   }
   if (e.n_dots > 0) {
     const double r0 = block_sum(d0, red);
