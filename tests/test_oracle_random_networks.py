@@ -106,3 +106,47 @@ def test_oracle_equals_independent_restatement_on_random_network(oracle, seed):
         # the fused single-pass CPU variant agrees too
         ierr, yf = A.action(t, x, fused=True)
         assert np.abs(yf - y).max() <= 1e-12 * scale
+
+
+def reference_wave_order(w):
+    """Index map of the reference at np = 1: per wave, children Y[:, j*nF + i] = frontier_i + nu_j
+    (reaction-major, StateSetConstrained.cpp:175-179) -> keep the valid ones -> first occurrence of every duplicate ->
+    drop those already present -> append in that order with status 1 (StateSetBase.cpp:207-241)."""
+    lhs, bounds = w["lhs"], w["bounds"]
+
+    def valid(x):
+        return all(v >= 0 for v in x) and all(l <= b for l, b in zip(lhs(x), bounds))
+
+    states = [tuple(w["x0"])]
+    present = {states[0]}
+    frontier = list(states)
+    while frontier:
+        children = [tuple(a + b for a, b in zip(x, nu)) for nu in w["SM"] for x in frontier]
+        new = []
+        for y in children:
+            if valid(y) and y not in present:
+                present.add(y)
+                new.append(y)
+        states += new
+        frontier = new
+    return states
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_index_map_is_the_reaction_major_first_discovery_order(oracle, seed):
+    w, S, R, K, W, rate, order, amp = random_network(seed)
+    st = oracle.StateSet(SM=np.array(w["SM"]).T)
+
+    def lhs_cb(X, out):
+        out[:, :] = X @ W.T
+        return 0
+
+    assert st.set_shape(w["bounds"], lhs_cb) == 0
+    assert st.add_states([w["x0"]]) == 0
+    assert st.expand() == 0
+    expect = reference_wave_order(w)
+    assert st.states().tolist() == [list(s) for s in expect]
+    # growing a bound re-activates the blocked states and appends; old indices never change (np = 1)
+    bigger = [b + 2 for b in w["bounds"]]
+    assert st.set_bounds(bigger) == 0 and st.expand() == 0
+    assert st.states()[: len(expect)].tolist() == [list(s) for s in expect]
