@@ -31,13 +31,15 @@ def parse():
     ap.add_argument("--lattice-dims", default=None, help="a,b,c states per axis (overrides --lattice; diagnostics)")
     ap.add_argument("--tv", action="store_true", help="time-varying births (R_tv = 3)")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant (0 = default lean kernel; 1,2,3,4 = alternatives, see fspmat.cu)")
-    ap.add_argument("--cpu-lattice", type=int, default=200, help="lattice edge of the bounded CPU-baseline sample")
-    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--cpu-lattice", type=int, default=0, help="lattice edge of the CPU-baseline arm (0 = the same lattice as the GPU arm)")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-parity", action="store_true", help="skip the partitioned-Action parity leg (oracle check before the timed region)")
+    ap.add_argument("--trace-steps", action="store_true", help="print per-rank per-step event times of the timed region to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-expand", action="store_true", help="skip the Expand() closure check of the lattice set")
-    ap.add_argument("--no-solve", action="store_true", help="skip the solve-to-t_f side measurement (N = 1 only)")
-    ap.add_argument("--solve-lattice", type=int, default=215, help="lattice edge of the GPU solve-to-t_f measurement")
+    ap.add_argument("--no-solve", action="store_true", help="skip the solve-to-t_f side measurement")
+    ap.add_argument("--solve-lattice", type=int, default=0, help="lattice edge of the GPU solve-to-t_f measurement (0 = --lattice)")
     ap.add_argument("--cpu-solve-lattice", type=int, default=128, help="lattice edge of the bounded CPU solve sample")
     return ap.parse_args()
 
@@ -110,70 +112,112 @@ def lattice_bytes_per_row(tv):
     return 16 + 12 * R + 8 * (ntv + (1 if R - ntv > 0 else 0))
 
 
-def cpu_baseline(args, steps=None, warmup=3):
-    """Reference-shaped multi-pass Action (oracle port) on a bounded sample of the same workload."""
+def workload_name(dims, tv):
+    n = dims[0] * dims[1] * dims[2]
+    return ("synthetic 3-D birth-death lattice %s = %d states, S=3 R=6 K=3 sinks, %s, FspMatrixConstrained::Action(t,x,y)"
+            % ("x".join(str(d) for d in dims), n, "R_tv=3" if tv else "time-invariant"))
+
+
+def lattice_dims(args):
+    return [args.lattice] * 3 if not args.lattice_dims else [int(v) for v in args.lattice_dims.split(",")]
+
+
+def cpu_baseline(args, steps=None, warmup=2):
+    """Reference-shaped multi-pass Action (oracle port: one CSR SpMV into a work vector + AXPY per matrix,
+    src/Matrix/FspMatrixBase.cpp:36-62) on the SAME lattice as the GPU arm, all host cores."""
     steps = steps or args.cpu_steps
     import numpy as np
     from oracle import oracle as O
-    L = args.cpu_lattice
-    name = "birth_death_3d_tv" if args.tv else "birth_death_3d"
-    st = O.StateSet(fixture=name, bounds=[L - 1] * 3)
-    st.expand()
+    cores = O.use_all_cores()  # torchrun exports OMP_NUM_THREADS=1; the baseline must use the box's cores
+    dims = lattice_dims(args)
+    if args.cpu_lattice:
+        dims = [args.cpu_lattice] * 3
+    n = dims[0] * dims[1] * dims[2]
+    # ~115 B/state of host memory (CSR + vectors); fall back to a bounded sample if the box cannot hold it
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 1 << 40
+    if n * 130 > avail:
+        edge = int((avail / 130.0) ** (1.0 / 3.0)) // 5 * 5
+        dims = [edge] * 3
+        n = edge ** 3
     A = O.FspMatrix(constrained=True)
-    assert A.generate_fixture(st, name) == 0
-    n = st.n
+    t0 = time.perf_counter()
+    assert A.generate_lattice(dims, tv=args.tv) == 0
+    t_gen = time.perf_counter() - t0
     rng = np.random.default_rng(12345)
     x = rng.random(A.nrows)
     x[n:] = 0.0
     x /= x.sum()
     y = np.empty_like(x)
     for _ in range(max(warmup, 1)):
-        A.action_into(0.0, x, y)
+        A.action_into(0.3, x, y)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        A.action_into(0.0, x, y)
+        A.action_into(0.3, x, y)
         ts.append(time.perf_counter() - t0)
     ts.sort()
     med = ts[len(ts) // 2]
-    nbytes = n * lattice_bytes_per_row(args.tv) + 12 * 3 * L * L + 8 * 3
-    return {"value": nbytes / med / 1e9, "unit": "GB/s", "cores": O.num_threads(), "kind": "port",
-            "sample": "%d^3 = %d-state lattice, median of %d reference-shaped (SpMV+AXPY per matrix) OpenMP Actions; "
-                      "oracle/fsp_oracle.c (the PETSc reference cannot be built in this image)" % (L, n, steps),
-            "ms_per_step": med * 1e3}
+    nbytes = n * lattice_bytes_per_row(args.tv) + 12 * (dims[0] * dims[1] + dims[1] * dims[2] + dims[0] * dims[2]) + 8 * 3
+    return {"value": nbytes / med / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": "%s lattice = %d states (%s), median of %d reference-shaped (CSR SpMV + AXPY per matrix) OpenMP Actions; "
+                      "oracle/fsp_oracle.c (the PETSc reference cannot be built in this image)"
+                      % ("x".join(str(d) for d in dims), n, "the GPU arm's workload" if dims == lattice_dims(args) else "bounded sample", steps),
+            "ms_per_step": med * 1e3, "dims": dims, "same_config": dims == lattice_dims(args), "build_seconds": round(t_gen, 2),
+            "sum_y": float(y.sum())}
 
 
-def solve_to_tf(args):
-    """Second half of BASELINE's metric: wall time of a KrylovFsp solve to t_f = 1 on the fixed lattice (p0 = delta(0)).
-    GPU: examples/lattice_solve.cpp (the host classes on the CUDA library), best of 2, at --solve-lattice and at the CPU
-    sample size; CPU: the oracle's restatement of KrylovFsp (oracle/krylov_oracle.py) on the bounded sample."""
-    import numpy as np
-    out = {"solver": "KrylovFsp (defaults: IOP q=2, m in [25,60], atol 1e-14)", "t_final": 1.0}
+def solve_to_tf(args, rank, world, local_rank, port_base):
+    """Second half of BASELINE's metric: wall time of KrylovFsp / CvodeFsp solves to t_f = 1 on the fixed lattice
+    (p0 = delta(0), analytic check: product of three Poisson pmfs), on N GPUs.  Every rank of this job runs
+    examples/lattice_solve (the host C++ classes on the CUDA library) as ITS rank of an N-rank solve, after the Action
+    workload has been released; rank 0 reports.  CPU beside it (N = 1 only): the oracle's restatement of KrylovFsp
+    (oracle/krylov_oracle.py) on a bounded sample."""
     exe = os.path.join(ROOT, "build", "examples", "lattice_solve")
+    edge = args.solve_lattice or args.lattice
+    out = {"t_final": 1.0, "lattice_edge": edge, "ranks": world}
 
-    def gpu(edge):
-        r = subprocess.run([exe, "--edge", str(edge), "--solver", "krylov", "--repeat", "2"], capture_output=True, text=True,
-                           timeout=240, env=dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0"))
+    def gpu(solver, e, port):
+        env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(local_rank), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        r = subprocess.run([exe, "--edge", str(e), "--solver", solver, "--repeat", "2"], capture_output=True, text=True,
+                           timeout=420, env=env)
+        if rank != 0:
+            return None
         j = json.loads(r.stdout.strip().splitlines()[-1])
-        return {"states": j["states"], "wall_s": j["wall_s"], "action_calls": j["action_calls"],
-                "l1_err_vs_poisson": j["l1_err_vs_poisson"]}
+        return {"states": j["states"], "wall_s": j["wall_s"], "action_calls": j["action_calls"], "status": j["status"],
+                "l1_err_vs_poisson": j["l1_err_vs_poisson"], "sum_p": j["sum_p"]}
 
-    out["gpu"] = gpu(args.solve_lattice)
-    out["gpu_at_cpu_sample_size"] = gpu(args.cpu_solve_lattice)
-    from oracle import oracle as O
-    from oracle.krylov_oracle import KrylovOracle
-    L = args.cpu_solve_lattice
-    st = O.StateSet(fixture="birth_death_3d", bounds=[L - 1] * 3)
-    st.expand()
-    A = O.FspMatrix(constrained=True)
-    assert A.generate_fixture(st, "birth_death_3d") == 0
-    p0 = np.zeros(A.nrows)
-    p0[st.state2index(np.array([[0, 0, 0]], dtype=np.int32))[0]] = 1.0
-    kry = KrylovOracle(A)
-    t0 = time.perf_counter()
-    p = kry.solve(p0, 1.0)
-    out["cpu"] = {"states": st.n, "wall_s": time.perf_counter() - t0, "action_calls": kry.num_rhs, "cores": O.num_threads(),
-                  "kind": "port", "sum_p": float(p.sum())}
+    for k, (solver, label) in enumerate((("krylov", "KrylovFsp (defaults: IOP q=2, m in [25,60], atol 1e-14)"),
+                                         ("cvode", "CvodeFsp (BDF, rtol 1e-6, atol 1e-14)"))):
+        try:
+            res = gpu(solver, edge, port_base + 40 * k)
+            if rank == 0:
+                res["solver"] = label
+                out[solver] = res
+        except Exception as e:  # noqa: BLE001
+            out[solver] = {"unavailable": repr(e)[:200]}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            import numpy as np
+            L = args.cpu_solve_lattice
+            out["krylov_at_cpu_sample_size"] = gpu("krylov", L, port_base + 80)
+            from oracle import oracle as O
+            from oracle.krylov_oracle import KrylovOracle
+            cores = O.use_all_cores()
+            A = O.FspMatrix(constrained=True)
+            assert A.generate_lattice([L] * 3) == 0
+            p0 = np.zeros(A.nrows)
+            p0[0] = 1.0  # lexicographic order: state (0,0,0) has index 0
+            kry = KrylovOracle(A)
+            t0 = time.perf_counter()
+            p = kry.solve(p0, 1.0)
+            out["cpu_krylov"] = {"states": L ** 3, "wall_s": time.perf_counter() - t0, "action_calls": kry.num_rhs, "cores": cores,
+                                 "kind": "port", "sum_p": float(p.sum())}
+        except Exception as e:  # noqa: BLE001
+            out["cpu_krylov"] = {"unavailable": repr(e)[:200]}
     return out
 
 
@@ -181,15 +225,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # K steps / W warm-ups as asked, each step one Action on the bounded CPU sample (a few ms to a few 100 ms per step)
-    steps, warmup = max(1, min(args.steps, 2000)), max(args.warmup, 3)
+    # K steps / W warm-ups as asked, each step one reference-shaped Action on the GPU arm's lattice (~0.1 s per step)
+    steps, warmup = max(1, min(args.steps, 200)), max(args.warmup, 3)
     cb = cpu_baseline(args, steps=steps, warmup=warmup)
     line = {
         "metric": "FSP Action() GB/s", "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "synthetic 3-D birth-death lattice Action() (CPU sample %d^3)" % args.cpu_lattice,
-                   "tv": bool(args.tv)},
+        "config": {"workload": workload_name(cb["dims"], args.tv), "states": cb["dims"][0] * cb["dims"][1] * cb["dims"][2],
+                   "bytes_per_row": lattice_bytes_per_row(args.tv), "same_config": cb["same_config"],
+                   "build_seconds": cb["build_seconds"]},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -210,20 +255,35 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
     from pacmensl_b200 import _capi, api
     from pacmensl_b200.lattice import Lattice
     L = _capi.lib()
     api.init(local_rank, dist)
 
+    # ---- parity leg: the partitioned Action at THIS N against the CPU oracle, by state key (before anything is timed)
+    parity = None
+    if not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import parity_leg
+        parity = parity_leg.run(api, dist, dev)
+        flag = torch.tensor([1.0 if (rank != 0 or parity["ok"]) else 0.0], device=dev)
+        if dist is not None:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() != 1.0:
+            if rank == 0:
+                print(json.dumps({"metric": "FSP Action() GB/s", "n_gpus": world, "parity": parity,
+                                  "error": "partitioned Action differs from the oracle"}))
+            raise SystemExit(3)
+
     # ---- build: state set (device hash directory) + operator through the host C++ classes -------------------
-    Ledge = args.lattice
     t_build0 = time.perf_counter()
-    dims = [Ledge] * 3 if not args.lattice_dims else [int(v) for v in args.lattice_dims.split(",")]
+    dims = lattice_dims(args)
     lat = Lattice([d - 1 for d in dims], tv=args.tv, expand=not args.no_expand)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build0
@@ -244,27 +304,41 @@ def main():
     t_eval = 0.3
 
     def step():
-        lat.action(t_eval, x, y)  # FspMatrixConstrained::Action: halo exchange (N > 1) + one fused kernel launch
+        lat.action(t_eval, x, y)  # FspMatrixConstrained::Action: ONE launch (N > 1: push + sinks + rows + finish)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
+    # the clock sampler (a fork + exec of nvidia-smi, tens of ms) starts BEFORE the warm-up and the barrier, so that
+    # no rank enters the timed region later than the others because of it
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    tick = torch.zeros(1, device=dev)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------------------
     launches0 = L.fsp_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if args.trace_steps else None
+    if dist is not None:
+        # device-side barrier on the launching stream: every GPU leaves this all-reduce at the same moment, and its
+        # timed region starts right there (host-side barrier exits are tens of microseconds apart)
+        dist.all_reduce(tick)
     ev0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         step()
+        if step_ev:
+            step_ev[k].record()
     ev1.record()
     torch.cuda.synchronize()
     launches = L.fsp_launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
+    if step_ev:
+        ts = [ev0.elapsed_time(e) for e in step_ev]
+        sys.stderr.write("[trace rank %d] total %.4f ms; per-step end times (ms): %s\n"
+                         % (rank, ms, " ".join("%.3f" % v for v in ts)))
     if dist is not None:
         dist.barrier()
         tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -278,8 +352,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = bytes_total / (ms_per_step * 1e-3) / 1e9
-    # At N = 1 a step IS one launch of the fused Action kernel, so the per-launch duration of the dominant kernel is
-    # the event-timed step; at N > 1 the step also holds the pack kernel + NCCL halo exchange + sink all-reduce.
+    # A step IS one launch of the Action kernel on every GPU (N = 1: fsp_action_lean; N > 1: fsp_action_halo_kernel),
+    # so the per-launch duration of the dominant kernel is the event-timed step.
     kms = ms_per_step
 
     # ---- e2e: the same Action through the C ABI with HOST buffers (H2D x, D2H y inside the timed region) -----
@@ -288,15 +362,17 @@ def main():
         xh = torch.empty(n_rows, dtype=torch.float64).pin_memory()
         yh = torch.empty(n_rows, dtype=torch.float64).pin_memory()
         xh.copy_(x)
-        k2 = max(3, min(args.steps, 10))
+        k2 = args.steps
 
         def e2e_step():
             ierr = lat.mat.action_host(t_eval, xh, yh)  # pfsp_mat_action_host: H2D(x) + Action + D2H(y)
             if ierr:
                 raise SystemExit("action_host failed")
 
-        e2e_step()
+        for _ in range(2):
+            e2e_step()
         torch.cuda.synchronize()
+        e2e_ok = bool(torch.equal(yh.to(dev), y))  # bit-identical to the device-vector Action of the same x
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
@@ -305,15 +381,16 @@ def main():
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / k2
         if dist is not None:
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            tt = torch.tensor([dt, 0.0 if e2e_ok else 1.0], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
+            dt, e2e_ok = float(tt[0].item()), tt[1].item() == 0.0
         e2e = {"value": bytes_total / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(n_rows * 8),
                "d2h_bytes_per_step": int(n_rows * 8), "ms_per_step": dt * 1e3, "steps": k2,
+               "bit_identical_to_device_action": e2e_ok,
                "call": "pfsp_mat_action_host (include/pacmensl_b200_host.h) with pinned host x, y"}
         del xh, yh
 
-    pending_line = {}
+    line = None
     if rank == 0:
         peak, peak_src = measured_peak()
         ach = bytes_local / (kms * 1e-3) / 1e9
@@ -322,54 +399,56 @@ def main():
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if tj.get("lattice") == Ledge and bool(tj.get("tv")) == bool(args.tv) and world == 1:
+                if tj.get("lattice") == args.lattice and bool(tj.get("tv")) == bool(args.tv) and world == 1:
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
+        p2p = api.p2p_enabled()
+        kernel = ("fsp_action_lean<6,0>" if world == 1 else
+                  ("fsp_action_halo_kernel<6> (push + sink + row + finishing CTAs in one launch)" if p2p
+                   else "fsp_action_lean<6,2> + boundary rows + NCCL halo (rank 0 share)"))
         line = {
             "metric": "FSP Action() GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (x ~ U(0,1) normalised, torch Philox seed 12345)",
-            "config": {"workload": "synthetic 3-D birth-death lattice %s = %d states, S=3 R=6 K=3 sinks, %s, "
-                                   "FspMatrixConstrained::Action(t,x,y)" % ("x".join(str(d) for d in dims), N, "R_tv=3" if args.tv else "time-invariant"),
+            "config": {"workload": workload_name(dims, args.tv),
                        "states": N, "bytes_per_row": lattice_bytes_per_row(args.tv),
                        "l2": "inputs (%.2f GB per Action) exceed the 126 MB L2; no flush needed" % (bytes_total / 1e9),
                        "partition": "1 block" if world == 1 else (
                            "%d contiguous row blocks (BLOCK); " % world + (
-                               "peer-memory path: fused pack+store+signal halo kernel over CUDA IPC windows (NVLink), interior pass, "
-                               "boundary kernel waiting on peer flags in device code, sink slots summed by the owner; no NCCL call per Action"
-                               if api.p2p_enabled() else "NCCL halo exchange + K-double sink all-reduce per Action")),
-                       "kernel_variant": args.variant, "build_seconds": round(t_build, 2)},
+                               "peer-memory path: ONE kernel per Action and GPU -- leading CTAs pack the boundary entries of x and store "
+                               "them into the peers' ghost windows (CUDA IPC over NVLink) + epoch flag, row CTAs wait in device code "
+                               "only where a warp meets a ghost column, sink slots summed by the owner; no NCCL call per Action"
+                               if p2p else "NCCL halo exchange + K-double sink all-reduce per Action")),
+                       "kernel_variant": args.variant, "build_seconds": round(t_build, 2),
+                       "timing": "device barrier (all-reduce) on the launching stream, then CUDA events around exactly K steps; max over ranks"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": ("fsp_action_lean<6,0>" if world == 1 else ("fsp_action_lean<6,2> + fsp_action_boundary_p2p_kernel (+ halo_push_kernel, sink kernel)" if api.p2p_enabled() else "fsp_action_lean<6,2> + boundary rows + NCCL halo (rank 0 share)")) + " (pacmensl_b200/csrc/fspmat.cu)",
+                         "kernel": kernel + " (pacmensl_b200/csrc/fspmat.cu)",
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_local},
-            "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks, "parity": parity,
         }
         if not args.no_cpu_baseline:
             cb = cpu_baseline(args)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        line["_solve_pending"] = world == 1 and not args.no_solve
-        pending_line = line
-        print_now = not line["_solve_pending"]
-        if print_now:
-            del line["_solve_pending"]
-            print(json.dumps(line))
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "same_config")}
     if dist is not None:
         dist.barrier()
     del lat, x, y
     api.finalize()
+    port_base = int(os.environ.get("MASTER_PORT", "29500")) + 101
     if dist is not None:
         dist.destroy_process_group()
-    if rank == 0 and pending_line.get("_solve_pending"):
+    torch.cuda.empty_cache()
+    if not args.no_solve:
         # side measurement after the device memory of the Action workload has been released; never fatal
-        del pending_line["_solve_pending"]
         try:
-            torch.cuda.empty_cache()
-            pending_line["solve_to_tf"] = solve_to_tf(args)
+            sol = solve_to_tf(args, rank, world, local_rank, port_base)
         except Exception as e:  # noqa: BLE001
-            pending_line["solve_to_tf"] = {"unavailable": repr(e)[:200]}
-        print(json.dumps(pending_line))
+            sol = {"unavailable": repr(e)[:200]}
+        if rank == 0:
+            line["solve_to_tf"] = sol
+    if rank == 0:
+        print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -3,7 +3,7 @@
 //   p0 = delta(0,0,0), t_f = 1.0, KrylovFsp defaults or CvodeFsp (rtol 1e-6, atol 1e-14) on a FIXED state set
 //   (edge^3 states), one rank per GPU (tools/launch_ranks.sh N build/examples/lattice_solve ...).
 // The three species are independent M/M/inf queues started empty, so p(t_f) is the product of three Poisson
-// pmfs with means (b_s/gamma_s)(1 - exp(-gamma_s t_f)); for N <= 3e7 the 1-norm error against it is reported.
+// pmfs with means (b_s/gamma_s)(1 - exp(-gamma_s t_f)); the 1-norm error against it is reported.
 //   usage: lattice_solve [--edge 215] [--solver krylov|cvode] [--tfinal 1.0] [--rtol 1e-6] [--atol 1e-14] [--repeat 1] [--no-fused]
 #include <chrono>
 #include <cmath>
@@ -103,7 +103,7 @@ int main(int argc, char *argv[]) {
     double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
     if (wall < wall_best) { wall_best = wall; setup_best = t_setup; }
     VecSum(P, &psum);
-    if (rep == repeat - 1 && fsp.GetNumGlobalStates() <= 30000000) {
+    if (rep == repeat - 1) {
       // 1-norm error against the product of Poisson pmfs (local block, then summed over ranks)
       const double b[3] = {40.0, 30.0, 20.0}, g[3] = {1.0, 1.5, 2.0};
       std::vector<std::vector<double>> pm(3, std::vector<double>(edge));

@@ -390,6 +390,28 @@ FSP_API int fsphalo_create(fspcomm_t c, fsphalo_t *out, const int *send_idx_dev,
 FSP_API int fsphalo_destroy(fsphalo_t h);
 /* start of an Action: launches the fused pack + store + signal kernel on `stream` and describes the epoch */
 FSP_API int fsphalo_begin(fsphalo_t h, const double *x_dev, void *stream, fsphalo_epoch *out);
+/* The same without a launch: *out describes the consumer side of the next epoch and *push (opaque) the producer side,
+ * for fspmat_action_halo, whose leading CTAs do the pack + store + signal themselves. */
+typedef struct fsphalo_push { unsigned long long opaque[64]; } fsphalo_push;
+FSP_API int fsphalo_next(fsphalo_t h, fsphalo_epoch *out, fsphalo_push *push);
+/* non-zero (and fsp_last_error set) once a device-side flag wait of this communicator has timed out: results produced
+ * since then were poisoned with NaN by the waiting kernels.  Call after a synchronisation that consumes results. */
+FSP_API int fsphalo_check(fsphalo_t h);
+FSP_API int fspcomm_check(fspcomm_t c);
+/* The whole multi-GPU Action (src/Matrix/FspMatrixBase.cpp:36-62 with the ghost VecScatter of MatMult on MATMPISELL,
+ * and the sink VecScatter ADD of FspMatrixConstrained.cpp:57-60) as ONE launch on one stream, no events, no NCCL:
+ *   leading CTAs   push: pack the boundary entries of x, store them into the peers' ghost windows, publish the epoch
+ *   next CTAs      K partial sink sums -> the sink owner's slot row + flag
+ *   row CTAs       1 row per thread in a rotated order that puts the CTAs with ghost rows last; a warp that meets a
+ *                  ghost column waits (device code, acquire at system scope) for the peers' flags, then reads the
+ *                  ghost entries at L2; every row is computed exactly once
+ *   last CTA       waits for every peer's flag (paces the reuse of the two ghost buffers) and, on the sink owner, adds
+ *                  the slots in rank order into y[n..n+K)
+ * A wait that times out poisons the affected rows of y with NaN and raises the communicator's error flag. */
+FSP_API int fspmat_action_halo(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev,
+                               const fsphalo_epoch *e, const fsphalo_push *push, void *stream);
+/* 1 when fspmat_action_halo covers this operator (values present, 1..16 reactions) */
+FSP_API int fspmat_halo_fused_supported(fspmat_t h);
 
 #ifdef __cplusplus
 }

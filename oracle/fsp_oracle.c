@@ -530,6 +530,129 @@ ORC_API int orc_mat_generate(orc_mat *A, const orc_set *st, int n_tv_in, const i
   return 0;
 }
 
+/* Direct generator for the synthetic 3-D birth-death lattice (BASELINE config 4) in the canonical
+ * lexicographic ordering idx = x0 + L0 (x1 + L1 x2) (sub2ind_nd convention, src/Sys/pacmenMath.h:33-59): builds the
+ * same reference-shaped operators as orc_mat_generate on that state set -- one CSR per TV reaction (diagonal +
+ * off-diagonal, INSERT) and one merged TI CSR (ADD_VALUES, ascending columns), plus the K = 3 sink matrices --
+ * without the BFS, the hash directory or the R x n staging arrays, so that the full 465^3 problem (1e8 states) can be
+ * set up in seconds for the CPU-baseline timing.  tests/test_oracle_kats.py checks it against orc_mat_generate
+ * (by state key) on small boxes.  Values come from the same fixture callback (bd3_prop). */
+static void orc_lattice_rows(orc_csr *M, int n, int nrows, int L0, int L1, int L2, int n_re, const int *reactions) {
+  /* two passes: count, then fill; rows ascending in column; reactions listed in `reactions` are merged (ADD) */
+  M->nrows = nrows; M->ncols = nrows;
+  M->ptr = (int *) calloc((size_t) nrows + 1, sizeof(int));
+  const int  Ls[3] = {L0, L1, L2};
+  const long stride[3] = {1, L0, (long) L0 * L1};
+  int *cnt = (int *) calloc((size_t) nrows + 1, sizeof(int));
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    int x[3] = {i % L0, (i / L0) % L1, i / (L0 * L1)};
+    int c = 1; /* diagonal */
+    for (int q = 0; q < n_re; ++q) {
+      int r = reactions[q], s = r / 2, src = x[s] - ((r & 1) ? -1 : 1);
+      if (src >= 0 && src < Ls[s]) c++;
+    }
+    cnt[i] = c;
+  }
+  long nz = 0;
+  for (int i = 0; i < nrows; ++i) { M->ptr[i] = (int) nz; nz += cnt[i]; }
+  M->ptr[nrows] = (int) nz;
+  free(cnt);
+  M->col = (int *) malloc(sizeof(int) * ((size_t) nz + 1));
+  M->val = (double *) malloc(sizeof(double) * ((size_t) nz + 1));
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    int     x[3] = {i % L0, (i / L0) % L1, i / (L0 * L1)};
+    orc_ent e[16];
+    int     m = 0;
+    double  dsum = 0.0;
+    for (int q = 0; q < n_re; ++q) { /* diagonal: -d_r(x_i), summed in the order of `reactions` (ADD_VALUES) */
+      int    r = reactions[q];
+      double d = 0.0;
+      bd3_prop(r, 3, 1, x, &d, NULL);
+      dsum += -1.0 * d;
+    }
+    e[m].col = i; e[m].val = dsum; m++;
+    for (int q = 0; q < n_re; ++q) { /* off-diagonal: d_r(x_i - nu_r) at the column of x_i - nu_r */
+      int r = reactions[q], s = r / 2, dir = (r & 1) ? -1 : 1;
+      int y[3] = {x[0], x[1], x[2]};
+      y[s] -= dir;
+      if (y[s] < 0 || y[s] >= Ls[s]) continue;
+      double d = 0.0;
+      bd3_prop(r, 3, 1, y, &d, NULL);
+      e[m].col = (int) (i - dir * stride[s]); e[m].val = d; m++;
+    }
+    for (int a = 1; a < m; ++a) { /* ascending columns (distinct by construction) */
+      orc_ent t = e[a];
+      int     b = a - 1;
+      while (b >= 0 && e[b].col > t.col) { e[b + 1] = e[b]; b--; }
+      e[b + 1] = t;
+    }
+    int p0 = M->ptr[i];
+    for (int a = 0; a < m; ++a) { M->col[p0 + a] = e[a].col; M->val[p0 + a] = e[a].val; }
+  }
+}
+static void orc_lattice_sinks(orc_csr *M, int n, int L0, int L1, int L2, int n_re, const int *reactions) {
+  /* K = 3 rows; row k gets (col i, d_r(x_i)) for every state with x_k == L_k - 1 and every listed birth of species k
+   * (FspMatrixConstrained.cpp:170-194: x_i + nu_r violates constraint k; a box face violates exactly one) */
+  const int Ls[3] = {L0, L1, L2};
+  M->nrows = 3; M->ncols = n + 3;
+  M->ptr = (int *) calloc(4, sizeof(int));
+  long tot = 0;
+  int  has[3] = {0, 0, 0};
+  for (int q = 0; q < n_re; ++q) if ((reactions[q] & 1) == 0) has[reactions[q] / 2] = 1;
+  for (int k = 0; k < 3; ++k) { M->ptr[k] = (int) tot; if (has[k]) tot += (long) n / Ls[k]; }
+  M->ptr[3] = (int) tot;
+  M->col = (int *) malloc(sizeof(int) * ((size_t) tot + 1));
+  M->val = (double *) malloc(sizeof(double) * ((size_t) tot + 1));
+  for (int k = 0; k < 3; ++k) {
+    if (!has[k]) continue;
+    long p = M->ptr[k];
+    for (int i = 0; i < n; ++i) {
+      int x[3] = {i % L0, (i / L0) % L1, i / (L0 * L1)};
+      if (x[k] != Ls[k] - 1) continue;
+      double d = 0.0;
+      bd3_prop(2 * k, 3, 1, x, &d, NULL);
+      M->col[p] = i; M->val[p] = d; p++;
+    }
+  }
+}
+ORC_API int orc_mat_generate_lattice(orc_mat *A, int L0, int L1, int L2, int tv) {
+  const long nl = (long) L0 * L1 * L2;
+  if (L0 < 1 || L1 < 1 || L2 < 1 || nl * 7 > 2147483000L) return -1;
+  const int n = (int) nl, R = 6, K = A->constrained ? 3 : 0;
+  orc_mat_destroy_values(A);
+  A->n = n; A->R = R; A->K = K; A->nrows = n + K;
+  A->t_fun = bd3_tfun; A->t_fun_args = NULL;
+  A->coef = (double *) calloc((size_t) R, sizeof(double));
+  A->work = (double *) calloc((size_t) A->nrows + 1, sizeof(double));
+  A->enabled = (int *) malloc(sizeof(int) * R);
+  A->tv = (int *) malloc(sizeof(int) * R);
+  A->ti = (int *) malloc(sizeof(int) * R);
+  A->n_en = R;
+  for (int r = 0; r < R; ++r) {
+    A->enabled[r] = r;
+    if (tv && (r & 1) == 0) A->tv[A->n_tv++] = r; else A->ti[A->n_ti++] = r;
+  }
+  A->tv_mats = (orc_csr *) calloc((size_t) (A->n_tv ? A->n_tv : 1), sizeof(orc_csr));
+  for (int q = 0; q < A->n_tv; ++q) orc_lattice_rows(&A->tv_mats[q], n, A->nrows, L0, L1, L2, 1, &A->tv[q]);
+  if (A->n_ti > 0) { orc_lattice_rows(&A->ti_mat, n, A->nrows, L0, L1, L2, A->n_ti, A->ti); A->has_ti = 1; }
+  if (A->constrained) {
+    A->tv_sinks = (orc_csr *) calloc((size_t) (A->n_tv ? A->n_tv : 1), sizeof(orc_csr));
+    for (int q = 0; q < A->n_tv; ++q) orc_lattice_sinks(&A->tv_sinks[q], n, L0, L1, L2, 1, &A->tv[q]);
+    if (A->n_ti > 0) orc_lattice_sinks(&A->ti_sinks, n, L0, L1, L2, A->n_ti, A->ti);
+  }
+  A->has_values = 1;
+  return 0;
+}
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void) n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Action (reference-shaped, multi-pass).  FspMatrixBase.cpp:36-62 + FspMatrixConstrained.cpp:31-64
  * ---------------------------------------------------------------------------------------------- */

@@ -73,6 +73,8 @@ def lib():
             "orc_expand_vec": (None, [ci, dp, ip, ci, dp]),
             "orc_set_from_fixture": (vp, [C.c_char_p, ip]),
             "orc_mat_generate_fixture": (ci, [vp, vp, C.c_char_p]),
+            "orc_mat_generate_lattice": (ci, [vp, ci, ci, ci, ci]),
+            "orc_set_num_threads": (None, [ci]),
             "orc_fixture_tcoef": (ci, [C.c_char_p, cd, dp]),
             "orc_num_threads": (ci, []),
             "orc_vec_dot": (cd, [C.c_long, dp, dp]),
@@ -228,6 +230,12 @@ class FspMatrix:
         return lib().orc_mat_generate(self.h, state_set.h, len(tv), _ip(tv), C.cast(pt, C.c_void_p),
                                       C.cast(px, C.c_void_p), len(en), _ip(en), None, None)
 
+    def generate_lattice(self, dims, tv=False):
+        """Reference-shaped operators of the synthetic birth-death lattice in lexicographic order, built directly
+        (no BFS / hash directory): the full 465^3 CPU-baseline workload.  Action only (no per-reaction arrays)."""
+        self.set = None
+        return lib().orc_mat_generate_lattice(self.h, int(dims[0]), int(dims[1]), int(dims[2]), 1 if tv else 0)
+
     @property
     def nrows(self):
         return lib().orc_mat_num_rows(self.h)
@@ -314,3 +322,14 @@ def expand_vec(p_old, new_idx, n_new):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def use_all_cores():
+    """OpenMP thread count = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would silently turn the CPU baseline into a single-core run)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(n)
+    return num_threads()

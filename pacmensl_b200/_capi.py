@@ -157,6 +157,11 @@ SIGNATURES = {
     "fsphalo_create": (ci, [vp, vpp, vp, lp, lp, ci]),
     "fsphalo_destroy": (ci, [vp]),
     "fsphalo_begin": (ci, [vp, vp, vp, vp]),
+    "fsphalo_next": (ci, [vp, vp, vp]),
+    "fsphalo_check": (ci, [vp]),
+    "fspcomm_check": (ci, [vp]),
+    "fspmat_action_halo": (ci, [vp, dp, vp, vp, vp, vp, vp]),
+    "fspmat_halo_fused_supported": (ci, [vp]),
 }
 
 _LIB = None

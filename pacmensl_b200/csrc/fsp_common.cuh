@@ -115,4 +115,36 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
   return true;
 }
 
+// ---- push role of the peer-memory halo (fspcomm.cu: halo_push_kernel; fspmat.cu: leading CTAs of the fused action) ---
+// pack + all-to-all over NVLink + signal: entry q of the send list goes straight into the ghost buffer of the peer that
+// needs it; the last push CTA to finish publishes the epoch on every peer (release at system scope orders it after all
+// the data stores, which each CTA made visible with a system-scope fence before taking its ticket).
+struct PushView {
+  int                 size, rank;
+  int                 n_ctas;              // CTAs that share the send list (grid-stride over it)
+  long                n_send;
+  unsigned long long  epoch;
+  const int          *send_idx;            // local indices into x, packed per destination in rank order
+  long                send_off[FSP_P2P_MAX_RANKS + 1];
+  double             *dst[FSP_P2P_MAX_RANKS];   // peer p's ghost buffer of this parity, offset to my segment
+  unsigned long long *flag[FSP_P2P_MAX_RANKS];  // peer p's halo flag of this parity for my rank
+  unsigned           *block_counter;
+};
+__device__ __forceinline__ void push_role(const PushView &a, const double *__restrict__ x, int cta) {
+  for (long q = (long) cta * blockDim.x + threadIdx.x; q < a.n_send; q += (long) a.n_ctas * blockDim.x) {
+    int p = 0;
+    while (q >= a.send_off[p + 1]) ++p;
+    a.dst[p][q - a.send_off[p]] = x[a.send_idx[q]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool push_last;
+  if (threadIdx.x == 0) push_last = (atomicAdd(a.block_counter, 1u) == (unsigned) a.n_ctas - 1u);
+  __syncthreads();
+  if (!push_last) return;
+  __threadfence_system();
+  if ((int) threadIdx.x < a.size) st_release_sys(a.flag[threadIdx.x], a.epoch);
+  if (threadIdx.x == 0) *a.block_counter = 0u;
+}
+
 }  // namespace fspb

@@ -135,35 +135,9 @@ struct fsphalo_s {
 
 namespace {
 
-struct PushArgs {
-  int                 size, rank, parity;
-  long                n_send;
-  unsigned long long  epoch;
-  long                send_off[kMaxRanks + 1];
-  double             *dst[kMaxRanks];    // peer p's ghost buffer of this parity, already offset to my segment
-  unsigned long long *flag[kMaxRanks];   // peer p's halo flag of this parity for my rank
-};
-
-// ONE kernel = pack + all-to-all over NVLink + signal: thread q stores x[send_idx[q]] into the ghost buffer of the
-// peer that needs it; the last CTA to finish publishes epoch on every peer (release at system scope orders it after
-// all the data stores, which each CTA made visible with a system-scope fence before taking its ticket).
-__global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a, const double *__restrict__ x,
-                                                        const int *__restrict__ send_idx, unsigned *block_counter) {
-  const long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < a.n_send) {
-    int p = 0;
-    while (q >= a.send_off[p + 1]) ++p;
-    a.dst[p][q - a.send_off[p]] = x[send_idx[q]];
-  }
-  __threadfence_system();
-  __syncthreads();
-  __shared__ bool last;
-  if (threadIdx.x == 0) last = (atomicAdd(block_counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!last) return;
-  __threadfence_system();
-  if (threadIdx.x < a.size) st_release_sys(a.flag[threadIdx.x], a.epoch);
-  if (threadIdx.x == 0) *block_counter = 0u;
+// ONE kernel = pack + all-to-all over NVLink + signal (push_role, fsp_common.cuh)
+__global__ void __launch_bounds__(256) halo_push_kernel(PushView a, const double *__restrict__ x) {
+  push_role(a, x, (int) blockIdx.x);
 }
 
 struct ReduceArgs {
@@ -500,24 +474,25 @@ int fsphalo_destroy(fsphalo_t h) {
   return 0;
 }
 
-int fsphalo_begin(fsphalo_t h, const double *x_dev, void *stream, fsphalo_epoch *out) {
+// Next epoch of the halo: fills the consumer's view (*out) and the producer's view (*push) without launching anything.
+static int halo_next(fsphalo_s *h, fsphalo_epoch *out, PushView *a) {
   fspcomm_s *c = h->c;
-  if (check_peer_error(c, "fsphalo_begin")) return -1;
+  if (check_peer_error(c, "fsphalo")) return -1;
   const unsigned long long epoch = ++h->w.epoch;
   const int par = (int) (epoch & 1ull);
-  PushArgs a;
-  a.size = c->size; a.rank = c->rank; a.parity = par; a.n_send = h->n_send; a.epoch = epoch;
-  for (int p = 0; p <= c->size; ++p) a.send_off[p] = h->send_off[p];
+  a->size = c->size; a->rank = c->rank; a->n_send = h->n_send; a->epoch = epoch;
+  a->send_idx = h->send_idx;
+  a->block_counter = h->block_counter;
+  // a few entries per thread: the push CTAs lead the fused action kernel and should be few and short
+  a->n_ctas = (int) std::max<long>(1, std::min<long>((h->n_send + 2047) / 2048, 1024));
+  for (int p = 0; p <= c->size; ++p) a->send_off[p] = h->send_off[p];
   for (int p = 0; p < c->size; ++p) {
     char       *base = reinterpret_cast<char *>(h->w.win.peer[p]);
     HaloHeader *H = reinterpret_cast<HaloHeader *>(base);
     double     *ghost = reinterpret_cast<double *>(base + sizeof(HaloHeader)) + (size_t) par * h->w.cap;
-    a.dst[p] = ghost + h->remote_off[p];
-    a.flag[p] = &H->halo_flags[par][c->rank];
+    a->dst[p] = ghost + h->remote_off[p];
+    a->flag[p] = &H->halo_flags[par][c->rank];
   }
-  const unsigned grid = (unsigned) std::max<long>(1, (h->n_send + 255) / 256);
-  halo_push_kernel<<<grid, 256, 0, resolve_stream(stream)>>>(a, x_dev, h->send_idx, h->block_counter);
-  FSP_LAUNCH_CHECK();
   char       *mine = reinterpret_cast<char *>(h->w.win.local);
   HaloHeader *M = reinterpret_cast<HaloHeader *>(mine);
   const int   owner = c->size - 1;
@@ -534,5 +509,26 @@ int fsphalo_begin(fsphalo_t h, const double *x_dev, void *stream, fsphalo_epoch 
   out->error_flag = c->err_dev;
   return 0;
 }
+
+int fsphalo_begin(fsphalo_t h, const double *x_dev, void *stream, fsphalo_epoch *out) {
+  PushView a;
+  if (halo_next(h, out, &a)) return -1;
+  halo_push_kernel<<<(unsigned) a.n_ctas, 256, 0, resolve_stream(stream)>>>(a, x_dev);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fsphalo_next(fsphalo_t h, fsphalo_epoch *out, fsphalo_push *push) {
+  static_assert(sizeof(fsphalo_push) >= sizeof(PushView), "fsphalo_push must be able to hold a PushView");
+  PushView a;
+  if (halo_next(h, out, &a)) return -1;
+  memset(push, 0, sizeof(*push));
+  memcpy(push, &a, sizeof(a));
+  return 0;
+}
+
+int fsphalo_check(fsphalo_t h) { return h ? check_peer_error(h->c, "fsphalo_check") : 0; }
+
+int fspcomm_check(fspcomm_t c) { return (c && c->p2p) ? check_peer_error(c, "fspcomm_check") : 0; }
 
 }  // extern "C"

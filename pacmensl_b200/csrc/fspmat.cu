@@ -20,6 +20,8 @@
 // Roofline: HBM bandwidth; arithmetic intensity ~0.15 flop/byte, so no tensor cores.
 #include <cub/cub.cuh>
 
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -520,6 +522,141 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_p2p_kernel(MatView m, 
   for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
   y[i] = fma(-d, __ldg(x + i), acc);
 }
+// ---- the whole multi-GPU Action in ONE launch (peer-memory mode, default) ----------------------------------------
+// Block roles in blockIdx order: [push CTAs][sink-partial CTAs][row CTAs, rotated][1 finishing CTA].
+//   push     pack + store to the peers' ghost windows + epoch flag (push_role): first in the grid, so the halo is in
+//            flight for the whole duration of the row pass
+//   sinks    K partial sums of this rank -> the owner's slot row + flag
+//   rows     the lean row code (1 row per thread, <= 32 registers, 8 CTAs/SM); CTA b handles rows of CTA (b + rot) mod
+//            n, where rot was chosen at generate time so that the longest circular run of ghost-free CTAs comes first
+//            (lattice blocks: both boundary planes end up at the tail).  No lookup table: a dependent load at the
+//            start of every CTA is a third memory round trip per row and costs 30 % (measured with cta_order[] above).
+//            A warp that meets a ghost column (col <= -2) waits for the peers' flags there and then; warps that never
+//            see one never touch a flag.  Every row is computed exactly once.
+//   finish   waits for every peer's halo flag (this is what paces the reuse of the two ghost buffers: a rank can only
+//            start epoch e+2 after all peers published e+1, i.e. finished reading e) and, on the sink owner, adds the
+//            partial sums in rank order (deterministic) into y[n..n+K).
+// Deadlock freedom: push and sink CTAs never wait; waiting CTAs only wait for PEERS' push CTAs, which run as soon as
+// the peer's kernel starts, whatever the order in which the hardware issues CTAs.
+struct HaloView {
+  PushView                  push;
+  const unsigned long long *halo_flags;
+  const unsigned long long *sink_flags;
+  const double             *sink_slots;
+  const double             *ghost;
+  double                   *sink_slot_remote;
+  unsigned long long       *sink_flag_remote;
+  unsigned int             *err;
+  int                       finish_sinks;   // this rank owns y[n..n+K)
+  int                       rot;
+};
+
+// (scalars by value: taking the address of the kernel-parameter struct would make every thread copy it to its stack)
+__device__ __noinline__ bool warp_wait_halo(const unsigned long long *halo_flags, unsigned long long epoch, int size,
+                                            int rank, unsigned int *err) {
+  const int lane = threadIdx.x & 31;
+  bool      ok = true;
+  if (lane < size && lane != rank) ok = wait_flag(halo_flags + lane, epoch, err);
+  return __all_sync(0xffffffffu, ok);
+}
+
+template <int P>
+__global__ void __launch_bounds__(kThreads, 8) fsp_action_halo_kernel(MatView m, Coefs cf, HaloView hv,
+                                                                      const double *__restrict__ x,
+                                                                      double *__restrict__ y) {
+  int b = (int) blockIdx.x;
+  if (b < hv.push.n_ctas) { push_role(hv.push, x, b); return; }
+  b -= hv.push.n_ctas;
+  if (b < m.sink_blocks) {
+    // partial sink sums of this rank; the last-arriving CTA stores the K sums into the owner's slots and signals
+    __shared__ double smem[32];
+    __shared__ bool   is_last;
+    double            acc = 0.0;
+    for (long q = m.sb_begin[b] + threadIdx.x; q < m.sb_end[b]; q += blockDim.x)
+      acc = fma(ld_stream(m.sink_val + q), __ldg(x + ld_stream(m.sink_idx + q)), acc);
+    const double r = block_sum(acc, smem);
+    if (threadIdx.x == 0) m.sink_partials[b] = r;
+    __threadfence();
+    if (threadIdx.x == 0) is_last = (atomicAdd(m.sink_counter, 1u) == (unsigned) m.sink_blocks - 1u);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = warp; k < m.K; k += nw) {
+      double s = 0.0;
+      for (int q = lane; q < m.sink_blocks; q += 32) {
+        const int seg = m.sb_seg[q];
+        if (seg >= 0 && seg % m.K == k) s = fma(cf.cd[seg / m.K], __ldcg(m.sink_partials + q), s);
+      }
+      s = warp_sum(s);
+      if (lane == 0) hv.sink_slot_remote[k] = s;
+    }
+    if (threadIdx.x == 0) *m.sink_counter = 0u;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(hv.sink_flag_remote, hv.push.epoch);
+    return;
+  }
+  b -= m.sink_blocks;
+  if (b >= m.main_blocks) {
+    // finishing CTA
+    bool ok = true;
+    if ((int) threadIdx.x < hv.push.size && (int) threadIdx.x != hv.push.rank)
+      ok = wait_flag(hv.halo_flags + threadIdx.x, hv.push.epoch, hv.err);
+    if (hv.finish_sinks && (int) threadIdx.x < hv.push.size)
+      ok = wait_flag(hv.sink_flags + threadIdx.x, hv.push.epoch, hv.err) && ok;
+    ok = __syncthreads_and(ok);
+    if (hv.finish_sinks && (int) threadIdx.x < m.K) {
+      double s = 0.0;
+      for (int p = 0; p < hv.push.size; ++p) s += __ldcg(hv.sink_slots + (size_t) p * FSP_P2P_MAX_SINKS + threadIdx.x);
+      y[m.n_rows_main + threadIdx.x] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);  // time-out: poison
+    }
+    return;
+  }
+  int cta = b + hv.rot;
+  if (cta >= m.main_blocks) cta -= m.main_blocks;
+  const int  i = cta * kThreads + (int) threadIdx.x;
+  const bool valid = i < m.n;
+  int        c[P];
+  double     o[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    c[p] = valid ? ld_stream(m.col + (size_t) p * m.ld + i) : -1;
+    o[p] = valid ? ld_stream(m.off + (size_t) p * m.ld + i) : 0.0;
+  }
+  // the diagonal planes and x_i are requested together with the column / value planes (first round trip)
+  double d = 0.0;
+#pragma unroll 2
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], valid ? ld_stream(m.diag + (size_t) g * m.ld + i) : 0.0, d);
+  const double xi = valid ? __ldg(x + i) : 0.0;
+  bool has_ghost = false;
+#pragma unroll
+  for (int p = 0; p < P; ++p) has_ghost |= (c[p] <= -2);
+  bool ok = true;
+  if (__any_sync(0xffffffffu, has_ghost)) ok = warp_wait_halo(hv.halo_flags, hv.push.epoch, hv.push.size, hv.push.rank, hv.err);
+  double acc = 0.0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    double xs;
+    if (c[p] >= 0) xs = __ldg(x + c[p]);
+    else if (c[p] == -1) xs = 0.0;
+    // ghost entries were stored by other GPUs while this kernel was running: read them at L2 (ld.cg), never L1
+    else xs = ok ? __ldcg(hv.ghost + (-(c[p] + 2))) : __longlong_as_double(0x7ff8000000000000ll);
+    acc = fma(cf.c[p] * o[p], xs, acc);
+  }
+  if (valid) y[i] = fma(-d, xi, acc);
+}
+typedef void (*halo_fn)(MatView, Coefs, HaloView, const double *, double *);
+halo_fn pick_halo(int P) {
+  switch (P) {
+#define FSP_CASE(N) case N: return fsp_action_halo_kernel<N>;
+    FSP_CASE(1) FSP_CASE(2) FSP_CASE(3) FSP_CASE(4) FSP_CASE(5) FSP_CASE(6) FSP_CASE(7) FSP_CASE(8)
+    FSP_CASE(9) FSP_CASE(10) FSP_CASE(11) FSP_CASE(12) FSP_CASE(13) FSP_CASE(14) FSP_CASE(15) FSP_CASE(16)
+#undef FSP_CASE
+    default: return nullptr;
+  }
+}
+
 typedef void (*p2p_fn)(MatView, Coefs, P2PWait, const double *, const double *, double *);
 p2p_fn pick_p2p(int P) {
   switch (P) {
@@ -699,6 +836,7 @@ struct fspmat_s {
   int      variant = 0;
   int     *d_cta_order = nullptr;      // CTA issue order of the single-kernel peer-memory action
   int      n_ctas = 0, n_interior_ctas = 0;
+  int      rot = 0;                    // CTA rotation of the fused halo action (longest ghost-free run first)
   double  *d_epi_partials = nullptr;   // fused-epilogue inner-product partials (allocated on first use)
   int     *d_boundary_rows = nullptr;  // rows referencing ghost entries (multi-GPU)
   long     n_boundary = 0;
@@ -812,6 +950,22 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
     if (h->n_boundary > 0) {
       mark_cta_kernel<<<(unsigned) ((h->n_boundary + 255) / 256), 256, 0, st>>>(h->d_boundary_rows, h->n_boundary, d_flag);
       FSP_LAUNCH_CHECK();
+    }
+    {
+      // rotation of the fused halo action: start right after the ghost CTA that precedes the longest circular run of
+      // ghost-free CTAs, so that this run comes first and the CTAs that wait for the peers come last
+      std::vector<int> flag((size_t) n_ctas);
+      FSP_CUDA_CHECK(cudaMemcpyAsync(flag.data(), d_flag, sizeof(int) * n_ctas, cudaMemcpyDeviceToHost, st));
+      FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+      int best_len = -1, best_start = 0, run = 0;
+      for (int q = 0; q < 2 * n_ctas; ++q) {
+        const int cta = q % n_ctas;
+        if (flag[(size_t) cta]) { run = 0; continue; }
+        ++run;
+        if (run > n_ctas) run = n_ctas;
+        if (run > best_len) { best_len = run; best_start = (q - run + 1 + n_ctas) % n_ctas; }
+      }
+      h->rot = best_len > 0 ? best_start : 0;
     }
     cub::CountingInputIterator<int> iota(0);
     CtaIsInterior pred{d_flag};
@@ -1108,6 +1262,29 @@ int fspmat_action_p2p(fspmat_t h, const double *coef_host, const double *x, doub
   w.sink_slots = e->sink_slots;
   w.epoch = e->epoch; w.n_ranks = e->n_ranks; w.err = e->error_flag; w.rank = e->self_rank;
   fn<<<m.main_blocks + (finish_sinks ? 1 : 0), kThreads, 0, resolve_stream(stream)>>>(m, cf, w, x, e->ghost, y);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+int fspmat_halo_fused_supported(fspmat_t h) { return (h->has_values && h->P >= 1 && h->P <= 16) ? 1 : 0; }
+
+int fspmat_action_halo(fspmat_t h, const double *coef_host, const double *x, double *y, const fsphalo_epoch *e,
+                       const fsphalo_push *push, void *stream) {
+  if (!h->has_values) return 0;
+  halo_fn fn = pick_halo(h->P);
+  if (!fn) { set_error("fspmat_action_halo: supports 1..16 reactions (got %d)", h->P); return -1; }
+  Coefs cf; MatView m;
+  fill_coefs_view(h, coef_host, cf, m);
+  m.main_blocks = (int) (((long) h->n + kThreads - 1) / kThreads);
+  HaloView hv;
+  memcpy(&hv.push, push, sizeof(PushView));
+  hv.halo_flags = e->halo_flags; hv.sink_flags = e->sink_flags; hv.sink_slots = e->sink_slots;
+  hv.ghost = e->ghost; hv.sink_slot_remote = e->sink_slot_remote; hv.sink_flag_remote = e->sink_flag_remote;
+  hv.err = e->error_flag;
+  hv.finish_sinks = (h->K > 0 && h->owns_sinks) ? 1 : 0;
+  hv.rot = (h->rot < m.main_blocks) ? h->rot : 0;
+  const int grid = hv.push.n_ctas + m.sink_blocks + m.main_blocks + 1;
+  fn<<<grid, kThreads, 0, resolve_stream(stream)>>>(m, cf, hv, x, y);
   FSP_LAUNCH_CHECK();
   return 0;
 }

@@ -477,11 +477,26 @@ PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec
     //   main stream : interior pass; then the boundary kernel waits for the peers' flags in device code, redoes the
     //                 rows with ghost entries and (sink owner) adds the slots in rank order into y[n..n+K)
     fsphalo_epoch ep;
-    // Default: interior pass + boundary kernel that waits for the peers' flags (validated and measured on 2 and 8
-    // GPUs).  FSP_P2P_SINGLE=1 selects the single-kernel form (ghost-free CTAs first, waiting CTAs last): correct, but
-    // it measured 0.96 ms against 0.74 ms per Action on 2 GPUs (465^3 lattice) -- CTAs are evidently not issued
-    // strictly in blockIdx order, so some waiting CTAs start early and hold SM slots; kept for further work.
-    static const bool split = [] { const char *e = std::getenv("FSP_P2P_SINGLE"); return !(e && e[0] == '1'); }();
+    // Default: ONE launch on the caller's stream (fspmat_action_halo: push CTAs, sink CTAs, row CTAs in rotated order
+    // with a device-side wait where a warp meets a ghost column, finishing CTA) -- no side stream, no events, every row
+    // computed once.  FSP_P2P_MODE=split keeps round 1's interior pass + boundary kernel (rows with ghost entries
+    // computed twice, 4 launches on 2 streams); FSP_P2P_MODE=order (or FSP_P2P_SINGLE=1) its single-kernel form with a
+    // CTA order table, which measured 0.96 ms against 0.74 ms (split) per Action on 2 GPUs: the table look-up at the
+    // start of every CTA is a third dependent memory round trip per row.
+    static const int p2p_mode = [] {
+      const char *e = std::getenv("FSP_P2P_MODE"), *s1 = std::getenv("FSP_P2P_SINGLE");
+      if (s1 && s1[0] == '1') return 2;
+      if (e && !std::strcmp(e, "split")) return 1;
+      if (e && !std::strcmp(e, "order")) return 2;
+      return 0;
+    }();
+    if (p2p_mode == 0 && fspmat_halo_fused_supported(dmat_)) {
+      fsphalo_push push;
+      FSPCHKERRQ(fsphalo_next(halo_, &ep, &push));
+      FSPCHKERRQ(fspmat_action_halo(dmat_, coefs, x->d_data, y->d_data, &ep, &push, stream));
+      return 0;
+    }
+    const bool split = p2p_mode != 2;
     FSPCHKERRQ(fsp_event_record(ev_x_ready_, stream));
     FSPCHKERRQ(fsp_stream_wait_event(comm_stream_, ev_x_ready_));
     FSPCHKERRQ(fsphalo_begin(halo_, x->d_data, comm_stream_, &ep));

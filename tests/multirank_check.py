@@ -44,49 +44,11 @@ def main():
     if rank == 0:
         print("peer-memory fast path: %s" % ("on" if api.p2p_enabled() else "off (NCCL)"))
 
-    # ---- 1. partitioned Action vs oracle ----
-    from helpers import rel_err
-    from oracle import oracle as O
-    for tv, name in ((False, "birth_death_3d"), (True, "birth_death_3d_tv")):
-        upper = [21, 17, 13]
-        lat = Lattice(upper, tv=tv)
-        N = lat.n_global
-        K = 3
-        rng = np.random.default_rng(99)
-        xg = rng.random(N + K)
-        sizes_rows = [0] * world
-        t_sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-        t_sizes[rank] = lat.n_rows
-        dist.all_reduce(t_sizes)
-        sizes_rows = [int(v) for v in t_sizes.tolist()]
-        xl = np.concatenate([xg[lat.start: lat.start + lat.n_local], xg[N:] if rank == world - 1 else np.zeros(0)])
-        assert len(xl) == lat.n_rows
-        for t in (0.0, 4.0):
-            xd = torch.from_numpy(xl).to(dev)
-            yd = torch.empty_like(xd)
-            for rep in range(5):  # repeated calls walk through both parities of the double-buffered ghost windows
-                yd.fill_(float("nan"))
-                lat.action(t, xd if rep == 4 else xd * (rep + 2.0), yd)
-            torch.cuda.synchronize()
-            yg = gather_blocks(yd, sizes_rows, dev)   # states of rank 0.., then the K sinks of the last rank
-            if rank == 0:
-                st = O.StateSet(fixture=name, bounds=upper)
-                st.expand()
-                A = O.FspMatrix(constrained=True)
-                A.generate_fixture(st, name)
-                Ls = [u + 1 for u in upper]
-                idx = np.arange(N)
-                X = np.stack([idx % Ls[0], (idx // Ls[0]) % Ls[1], idx // (Ls[0] * Ls[1])], axis=1).astype(np.int32)
-                perm = st.state2index(X)
-                x_or = np.zeros(N + K)
-                x_or[perm] = xg[:N]
-                x_or[N:] = xg[N:]
-                ierr, y_or = A.action(t, x_or)
-                e1 = rel_err(yg[:N], y_or[perm], scale=np.abs(y_or).max())
-                e2 = rel_err(yg[N:], y_or[N:], scale=np.abs(y_or).max())
-                print("action parity tv=%d t=%g: rel_err states %.2e sinks %.2e" % (tv, t, e1, e2))
-                ok &= e1 <= 1e-12 and e2 <= 1e-12
-        del lat
+    # ---- 1. partitioned Action vs oracle, by state key (lattice TI/TV, transcr_reg_6d, hog1p, and pure_birth where
+    #         rank 0 references no ghost column at all -- the case that broke round 1's single-kernel path) ----
+    import parity_leg
+    par = parity_leg.run(api, dist, dev, verbose=True)
+    ok &= par["ok"] if rank == 0 else True
 
     # ---- 2. adaptive FSP solve on N ranks vs Poisson ----
     for ode, label in ((api.KRYLOV, "krylov"), (api.CVODE, "cvode")):

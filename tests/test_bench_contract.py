@@ -24,6 +24,17 @@ def test_reference_arm_prints_the_contract_line():
     assert j["gpu_launches"] == 0 and j["vs_baseline"] is None
 
 
+def test_reference_arm_uses_all_cores_under_torchrun_env():
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every core it may run on
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                        "--lattice", "40"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    assert j["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert j["config"]["same_config"] is True and j["config"]["states"] == 40 ** 3 and j["n_gpus"] == 2
+
+
 def test_reference_arm_other_ranks_exit_without_work():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2"],

@@ -136,3 +136,34 @@ def test_t_fun_error_propagates(oracle):
 def test_expand_vec(oracle):
     p = oracle.expand_vec([0.1, 0.2, 0.3], [2, 0, 4], 6)
     assert p.tolist() == [0.2, 0.0, 0.1, 0.0, 0.3, 0.0]
+
+
+@pytest.mark.parametrize("tv", [False, True])
+@pytest.mark.parametrize("dims", [[7, 5, 4], [1, 6, 3], [9, 9, 9]])
+def test_direct_lattice_generator_matches_generic(oracle, tv, dims):
+    # the CPU-baseline operator of the full 465^3 lattice is built directly in lexicographic order
+    # (orc_mat_generate_lattice); it must be the operator orc_mat_generate produces on the BFS-ordered set, by state key
+    O = oracle
+    name = "birth_death_3d_tv" if tv else "birth_death_3d"
+    st = O.StateSet(fixture=name, bounds=[d - 1 for d in dims])
+    st.expand()
+    A = O.FspMatrix(constrained=True)
+    assert A.generate_fixture(st, name) == 0
+    B = O.FspMatrix(constrained=True)
+    assert B.generate_lattice(dims, tv) == 0
+    N = st.n
+    assert N == int(np.prod(dims)) and B.nrows == A.nrows == N + 3 and A.flops() == B.flops()
+    idx = np.arange(N)
+    X = np.stack([idx % dims[0], (idx // dims[0]) % dims[1], idx // (dims[0] * dims[1])], axis=1).astype(np.int32)
+    perm = st.state2index(X)
+    assert (perm >= 0).all()
+    xl = np.random.default_rng(5).random(N + 3)
+    xo = np.zeros(N + 3)
+    xo[perm] = xl[:N]
+    xo[N:] = xl[N:]
+    for t in (0.0, 2.5):
+        _, ya = A.action(t, xo)
+        _, yb = B.action(t, xl)
+        # same entries; the summation order inside a row follows the column order of each ordering (last-bit effects)
+        np.testing.assert_allclose(yb[:N], ya[perm], rtol=1e-13, atol=1e-13 * np.abs(ya).max())
+        np.testing.assert_allclose(yb[N:], ya[N:], rtol=1e-13)
