@@ -294,6 +294,29 @@ __global__ void __launch_bounds__(kThreads) fsp_action_generic(MatView m, Coefs 
 // because every thread does TWO dependent memory round trips (column index, then the gathered x entry).
 // GHOST: 0 = no ghost columns exist (single GPU), 1 = ghost buffer valid, 2 = interior pass (ghost entries count 0),
 //        3 = no ghost columns, rows [m.row0, m.n) only (chunks of the host-vector pipeline, fspmat_action_rows).
+// One row of y = A(t) x, the body shared by the single-GPU kernel and the row CTAs of the fused multi-GPU kernel.
+// GHOST: 0 = no ghost columns can occur; 1 = ghost entries are read from `ghost` at L2 (ld.cg: other GPUs stored them
+// while this kernel was running) plus `poison` (0, or NaN after a timed-out wait); 2 = ghost entries count 0.
+template <int P, int GHOST>
+__device__ __forceinline__ double lean_row(const MatView &m, const Coefs &cf, const double *__restrict__ x,
+                                           const double *ghost, double poison, int i) {
+  const int    *cp = m.col + i;
+  const double *op = m.off + i;
+  double acc = 0.0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int    c = ld_stream(cp + (size_t) p * m.ld);
+    const double o = ld_stream(op + (size_t) p * m.ld);
+    double xs = c >= 0 ? __ldg(x + c) : 0.0;
+    if (GHOST == 1) xs += c <= -2 ? __ldcg(ghost + (-(c + 2))) + poison : 0.0;
+    acc = fma(cf.c[p] * o, xs, acc);
+  }
+  double d = 0.0;
+  const double *dp = m.diag + i;
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
+  return fma(-d, __ldg(x + i), acc);
+}
+
 template <int P, int GHOST>
 __global__ void __launch_bounds__(kThreads, 8) fsp_action_lean(MatView m, Coefs cf, const double *__restrict__ x,
                                                                 const double *__restrict__ ghost,
@@ -304,23 +327,7 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_lean(MatView m, Coefs 
   }
   const int i = (GHOST == 3 ? m.row0 : 0) + (int) blockIdx.x * kThreads + (int) threadIdx.x;
   if (i >= m.n) return;
-  const int    *cp = m.col + i;
-  const double *op = m.off + i;
-  double acc = 0.0;
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    const int    c = ld_stream(cp + (size_t) p * m.ld);
-    const double o = ld_stream(op + (size_t) p * m.ld);
-    double xs;
-    if (GHOST == 0 || GHOST == 3) xs = c >= 0 ? __ldg(x + c) : 0.0;
-    else if (GHOST == 2) xs = c >= 0 ? __ldg(x + c) : 0.0;
-    else xs = c >= 0 ? __ldg(x + c) : (c == -1 ? 0.0 : __ldg(ghost + (-(c + 2))));
-    acc = fma(cf.c[p] * o, xs, acc);
-  }
-  double d = 0.0;
-  const double *dp = m.diag + i;
-  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(dp + (size_t) g * m.ld), d);
-  y[i] = fma(-d, __ldg(x + i), acc);
+  y[i] = lean_row<P, (GHOST == 1 ? 1 : 0)>(m, cf, x, ghost, 0.0, i);
 }
 
 // Action with fused epilogue (solver hot loops).  Same shape as the lean kernel (1 row per thread, 32 registers, 8
@@ -531,8 +538,8 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_p2p_kernel(MatView m, 
 //            n, where rot was chosen at generate time so that the longest circular run of ghost-free CTAs comes first
 //            (lattice blocks: both boundary planes end up at the tail).  No lookup table: a dependent load at the
 //            start of every CTA is a third memory round trip per row and costs 30 % (measured with cta_order[] above).
-//            A warp that meets a ghost column (col <= -2) waits for the peers' flags there and then; warps that never
-//            see one never touch a flag.  Every row is computed exactly once.
+//            The first n_fast CTAs of that order hold no ghost column and run exactly the single-GPU row code; the
+//            others first wait for the peers' flags.  Every row is computed exactly once.
 //   finish   waits for every peer's halo flag (this is what paces the reuse of the two ghost buffers: a rank can only
 //            start epoch e+2 after all peers published e+1, i.e. finished reading e) and, on the sink owner, adds the
 //            partial sums in rank order (deterministic) into y[n..n+K).
@@ -548,17 +555,9 @@ struct HaloView {
   unsigned long long       *sink_flag_remote;
   unsigned int             *err;
   int                       finish_sinks;   // this rank owns y[n..n+K)
-  int                       rot;
+  int                       rot;            // row CTA b handles the rows of CTA (b + rot) mod n
+  int                       n_fast;         // the first n_fast row CTAs (in that order) hold no ghost column
 };
-
-// (scalars by value: taking the address of the kernel-parameter struct would make every thread copy it to its stack)
-__device__ __noinline__ bool warp_wait_halo(const unsigned long long *halo_flags, unsigned long long epoch, int size,
-                                            int rank, unsigned int *err) {
-  const int lane = threadIdx.x & 31;
-  bool      ok = true;
-  if (lane < size && lane != rank) ok = wait_flag(halo_flags + lane, epoch, err);
-  return __all_sync(0xffffffffu, ok);
-}
 
 template <int P>
 __global__ void __launch_bounds__(kThreads, 8) fsp_action_halo_kernel(MatView m, Coefs cf, HaloView hv,
@@ -615,36 +614,19 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_halo_kernel(MatView m,
   }
   int cta = b + hv.rot;
   if (cta >= m.main_blocks) cta -= m.main_blocks;
-  const int  i = cta * kThreads + (int) threadIdx.x;
-  const bool valid = i < m.n;
-  int        c[P];
-  double     o[P];
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    c[p] = valid ? ld_stream(m.col + (size_t) p * m.ld + i) : -1;
-    o[p] = valid ? ld_stream(m.off + (size_t) p * m.ld + i) : 0.0;
+  const int i = cta * kThreads + (int) threadIdx.x;
+  if (b < hv.n_fast) {
+    // ghost-free CTAs (by construction of rot / n_fast at generate time): exactly the single-GPU row code
+    if (i < m.n) y[i] = lean_row<P, 0>(m, cf, x, nullptr, 0.0, i);
+    return;
   }
-  // the diagonal planes and x_i are requested together with the column / value planes (first round trip)
-  double d = 0.0;
-#pragma unroll 2
-  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], valid ? ld_stream(m.diag + (size_t) g * m.ld + i) : 0.0, d);
-  const double xi = valid ? __ldg(x + i) : 0.0;
-  bool has_ghost = false;
-#pragma unroll
-  for (int p = 0; p < P; ++p) has_ghost |= (c[p] <= -2);
+  // CTAs that may hold ghost columns: wait for the peers' flags, then the same row code with the ghost window
   bool ok = true;
-  if (__any_sync(0xffffffffu, has_ghost)) ok = warp_wait_halo(hv.halo_flags, hv.push.epoch, hv.push.size, hv.push.rank, hv.err);
-  double acc = 0.0;
-#pragma unroll
-  for (int p = 0; p < P; ++p) {
-    double xs;
-    if (c[p] >= 0) xs = __ldg(x + c[p]);
-    else if (c[p] == -1) xs = 0.0;
-    // ghost entries were stored by other GPUs while this kernel was running: read them at L2 (ld.cg), never L1
-    else xs = ok ? __ldcg(hv.ghost + (-(c[p] + 2))) : __longlong_as_double(0x7ff8000000000000ll);
-    acc = fma(cf.c[p] * o[p], xs, acc);
-  }
-  if (valid) y[i] = fma(-d, xi, acc);
+  if ((int) threadIdx.x < hv.push.size && (int) threadIdx.x != hv.push.rank)
+    ok = wait_flag(hv.halo_flags + threadIdx.x, hv.push.epoch, hv.err);
+  ok = __syncthreads_and(ok);
+  const double poison = ok ? 0.0 : __longlong_as_double(0x7ff8000000000000ll);  // time-out: NaN into the rows that need the halo
+  if (i < m.n) y[i] = lean_row<P, 1>(m, cf, x, hv.ghost, poison, i);
 }
 typedef void (*halo_fn)(MatView, Coefs, HaloView, const double *, double *);
 halo_fn pick_halo(int P) {
@@ -836,7 +818,7 @@ struct fspmat_s {
   int      variant = 0;
   int     *d_cta_order = nullptr;      // CTA issue order of the single-kernel peer-memory action
   int      n_ctas = 0, n_interior_ctas = 0;
-  int      rot = 0;                    // CTA rotation of the fused halo action (longest ghost-free run first)
+  int      rot = 0, n_fast = 0;        // fused halo action: CTA rotation (longest ghost-free run first) and its length
   double  *d_epi_partials = nullptr;   // fused-epilogue inner-product partials (allocated on first use)
   int     *d_boundary_rows = nullptr;  // rows referencing ghost entries (multi-GPU)
   long     n_boundary = 0;
@@ -966,6 +948,7 @@ int fspmat_generate(fspmat_t h, const fspmat_desc *d) {
         if (run > best_len) { best_len = run; best_start = (q - run + 1 + n_ctas) % n_ctas; }
       }
       h->rot = best_len > 0 ? best_start : 0;
+      h->n_fast = best_len > 0 ? best_len : 0;
     }
     cub::CountingInputIterator<int> iota(0);
     CtaIsInterior pred{d_flag};
@@ -1283,6 +1266,8 @@ int fspmat_action_halo(fspmat_t h, const double *coef_host, const double *x, dou
   hv.err = e->error_flag;
   hv.finish_sinks = (h->K > 0 && h->owns_sinks) ? 1 : 0;
   hv.rot = (h->rot < m.main_blocks) ? h->rot : 0;
+  // operators without ghost columns (d_cta_order unset): every CTA is ghost-free
+  hv.n_fast = h->n_ghost > 0 ? h->n_fast : m.main_blocks;
   const int grid = hv.push.n_ctas + m.sink_blocks + m.main_blocks + 1;
   fn<<<grid, kThreads, 0, resolve_stream(stream)>>>(m, cf, hv, x, y);
   FSP_LAUNCH_CHECK();
