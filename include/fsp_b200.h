@@ -410,6 +410,19 @@ FSP_API int fspcomm_check(fspcomm_t c);
  * A wait that times out poisons the affected rows of y with NaN and raises the communicator's error flag. */
 FSP_API int fspmat_action_halo(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev,
                                const fsphalo_epoch *e, const fsphalo_push *push, void *stream);
+/* Pieces of fspmat_action_halo for callers that feed x in chunks (the host-vector pipeline, FspMatrixBase::ActionHost on
+ * N ranks); all pieces of one Action share the (e, push) pair of ONE fsphalo_next call.
+ *   parts            bit 0: push CTAs -- they read packed_send_dev[q] when it is non-NULL (the caller packed
+ *                    x[send_idx[q]] itself, e.g. on the host) and x_dev[send_idx[q]] otherwise;
+ *                    bit 1: the K partial sink sums of this rank (needs all of x_dev) -> owner's slots + flag;
+ *                    bit 2: the finishing CTA (waits for every peer's flag; sink owner: slots -> y[n..n+K)).  Every
+ *                    Action must run it exactly once, last: it paces the reuse of the two ghost buffers.
+ *   rows             [row_begin, row_end) of y; rows_have_ghosts != 0: the CTAs wait for the peers' flags first. */
+FSP_API int fspmat_action_halo_part(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev,
+                                    const fsphalo_epoch *e, const fsphalo_push *push, int parts, long row_begin,
+                                    long row_end, int rows_have_ghosts, const double *packed_send_dev, void *stream);
+/* chunk_flag_host[c] = 1 when rows [c*chunk_rows, (c+1)*chunk_rows) hold a row that references a ghost entry */
+FSP_API int fspmat_chunk_has_ghost(fspmat_t h, long chunk_rows, int n_chunks, int *chunk_flag_host);
 /* 1 when fspmat_action_halo covers this operator (values present, 1..16 reactions) */
 FSP_API int fspmat_halo_fused_supported(fspmat_t h);
 

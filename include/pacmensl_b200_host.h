@@ -32,6 +32,10 @@ FSP_API int         pfsp_init(int device, const char *nccl_id, int rank, int siz
 FSP_API int         pfsp_finalize(void);
 /* 1 when the world communicator uses the peer-memory (CUDA IPC over NVLink) fast path, 0 = NCCL path / single rank */
 FSP_API int         pfsp_p2p_enabled(void);
+/* Synchronises the device and returns non-zero (message in fsp_last_error) if a device-side wait for a peer GPU has timed
+ * out since the communicator was created: the results produced since then were poisoned with NaN.  Asynchronous calls
+ * (pfsp_mat_action returns once its kernel is queued) cannot report this themselves. */
+FSP_API int         pfsp_check(void);
 FSP_API const char *pfsp_last_error(void);
 
 /* ---- state set ---- */

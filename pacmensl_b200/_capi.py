@@ -162,6 +162,8 @@ SIGNATURES = {
     "fspcomm_check": (ci, [vp]),
     "fspmat_action_halo": (ci, [vp, dp, vp, vp, vp, vp, vp]),
     "fspmat_halo_fused_supported": (ci, [vp]),
+    "fspmat_action_halo_part": (ci, [vp, dp, vp, vp, vp, vp, ci, cl, cl, ci, vp, vp]),
+    "fspmat_chunk_has_ghost": (ci, [vp, cl, ci, ip]),
 }
 
 _LIB = None

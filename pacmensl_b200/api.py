@@ -21,6 +21,7 @@ HOST_SIGNATURES = {
     "pfsp_init": (ci, [ci, C.c_char_p, ci, ci]),
     "pfsp_finalize": (ci, []),
     "pfsp_p2p_enabled": (ci, []),
+    "pfsp_check": (ci, []),
     "pfsp_last_error": (C.c_char_p, []),
     "pfsp_set_create": (ci, [vpp]),
     "pfsp_set_destroy": (ci, [vp]),
@@ -115,6 +116,11 @@ def init(device=0, dist=None):
 
 def finalize():
     lib().pfsp_finalize()
+
+
+def health_check():
+    """Device synchronisation + peer-memory health: non-zero once a device-side wait for a peer GPU has timed out."""
+    return lib().pfsp_check()
 
 
 def p2p_enabled():

@@ -95,9 +95,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-// spin until *flag >= epoch; false (and *err = 1) after kSpinTimeoutNs so that a lost peer cannot hang the GPU.  Once
+// spin until *flag >= epoch; false (and *err = 1) after the time-out so that a lost peer cannot hang the GPU.  Once
 // the error flag is up (an earlier wait timed out) every later wait gives up after ~1000 polls instead of another
-// 20 s, so a failed rank costs its peers one time-out, not one per kernel.
+// 20 s, so a failed rank costs its peers one time-out, not one per kernel.  err points at two mapped host words:
+// err[0] = error flag, err[1] = time-out in milliseconds (0: the default kSpinTimeoutNs; FSP_SPIN_TIMEOUT_MS).
+// Callers must act on a false return: poison what they were about to produce (NaN) -- never consume the peer data.
 __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long epoch, unsigned int *err) {
   if (ld_acquire_sys(flag) >= epoch) return true;
   const unsigned long long t0 = global_ns();
@@ -106,7 +108,9 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
     __nanosleep(64);
     if ((++polls & 1023u) == 0u) {
       if (err && *(volatile unsigned int *) err) return false;
-      if (global_ns() - t0 > kSpinTimeoutNs) {
+      const unsigned           ms = err ? ((volatile unsigned int *) err)[1] : 0u;
+      const unsigned long long limit = ms ? (unsigned long long) ms * 1000000ull : kSpinTimeoutNs;
+      if (global_ns() - t0 > limit) {
         if (err) *(volatile unsigned int *) err = 1u;
         return false;
       }
@@ -134,7 +138,7 @@ __device__ __forceinline__ void push_role(const PushView &a, const double *__res
   for (long q = (long) cta * blockDim.x + threadIdx.x; q < a.n_send; q += (long) a.n_ctas * blockDim.x) {
     int p = 0;
     while (q >= a.send_off[p + 1]) ++p;
-    a.dst[p][q - a.send_off[p]] = x[a.send_idx[q]];
+    a.dst[p][q - a.send_off[p]] = a.send_idx ? x[a.send_idx[q]] : x[q];  // send_idx == null: x is the packed send buffer
   }
   __threadfence_system();
   __syncthreads();

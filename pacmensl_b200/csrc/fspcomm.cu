@@ -30,7 +30,7 @@ namespace {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclInt32 = 2, ncclFloat64 = 8 };
+enum { ncclInt32 = 2, ncclInt64 = 4, ncclFloat64 = 8 };
 enum { ncclSum = 0, ncclMax = 2 };
 
 struct NcclApi {
@@ -118,6 +118,7 @@ struct fspcomm_s {
   unsigned long long red_epoch = 0;
   unsigned int      *err_host = nullptr;  // pinned + mapped: device code sets it when a flag wait times out
   unsigned int      *err_dev = nullptr;
+  double            *stage = nullptr;     // small device staging buffer of the set-up collectives (handles, agreement flags)
   struct PooledHalo { PeerWindow win; size_t cap = 0; unsigned long long epoch = 0; };
   std::vector<PooledHalo> halo_pool;  // windows returned by fsphalo_destroy, identical order/capacity on all ranks
 };
@@ -161,47 +162,77 @@ __global__ void __launch_bounds__(128) p2p_allreduce_kernel(ReduceArgs a, double
   }
   __threadfence_system();
   __syncthreads();
+  bool ok = true;
   if (t < a.size) {
     st_release_sys(a.flag[t], a.epoch);
-    wait_flag(a.my_flags + t, a.epoch, a.err);
+    ok = wait_flag(a.my_flags + t, a.epoch, a.err);
   }
-  __syncthreads();
+  ok = __syncthreads_and(ok);
   if (t < a.n) {
     double s = __ldcg(a.my_slots + t);
     for (int p = 1; p < a.size; ++p) {
       const double v = __ldcg(a.my_slots + (size_t) p * kMaxRedVals + t);
       s = IS_MAX ? fmax(s, v) : s + v;
     }
-    buf[t] = s;
+    // a peer that never arrived: poison the result instead of leaving a partial sum in place (the host reports the
+    // error at its next synchronisation: fspcomm_check / check_peer_error)
+    buf[t] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
   }
 }
 
+constexpr size_t kStageBytes = 64 * (size_t) (kMaxRanks + 2);
+
+// Agreement step of the collective set-up paths: returns 0 when EVERY rank passed ok == true, 1 when some rank failed
+// (all ranks then take the same fall-back), -1 when the collective itself failed.  Every rank-local fallible step of a
+// collective set-up is followed by one of these before its result is committed, so ranks can never disagree on
+// whether a window / the peer-memory path exists (a disagreement ends in 20 s spin time-outs or an NCCL hang).
+int agree(fspcomm_s *c, bool ok) {
+  double v = ok ? 0.0 : 1.0;
+  if (cudaMemcpy(c->stage, &v, 8, cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); v = 1.0; }
+  if (g_nccl.AllReduce(c->stage, c->stage, 1, ncclFloat64, ncclSum, c->comm, (cudaStream_t) 0) != ncclSuccess) return -1;
+  if (cudaMemcpy(&v, c->stage, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return v == 0.0 ? 0 : 1;
+}
+
+void window_destroy(fspcomm_s *c, PeerWindow *w);
+
+// collective: allocate + zero the local part, all-gather the IPC handles over NCCL, map every peer.  Returns 0 on ALL
+// ranks or -1 on ALL ranks (nothing left allocated or mapped): local failures are agreed on before returning, and every
+// rank takes part in every collective call whatever happened to it locally.
 int window_create(fspcomm_s *c, size_t bytes, PeerWindow *w) {
-  // collective: allocate + zero the local part, all-gather the IPC handles over NCCL, map every peer
+  *w = PeerWindow();
   w->bytes = bytes;
-  FSP_CUDA_CHECK(cudaMalloc(&w->local, bytes));
-  FSP_CUDA_CHECK(cudaMemset(w->local, 0, bytes));
-  FSP_CUDA_CHECK(cudaDeviceSynchronize());
+  bool ok = cudaMalloc(&w->local, bytes) == cudaSuccess;
+  if (!ok) w->local = nullptr;
+  ok = ok && cudaMemset(w->local, 0, bytes) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
   cudaIpcMemHandle_t mine;
-  FSP_CUDA_CHECK(cudaIpcGetMemHandle(&mine, w->local));
+  memset(&mine, 0, sizeof(mine));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  double *d_send = nullptr, *d_all = nullptr;
-  FSP_CUDA_CHECK(cudaMalloc(&d_send, 64));
-  FSP_CUDA_CHECK(cudaMalloc(&d_all, 64 * (size_t) c->size));
-  FSP_CUDA_CHECK(cudaMemcpy(d_send, &mine, 64, cudaMemcpyHostToDevice));
-  FSP_NCCL_CHECK(g_nccl.AllGather(d_send, d_all, 8, ncclFloat64, c->comm, (cudaStream_t) 0));
+  ok = ok && cudaIpcGetMemHandle(&mine, w->local) == cudaSuccess;
+  double *d_send = c->stage + 8, *d_all = c->stage + 16;  // 64 bytes + 64 bytes per rank
+  ok = (cudaMemcpy(d_send, &mine, 64, cudaMemcpyHostToDevice) == cudaSuccess) && ok;
+  const bool coll_ok = g_nccl.AllGather(d_send, d_all, 8, ncclFloat64, c->comm, (cudaStream_t) 0) == ncclSuccess;
   std::vector<cudaIpcMemHandle_t> all((size_t) c->size);
-  FSP_CUDA_CHECK(cudaMemcpy(all.data(), d_all, 64 * (size_t) c->size, cudaMemcpyDeviceToHost));
-  cudaFree(d_send);
-  cudaFree(d_all);
-  for (int p = 0; p < c->size; ++p) {
-    if (p == c->rank) { w->peer[p] = w->local; continue; }
-    cudaError_t e = cudaIpcOpenMemHandle(&w->peer[p], all[(size_t) p], cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      set_error("cudaIpcOpenMemHandle(peer %d) failed: %s", p, cudaGetErrorString(e));
-      cudaGetLastError();
-      return -1;
+  ok = ok && coll_ok && cudaMemcpy(all.data(), d_all, 64 * (size_t) c->size, cudaMemcpyDeviceToHost) == cudaSuccess;
+  // every rank must have produced a handle before anybody maps anything
+  int agreed = coll_ok ? agree(c, ok) : -1;
+  if (agreed == 0) {
+    for (int p = 0; p < c->size && ok; ++p) {
+      if (p == c->rank) { w->peer[p] = w->local; continue; }
+      cudaError_t e = cudaIpcOpenMemHandle(&w->peer[p], all[(size_t) p], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        set_error("cudaIpcOpenMemHandle(peer %d) failed: %s", p, cudaGetErrorString(e));
+        w->peer[p] = nullptr;
+        ok = false;
+      }
     }
+    agreed = agree(c, ok);
+  }
+  cudaGetLastError();
+  if (agreed != 0) {
+    window_destroy(c, w);
+    if (agreed > 0 && ok) set_error("window_create: another rank could not create or map its peer-memory window");
+    return -1;
   }
   return 0;
 }
@@ -243,31 +274,34 @@ int p2p_allreduce(fspcomm_s *c, double *buf, int n, bool is_max, cudaStream_t st
   return 0;
 }
 
-// collective; leaves c->p2p == false (NCCL path) if any rank cannot map any peer or FSP_P2P=0
+// collective; leaves c->p2p == false (NCCL path) on ALL ranks if any rank cannot map any peer, cannot set up its
+// error flag, or FSP_P2P=0.  Returns -1 only when a collective call itself failed.
 int p2p_setup(fspcomm_s *c) {
   const char *env = getenv("FSP_P2P");
-  int want = (env && !strcmp(env, "0")) ? 0 : 1;
-  if (c->size > kMaxRanks) want = 0;
-  int ok = want;
-  if (want) {
-    if (window_create(c, sizeof(CtrlLayout), &c->ctrl)) ok = 0;
+  bool want = !(env && !strcmp(env, "0")) && c->size <= kMaxRanks;
+  // every rank must want it (the environment could differ between ranks)
+  int agreed = agree(c, want);
+  if (agreed < 0) return -1;
+  c->p2p = false;
+  if (agreed != 0) return 0;
+  if (window_create(c, sizeof(CtrlLayout), &c->ctrl)) return 0;  // consistent on all ranks
+  bool ok = cudaHostAlloc((void **) &c->err_host, 2 * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess;
+  if (ok) {
+    const char *tmo = getenv("FSP_SPIN_TIMEOUT_MS");  // device-side flag waits give up after this long (default 20 s)
+    c->err_host[0] = 0u;
+    c->err_host[1] = tmo ? (unsigned) atoi(tmo) : 0u;
+    ok = cudaHostGetDevicePointer((void **) &c->err_dev, c->err_host, 0) == cudaSuccess;
+  } else {
+    c->err_host = nullptr;
   }
-  // agree: minimum over ranks
-  double *d = nullptr;
-  if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
-  double v = ok ? 0.0 : 1.0;
-  cudaMemcpy(d, &v, 8, cudaMemcpyHostToDevice);
-  int r = g_nccl.AllReduce(d, d, 1, ncclFloat64, ncclSum, c->comm, (cudaStream_t) 0);
-  cudaMemcpy(&v, d, 8, cudaMemcpyDeviceToHost);
-  cudaFree(d);
-  if (r != ncclSuccess || v != 0.0) {
-    if (c->ctrl.local) window_destroy(c, &c->ctrl);
-    c->p2p = false;
-    return 0;
+  cudaGetLastError();
+  agreed = agree(c, ok);
+  if (agreed != 0) {
+    window_destroy(c, &c->ctrl);
+    if (c->err_host) cudaFreeHost(c->err_host);
+    c->err_host = nullptr; c->err_dev = nullptr;
+    return agreed < 0 ? -1 : 0;
   }
-  if (cudaHostAlloc((void **) &c->err_host, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess) { window_destroy(c, &c->ctrl); return 0; }
-  *c->err_host = 0u;
-  if (cudaHostGetDevicePointer((void **) &c->err_dev, c->err_host, 0) != cudaSuccess) { window_destroy(c, &c->ctrl); return 0; }
   c->p2p = true;
   return 0;
 }
@@ -293,7 +327,11 @@ int fspcomm_create(fspcomm_t *out, const char id[FSPCOMM_ID_BYTES], int rank, in
     memcpy(uid.internal, id, FSPCOMM_ID_BYTES);
     int r = g_nccl.CommInitRank(&c->comm, size, uid, rank);
     if (r != ncclSuccess) { set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); delete c; return -1; }
-    p2p_setup(c);  // peer-memory fast path when every rank can map every peer; NCCL path otherwise
+    // staging buffer of the set-up collectives; if even this fails the device is unusable (the peers cannot be told
+    // through NCCL without device memory): fatal
+    if (cudaMalloc(&c->stage, kStageBytes) != cudaSuccess) { set_error("fspcomm_create: cannot allocate the staging buffer"); g_nccl.CommDestroy(c->comm); delete c; return -1; }
+    // peer-memory fast path when every rank can map every peer; NCCL path otherwise
+    if (p2p_setup(c)) { set_error("fspcomm_create: the peer-memory set-up collective failed"); cudaFree(c->stage); g_nccl.CommDestroy(c->comm); delete c; return -1; }
   }
   *out = c;
   return 0;
@@ -317,6 +355,7 @@ int fspcomm_destroy(fspcomm_t c) {
     if (c->err_host) cudaFreeHost(c->err_host);
     c->p2p = false;
   }
+  if (c->stage) cudaFree(c->stage);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   delete c;
   return 0;
@@ -382,21 +421,28 @@ int fspcomm_halo_exchange(fspcomm_t c, const double *send, const long *send_coun
 
 int fspcomm_alltoall_counts(fspcomm_t c, const long *send_host, long *recv_host, void *stream) {
   if (!c || c->size == 1) { recv_host[0] = send_host[0]; return 0; }
-  const int    P = c->size;
+  const int P = c->size;
+  if (P > 256) { set_error("fspcomm_alltoall_counts: too many ranks"); return -1; }
+  static_assert(sizeof(long) == 8, "counts travel as int64");
   cudaStream_t st = resolve_stream(stream);
-  double      *d_send = nullptr, *d_all = nullptr;
-  FSP_CUDA_CHECK(pmalloc(&d_send, sizeof(double) * P));
-  FSP_CUDA_CHECK(pmalloc(&d_all, sizeof(double) * P * P));
-  double hs[256], hall[256 * 8];
-  if (P > 256 || P * P > 2048) { set_error("fspcomm_alltoall_counts: too many ranks"); return -1; }
-  for (int p = 0; p < P; ++p) hs[p] = (double) send_host[p];
-  FSP_CUDA_CHECK(cudaMemcpyAsync(d_send, hs, sizeof(double) * P, cudaMemcpyHostToDevice, st));
-  FSP_NCCL_CHECK(g_nccl.AllGather(d_send, d_all, (size_t) P, ncclFloat64, c->comm, st));
-  FSP_CUDA_CHECK(cudaMemcpyAsync(hall, d_all, sizeof(double) * P * P, cudaMemcpyDeviceToHost, st));
-  FSP_CUDA_CHECK(cudaStreamSynchronize(st));
-  for (int p = 0; p < P; ++p) recv_host[p] = (long) hall[p * P + c->rank];
+  long        *d_send = nullptr, *d_all = nullptr;
+  int          rc = -1;
+  std::vector<long> hall((size_t) P * P);
+  do {
+    if (pmalloc(&d_send, sizeof(long) * P) != cudaSuccess || pmalloc(&d_all, sizeof(long) * P * P) != cudaSuccess) {
+      set_error("fspcomm_alltoall_counts: allocation failed");
+      break;
+    }
+    if (cudaMemcpyAsync(d_send, send_host, sizeof(long) * P, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+    if (g_nccl.AllGather(d_send, d_all, (size_t) P, ncclInt64, c->comm, st) != ncclSuccess) { set_error("fspcomm_alltoall_counts: ncclAllGather failed"); break; }
+    if (cudaMemcpyAsync(hall.data(), d_all, sizeof(long) * P * P, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+    if (cudaStreamSynchronize(st) != cudaSuccess) break;
+    for (int p = 0; p < P; ++p) recv_host[p] = hall[(size_t) p * P + c->rank];
+    rc = 0;
+  } while (0);
+  if (rc) cudaGetLastError();
   pfree(d_send); pfree(d_all);
-  return 0;
+  return rc;
 }
 
 int fspcomm_exchange_int(fspcomm_t c, const int *send, const long *send_counts, int *recv, const long *recv_counts,
@@ -432,34 +478,44 @@ int fsphalo_create(fspcomm_t c, fsphalo_t *out, const int *send_idx_dev, const l
   }
   h->n_send = h->send_off[c->size];
   h->n_ghost = recv_off[c->size];
+  // Collective from here on: a rank-local failure is carried in `ok` through every collective call and agreed on before
+  // the pool (which must stay identical on all ranks) is touched, so either every rank gets a halo or none does.
   // every peer learns where its segment starts in my ghost buffer
-  if (fspcomm_alltoall_counts(c, recv_off, h->remote_off, nullptr)) { delete h; return -1; }
+  bool ok = fspcomm_alltoall_counts(c, recv_off, h->remote_off, nullptr) == 0;
   // window capacity: the maximum ghost count over ranks (all ranks must take the same pool decision)
-  double *d = nullptr;
-  FSP_CUDA_CHECK(cudaMalloc(&d, 8));
   double need = (double) h->n_ghost;
-  FSP_CUDA_CHECK(cudaMemcpy(d, &need, 8, cudaMemcpyHostToDevice));
-  FSP_NCCL_CHECK(g_nccl.AllReduce(d, d, 1, ncclFloat64, ncclMax, c->comm, (cudaStream_t) 0));
-  FSP_CUDA_CHECK(cudaMemcpy(&need, d, 8, cudaMemcpyDeviceToHost));
-  cudaFree(d);
-  const size_t cap_need = (size_t) need;
-  bool found = false;
-  for (size_t q = 0; q < c->halo_pool.size(); ++q) {
-    if (c->halo_pool[q].cap >= cap_need) {
-      h->w = c->halo_pool[q];
-      c->halo_pool.erase(c->halo_pool.begin() + (long) q);
-      found = true;
-      break;
+  ok = (cudaMemcpy(c->stage, &need, 8, cudaMemcpyHostToDevice) == cudaSuccess) && ok;
+  const bool coll_ok = g_nccl.AllReduce(c->stage, c->stage, 1, ncclFloat64, ncclMax, c->comm, (cudaStream_t) 0) == ncclSuccess;
+  ok = ok && coll_ok && cudaMemcpy(&need, c->stage, 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  ok = (cudaMalloc(&h->block_counter, sizeof(unsigned)) == cudaSuccess) && ok;
+  if (h->block_counter) ok = (cudaMemset(h->block_counter, 0, sizeof(unsigned)) == cudaSuccess) && ok;
+  cudaGetLastError();
+  int agreed = coll_ok ? agree(c, ok) : -1;
+  if (agreed == 0) {
+    const size_t cap_need = (size_t) need;
+    bool found = false;
+    for (size_t q = 0; q < c->halo_pool.size(); ++q) {
+      if (c->halo_pool[q].cap >= cap_need) {
+        h->w = c->halo_pool[q];
+        c->halo_pool.erase(c->halo_pool.begin() + (long) q);
+        found = true;
+        break;
+      }
+    }
+    if (!found) {
+      size_t cap = ((cap_need + cap_need / 4 + 1024) + 31) / 32 * 32;
+      // consistent on all ranks (window_create agrees internally); the pool is untouched when it fails
+      if (window_create(c, sizeof(HaloHeader) + 2 * cap * sizeof(double), &h->w.win)) agreed = 1;
+      h->w.cap = cap;
+      h->w.epoch = 0;
     }
   }
-  if (!found) {
-    size_t cap = ((cap_need + cap_need / 4 + 1024) + 31) / 32 * 32;
-    if (window_create(c, sizeof(HaloHeader) + 2 * cap * sizeof(double), &h->w.win)) { delete h; return -1; }
-    h->w.cap = cap;
-    h->w.epoch = 0;
+  if (agreed != 0) {
+    if (ok) set_error("fsphalo_create: set-up failed on a rank of the communicator");
+    if (h->block_counter) cudaFree(h->block_counter);
+    delete h;
+    return -1;
   }
-  FSP_CUDA_CHECK(cudaMalloc(&h->block_counter, sizeof(unsigned)));
-  FSP_CUDA_CHECK(cudaMemset(h->block_counter, 0, sizeof(unsigned)));
   *out = h;
   return 0;
 }

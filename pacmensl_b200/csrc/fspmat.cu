@@ -460,20 +460,23 @@ __global__ void __launch_bounds__(kThreads) fsp_action_boundary_p2p_kernel(MatVi
                                                                            const double *__restrict__ x,
                                                                            const double *ghost, double *__restrict__ y) {
   if ((int) blockIdx.x >= m.main_blocks) {
-    if ((int) threadIdx.x < w.n_ranks) wait_flag(w.sink_flags + threadIdx.x, w.epoch, w.err);
-    __syncthreads();
+    bool ok = true;
+    if ((int) threadIdx.x < w.n_ranks) ok = wait_flag(w.sink_flags + threadIdx.x, w.epoch, w.err);
+    ok = __syncthreads_and(ok);
     if ((int) threadIdx.x < m.K) {
       double s = 0.0;
       for (int p = 0; p < w.n_ranks; ++p) s += __ldcg(w.sink_slots + (size_t) p * FSP_P2P_MAX_SINKS + threadIdx.x);
-      y[m.n_rows_main + threadIdx.x] = s;
+      y[m.n_rows_main + threadIdx.x] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);  // time-out: poison
     }
     return;
   }
-  if ((int) threadIdx.x < w.n_ranks && (int) threadIdx.x != w.rank) wait_flag(w.halo_flags + threadIdx.x, w.epoch, w.err);
-  __syncthreads();
+  bool ok = true;
+  if ((int) threadIdx.x < w.n_ranks && (int) threadIdx.x != w.rank) ok = wait_flag(w.halo_flags + threadIdx.x, w.epoch, w.err);
+  ok = __syncthreads_and(ok);
   const long q = (long) blockIdx.x * kThreads + threadIdx.x;
   if (q >= m.n) return;
   const long   i = (long) m.row_list[q];
+  if (!ok) { y[i] = __longlong_as_double(0x7ff8000000000000ll); return; }  // time-out: poison the rows that need the halo
   const double xi = __ldg(x + i);
   double       d = 0.0;
   for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], ld_stream(m.diag + g * m.ld + i), d);
@@ -497,19 +500,25 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_p2p_kernel(MatView m, 
                                                                      const double *__restrict__ x, const double *ghost,
                                                                      double *__restrict__ y) {
   if ((int) blockIdx.x >= m.main_blocks) {
-    if ((int) threadIdx.x < w.n_ranks) wait_flag(w.sink_flags + threadIdx.x, w.epoch, w.err);
-    __syncthreads();
+    bool ok = true;
+    if ((int) threadIdx.x < w.n_ranks) ok = wait_flag(w.sink_flags + threadIdx.x, w.epoch, w.err);
+    ok = __syncthreads_and(ok);
     if ((int) threadIdx.x < m.K) {
       double s = 0.0;
       for (int p = 0; p < w.n_ranks; ++p) s += __ldcg(w.sink_slots + (size_t) p * FSP_P2P_MAX_SINKS + threadIdx.x);
-      y[m.n_rows_main + threadIdx.x] = s;
+      y[m.n_rows_main + threadIdx.x] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);  // time-out: poison
     }
     return;
   }
   const int cta = m.cta_order[blockIdx.x];
   if ((int) blockIdx.x >= m.n_interior_ctas) {
-    if ((int) threadIdx.x < w.n_ranks && (int) threadIdx.x != w.rank) wait_flag(w.halo_flags + threadIdx.x, w.epoch, w.err);
-    __syncthreads();
+    bool ok = true;
+    if ((int) threadIdx.x < w.n_ranks && (int) threadIdx.x != w.rank) ok = wait_flag(w.halo_flags + threadIdx.x, w.epoch, w.err);
+    if (!__syncthreads_and(ok)) {  // time-out: poison the rows that need the halo
+      const int j = cta * kThreads + (int) threadIdx.x;
+      if (j < m.n) y[j] = __longlong_as_double(0x7ff8000000000000ll);
+      return;
+    }
   }
   const int i = cta * kThreads + (int) threadIdx.x;
   if (i >= m.n) return;
@@ -555,6 +564,8 @@ struct HaloView {
   unsigned long long       *sink_flag_remote;
   unsigned int             *err;
   int                       finish_sinks;   // this rank owns y[n..n+K)
+  int                       n_push;         // leading push CTAs of this launch (0: the push is not part of it)
+  const double             *push_src;       // null: the push CTAs gather x[send_idx[q]]; else they read this packed buffer
   int                       rot;            // row CTA b handles the rows of CTA (b + rot) mod n
   int                       n_fast;         // the first n_fast row CTAs (in that order) hold no ghost column
 };
@@ -564,8 +575,8 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_halo_kernel(MatView m,
                                                                       const double *__restrict__ x,
                                                                       double *__restrict__ y) {
   int b = (int) blockIdx.x;
-  if (b < hv.push.n_ctas) { push_role(hv.push, x, b); return; }
-  b -= hv.push.n_ctas;
+  if (b < hv.n_push) { push_role(hv.push, hv.push_src ? hv.push_src : x, b); return; }
+  b -= hv.n_push;
   if (b < m.sink_blocks) {
     // partial sink sums of this rank; the last-arriving CTA stores the K sums into the owner's slots and signals
     __shared__ double smem[32];
@@ -614,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 8) fsp_action_halo_kernel(MatView m,
   }
   int cta = b + hv.rot;
   if (cta >= m.main_blocks) cta -= m.main_blocks;
-  const int i = cta * kThreads + (int) threadIdx.x;
+  const int i = m.row0 + cta * kThreads + (int) threadIdx.x;
   if (b < hv.n_fast) {
     // ghost-free CTAs (by construction of rot / n_fast at generate time): exactly the single-GPU row code
     if (i < m.n) y[i] = lean_row<P, 0>(m, cf, x, nullptr, 0.0, i);
@@ -778,6 +789,10 @@ __global__ void chunk_max_col_kernel(int n, int P, long ld, const int *__restric
   } else if (i < n) {
     atomicMax(chunk_max + (int) (i / chunk_rows), mx);
   }
+}
+__global__ void mark_chunk_kernel(const int *__restrict__ rows, long n_rows, long chunk_rows, int *__restrict__ flag) {
+  long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_rows) flag[rows[q] / chunk_rows] = 1;
 }
 struct RowHasGhost {
   const int *col; long ld; int P;
@@ -1177,6 +1192,21 @@ int fspmat_chunk_max_columns(fspmat_t h, long chunk_rows, int n_chunks, int *chu
   return 0;
 }
 
+// chunk_flag_host[c] = 1 when rows [c*chunk_rows, (c+1)*chunk_rows) contain a row that references a ghost entry
+int fspmat_chunk_has_ghost(fspmat_t h, long chunk_rows, int n_chunks, int *chunk_flag_host) {
+  for (int c = 0; c < n_chunks; ++c) chunk_flag_host[c] = 0;
+  if (!h->has_values || h->n_boundary <= 0) return 0;
+  if (chunk_rows <= 0 || (long) n_chunks * chunk_rows < h->n) { set_error("fspmat_chunk_has_ghost: chunks do not cover the rows"); return -1; }
+  int *d = nullptr;
+  FSP_CUDA_CHECK(pmalloc(&d, sizeof(int) * n_chunks));
+  FSP_CUDA_CHECK(cudaMemsetAsync(d, 0, sizeof(int) * n_chunks, (cudaStream_t) 0));
+  mark_chunk_kernel<<<(unsigned) ((h->n_boundary + 255) / 256), 256, 0, (cudaStream_t) 0>>>(h->d_boundary_rows, h->n_boundary, chunk_rows, d);
+  FSP_LAUNCH_CHECK();
+  FSP_CUDA_CHECK(cudaMemcpy(chunk_flag_host, d, sizeof(int) * n_chunks, cudaMemcpyDeviceToHost));
+  pfree(d);
+  return 0;
+}
+
 int fspmat_fused_supported(fspmat_t h) { return (h->has_values && h->n_ghost == 0 && h->P >= 1 && h->P <= 16) ? 1 : 0; }
 
 int fspmat_action_fused(fspmat_t h, const double *coef_host, const double *x, double *y, const fspmat_epilogue *ep,
@@ -1251,27 +1281,54 @@ int fspmat_action_p2p(fspmat_t h, const double *coef_host, const double *x, doub
 
 int fspmat_halo_fused_supported(fspmat_t h) { return (h->has_values && h->P >= 1 && h->P <= 16) ? 1 : 0; }
 
-int fspmat_action_halo(fspmat_t h, const double *coef_host, const double *x, double *y, const fsphalo_epoch *e,
-                       const fsphalo_push *push, void *stream) {
+static int launch_halo(fspmat_t h, const double *coef_host, const double *x, double *y, const fsphalo_epoch *e,
+                       const fsphalo_push *push, int parts, long row_begin, long row_end, int rows_have_ghosts,
+                       const double *packed_send, cudaStream_t st) {
   if (!h->has_values) return 0;
   halo_fn fn = pick_halo(h->P);
   if (!fn) { set_error("fspmat_action_halo: supports 1..16 reactions (got %d)", h->P); return -1; }
   Coefs cf; MatView m;
   fill_coefs_view(h, coef_host, cf, m);
-  m.main_blocks = (int) (((long) h->n + kThreads - 1) / kThreads);
+  const bool whole = row_begin == 0 && row_end == h->n;
+  m.row0 = (int) row_begin;
+  m.n = (int) row_end;
+  m.main_blocks = (int) ((row_end - row_begin + kThreads - 1) / kThreads);
+  if (!(parts & 2)) m.sink_blocks = 0;
   HaloView hv;
   memcpy(&hv.push, push, sizeof(PushView));
+  hv.n_push = (parts & 1) ? hv.push.n_ctas : 0;
+  hv.push_src = packed_send;
+  if (packed_send) hv.push.send_idx = nullptr;
   hv.halo_flags = e->halo_flags; hv.sink_flags = e->sink_flags; hv.sink_slots = e->sink_slots;
   hv.ghost = e->ghost; hv.sink_slot_remote = e->sink_slot_remote; hv.sink_flag_remote = e->sink_flag_remote;
   hv.err = e->error_flag;
   hv.finish_sinks = (h->K > 0 && h->owns_sinks) ? 1 : 0;
-  hv.rot = (h->rot < m.main_blocks) ? h->rot : 0;
-  // operators without ghost columns (d_cta_order unset): every CTA is ghost-free
-  hv.n_fast = h->n_ghost > 0 ? h->n_fast : m.main_blocks;
-  const int grid = hv.push.n_ctas + m.sink_blocks + m.main_blocks + 1;
-  fn<<<grid, kThreads, 0, resolve_stream(stream)>>>(m, cf, hv, x, y);
+  if (whole) {
+    hv.rot = (h->rot < m.main_blocks) ? h->rot : 0;
+    // operators without ghost columns on this rank: every CTA is ghost-free
+    hv.n_fast = h->n_ghost > 0 ? h->n_fast : m.main_blocks;
+  } else {
+    hv.rot = 0;
+    hv.n_fast = (rows_have_ghosts && h->n_ghost > 0) ? 0 : m.main_blocks;
+  }
+  const int grid = hv.n_push + m.sink_blocks + m.main_blocks + ((parts & 4) ? 1 : 0);
+  if (grid == 0) return 0;
+  fn<<<grid, kThreads, 0, st>>>(m, cf, hv, x, y);
   FSP_LAUNCH_CHECK();
   return 0;
+}
+
+int fspmat_action_halo(fspmat_t h, const double *coef_host, const double *x, double *y, const fsphalo_epoch *e,
+                       const fsphalo_push *push, void *stream) {
+  return launch_halo(h, coef_host, x, y, e, push, 7, 0, h->n, 1, nullptr, resolve_stream(stream));
+}
+
+int fspmat_action_halo_part(fspmat_t h, const double *coef_host, const double *x, double *y, const fsphalo_epoch *e,
+                            const fsphalo_push *push, int parts, long row_begin, long row_end, int rows_have_ghosts,
+                            const double *packed_send_dev, void *stream) {
+  if (row_begin < 0 || row_end > h->n || row_begin > row_end) { set_error("fspmat_action_halo_part: bad row range"); return -1; }
+  return launch_halo(h, coef_host, x, y, e, push, parts, row_begin, row_end, rows_have_ghosts, packed_send_dev,
+                     resolve_stream(stream));
 }
 
 int fspmat_p2p_cta_counts(fspmat_t h, long *n_interior, long *n_total) {

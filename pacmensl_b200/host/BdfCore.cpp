@@ -425,6 +425,7 @@ int BdfCore::lin_solve(Vec b, Vec ewt, double ss_b, double tn, bool first_newton
     }
     hhost_.resize((size_t) lmax + 8);
     VCHK(fsp_memcpy_d2h(hhost_.data(), hd, sizeof(double) * (lmax + 6), stream_));
+    if (multi) VCHK(fspcomm_check(comm_->nccl));
     for (int i = 0; i <= l; ++i) Hes[i][l] = hhost_[i];
     const double vk_norm = std::sqrt(std::max(0.0, hhost_[lmax + 5]));
     double       new_norm = std::sqrt(std::max(0.0, hhost_[l + 1]));
@@ -792,7 +793,7 @@ int BdfCore::Step(double *t_reached, Vec yout, Vec *sout) {
     if (ns_ > 0) {
       // staggered-1: re-evaluate f at the converged y, then correct each sensitivity in turn
       int r = rhs(tn_, y_, ftemp_);
-      if (r != 0) { nflag = r < 0 ? BDF_RHS_FAIL : CONV_FAIL; }
+      if (r != 0) { nflag = r < 0 ? (int) BDF_RHS_FAIL : (int) CONV_FAIL; }
       else {
         nflag = BDF_SUCCESS;
         for (int is = 0; is < ns_; ++is) {

@@ -46,6 +46,8 @@ FspMatrixBase::~FspMatrixBase() {
   if (dmat_) fspmat_destroy(dmat_);
   dmat_ = nullptr;
   FreePinned_();
+  if (pin_send_) fsp_free_host(pin_send_);
+  pin_send_ = nullptr;
   for (void *e : ev_up_) fsp_event_destroy(e);
   for (void *e : ev_cmp_) fsp_event_destroy(e);
   for (void *s : {up_stream_, down_stream_, host_compute_stream_}) if (s) { fsp_stream_sync(s); fsp_stream_destroy(s); }
@@ -61,6 +63,8 @@ int FspMatrixBase::Destroy() {
   if (dmat_) fspmat_clear(dmat_);
   if (halo_) { fsphalo_destroy(halo_); halo_ = nullptr; }
   host_chunk_need_.clear();
+  host_chunk_ghost_.clear();
+  send_idx_host_.clear();
   host_chunk_rows_ = 0;
   ghost_buf_.release();
   send_buf_.release();
@@ -573,8 +577,12 @@ PacmenslErrorCode FspMatrixBase::ActionHost(PetscReal t, const double *x_host, d
   const long n = num_rows_local_, ns = num_states_local_;
   if (hx_.resize((size_t) std::max<long>(n, 1)) || hy_.resize((size_t) std::max<long>(n, 1))) PACMENSLCHKERRQ(-1);
   static const int n_chunks_env = [] { const char *e = std::getenv("FSP_HOST_CHUNKS"); return e ? std::atoi(e) : 32; }();
-  const bool pipelined = has_values_ == PETSC_TRUE && comm_size_ == 1 && n_chunks_env > 1 && ns >= 64L * 256 * n_chunks_env &&
-                         (int) (tv_reactions_.size() + ti_reactions_.size()) <= 16;
+  // every rank of a multi-GPU job must take the same path (the peer-memory pipeline is collective): decide on the
+  // GLOBAL size there
+  const long size_key = comm_size_ == 1 ? ns : (long) num_rows_global_ / comm_size_;
+  const bool pipelined = has_values_ == PETSC_TRUE && n_chunks_env > 1 && size_key >= 64L * 256 * n_chunks_env &&
+                         (int) (tv_reactions_.size() + ti_reactions_.size()) <= 16 &&
+                         (comm_size_ == 1 || (halo_ != nullptr && fspmat_halo_fused_supported(dmat_)));
   if (!pipelined) {
     FSPCHKERRQ(fsp_memcpy_h2d(hx_.get(), x_host, sizeof(double) * n, nullptr));
     _p_Vec x, y;
@@ -597,6 +605,7 @@ PacmenslErrorCode FspMatrixBase::ActionHost(PetscReal t, const double *x_host, d
   const long chunk = ((ns + C - 1) / C + 255) / 256 * 256;
   if (host_chunk_need_.empty() || host_chunk_rows_ != chunk) {
     host_chunk_need_.assign((size_t) C, -1);
+    host_chunk_ghost_.clear();
     FSPCHKERRQ(fspmat_chunk_max_columns(dmat_, chunk, C, host_chunk_need_.data()));
     host_chunk_rows_ = chunk;
   }
@@ -608,6 +617,7 @@ PacmenslErrorCode FspMatrixBase::ActionHost(PetscReal t, const double *x_host, d
   while ((int) ev_up_.size() < C + 1) { void *e = nullptr; FSPCHKERRQ(fsp_event_create(&e)); ev_up_.push_back(e); }
   while ((int) ev_cmp_.size() < C + 1) { void *e = nullptr; FSPCHKERRQ(fsp_event_create(&e)); ev_cmp_.push_back(e); }
   const double *coefs = time_coefficients_.memptr();
+  if (comm_size_ > 1) return ActionHostPartitioned_(coefs, x_host, y_host, C, chunk);
   // stage 1: all uploads, in order (chunk k of x, the sink entries ride with the last chunk)
   for (int k = 0; k < C; ++k) {
     const long b = std::min<long>(ns, (long) k * chunk), e = (k == C - 1) ? n : std::min<long>(ns, (long) (k + 1) * chunk);
@@ -636,6 +646,72 @@ PacmenslErrorCode FspMatrixBase::ActionHost(PetscReal t, const double *x_host, d
   FSPCHKERRQ(fsp_stream_sync(down_stream_));
   FSPCHKERRQ(fsp_stream_sync(host_compute_stream_));
   FSPCHKERRQ(fsp_stream_sync(up_stream_));
+  return 0;
+}
+
+// The same pipeline on every rank of a multi-GPU job (each rank has its own PCIe link).  Per rank:
+//   1. the boundary entries of x that the peers need are packed on the HOST (x_host[send_idx]), uploaded first, and
+//      pushed into the peers' ghost windows by the push CTAs (fspmat_action_halo_part, bit 0) -- the halo is in
+//      flight while the bulk of x is still crossing PCIe;
+//   2. x goes up in chunks; a chunk of rows without ghost columns runs as soon as the prefix of x it references has
+//      arrived, its part of y goes down behind it; chunks WITH ghost columns run last (their CTAs wait for the peers'
+//      flags in device code);
+//   3. sink partial sums + the finishing CTA (pacing; on the sink owner the K sums) close the Action.
+// Bit-identical to the device-vector Action (same row code, every row computed once).
+PacmenslErrorCode FspMatrixBase::ActionHostPartitioned_(const double *coefs, const double *x_host, double *y_host, int C, long chunk) {
+  const long n = num_rows_local_, ns = num_states_local_;
+  if (host_chunk_ghost_.empty() || (long) host_chunk_ghost_.size() != C) {
+    host_chunk_ghost_.assign((size_t) C, 0);
+    FSPCHKERRQ(fspmat_chunk_has_ghost(dmat_, chunk, C, host_chunk_ghost_.data()));
+  }
+  if (n_send_ > 0 && send_idx_host_.empty()) {
+    send_idx_host_.resize((size_t) n_send_);
+    FSPCHKERRQ(fsp_memcpy_d2h(send_idx_host_.data(), send_idx_.get(), sizeof(int) * n_send_, nullptr));
+  }
+  if (n_send_ > 0 && (!pin_send_ || pin_send_cap_ < n_send_)) {
+    if (pin_send_) fsp_free_host(pin_send_);
+    FSPCHKERRQ(fsp_malloc_host((void **) &pin_send_, sizeof(double) * (size_t) n_send_));
+    pin_send_cap_ = n_send_;
+  }
+  fsphalo_epoch ep;
+  fsphalo_push  push;
+  FSPCHKERRQ(fsphalo_next(halo_, &ep, &push));
+  // 1. pack on the host, upload, push
+  for (long q = 0; q < n_send_; ++q) pin_send_[q] = x_host[send_idx_host_[(size_t) q]];
+  if (n_send_ > 0) FSPCHKERRQ(fsp_memcpy_h2d_async(send_buf_.get(), pin_send_, sizeof(double) * n_send_, up_stream_));
+  FSPCHKERRQ(fspmat_action_halo_part(dmat_, coefs, hx_.get(), hy_.get(), &ep, &push, 1, 0, 0, 0, send_buf_.get(), up_stream_));
+  // 2. uploads in order (the sink entries of x ride with the last chunk)
+  for (int k = 0; k < C; ++k) {
+    const long b = std::min<long>(ns, (long) k * chunk), e = (k == C - 1) ? n : std::min<long>(ns, (long) (k + 1) * chunk);
+    if (e > b) FSPCHKERRQ(fsp_memcpy_h2d_async(hx_.get() + b, x_host + b, sizeof(double) * (e - b), up_stream_));
+    FSPCHKERRQ(fsp_event_record(ev_up_[k], up_stream_));
+  }
+  for (int pass = 0; pass < 2; ++pass) {  // ghost-free chunks first, chunks that wait for the peers last
+    for (int c = 0; c < C; ++c) {
+      if ((host_chunk_ghost_[c] != 0) != (pass == 1)) continue;
+      const long b = std::min<long>(ns, (long) c * chunk), e = std::min<long>(ns, (long) (c + 1) * chunk);
+      if (e <= b) continue;
+      const long need = std::max<long>(host_chunk_need_[c], e - 1);
+      const int  k_need = (int) std::min<long>(C - 1, need / chunk);
+      FSPCHKERRQ(fsp_stream_wait_event(host_compute_stream_, ev_up_[k_need]));
+      FSPCHKERRQ(fspmat_action_halo_part(dmat_, coefs, hx_.get(), hy_.get(), &ep, &push, 0, b, e, pass, nullptr, host_compute_stream_));
+      FSPCHKERRQ(fsp_event_record(ev_cmp_[c], host_compute_stream_));
+      FSPCHKERRQ(fsp_stream_wait_event(down_stream_, ev_cmp_[c]));
+      FSPCHKERRQ(fsp_memcpy_d2h_async(y_host + b, hy_.get() + b, sizeof(double) * (e - b), down_stream_));
+    }
+  }
+  // 3. sinks + finish (needs all of x; every rank runs the finishing CTA: it paces the ghost-buffer reuse)
+  FSPCHKERRQ(fsp_stream_wait_event(host_compute_stream_, ev_up_[C - 1]));
+  FSPCHKERRQ(fspmat_action_halo_part(dmat_, coefs, hx_.get(), hy_.get(), &ep, &push, 2 | 4, 0, 0, 0, nullptr, host_compute_stream_));
+  if (n > ns) {
+    FSPCHKERRQ(fsp_event_record(ev_cmp_[C], host_compute_stream_));
+    FSPCHKERRQ(fsp_stream_wait_event(down_stream_, ev_cmp_[C]));
+    FSPCHKERRQ(fsp_memcpy_d2h_async(y_host + ns, hy_.get() + ns, sizeof(double) * (n - ns), down_stream_));
+  }
+  FSPCHKERRQ(fsp_stream_sync(down_stream_));
+  FSPCHKERRQ(fsp_stream_sync(host_compute_stream_));
+  FSPCHKERRQ(fsp_stream_sync(up_stream_));
+  FSPCHKERRQ(fsphalo_check(halo_));
   return 0;
 }
 

@@ -96,7 +96,9 @@ class PACMENSL_API FspMatrixBase {
   std::vector<int>     cache_enabled_;
   // host-vector pipeline (ActionHost)
   DeviceBuffer<double> hx_, hy_;
-  std::vector<int>     host_chunk_need_;
+  std::vector<int>     host_chunk_need_, host_chunk_ghost_, send_idx_host_;
+  double              *pin_send_ = nullptr;
+  long                 pin_send_cap_ = 0;
   long                 host_chunk_rows_ = 0;
   void                *up_stream_ = nullptr, *down_stream_ = nullptr, *host_compute_stream_ = nullptr;
   std::vector<void *>  ev_up_, ev_cmp_;
@@ -107,6 +109,7 @@ class PACMENSL_API FspMatrixBase {
   void   *copy_stream_ = nullptr;
   int     pin_species_ = 0, pin_R_ = 0;
   long    pin_super_ = 0;
+  PacmenslErrorCode ActionHostPartitioned_(const double *coefs, const double *x_host, double *y_host, int n_chunks, long chunk_rows);
   int  EvaluatePropensitiesHost_(fspset_t dset, int n_species, long first, long count, const PropFun &prop_x, void *prop_x_args);
   void FreePinned_();
 

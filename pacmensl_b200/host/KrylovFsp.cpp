@@ -369,6 +369,7 @@ int KrylovFsp::GenerateBasis(const Vec &v, int m_start, PetscBool *happy_breakdo
   const int ncols = m_ - m_start;
   hhost_.resize((size_t) ncols * stride);
   FSPCHKERRQ(fsp_memcpy_d2h(hhost_.data(), hdev_.get() + (size_t) m_start * stride, sizeof(double) * ncols * stride, stream));
+  if (comm_ && comm_->nccl) FSPCHKERRQ(fspcomm_check(comm_->nccl));  // a timed-out peer wait poisoned the Hessenberg entries
   for (int j = m_start; j < m_; ++j) {
     const double *hcol = hhost_.data() + (size_t) (j - m_start) * stride;
     int           is = (q_iop > 0) ? ((j - q_iop + 1 >= 0) ? j - q_iop + 1 : 0) : 0;

@@ -178,6 +178,7 @@ int SensFspSolverMultiSinks::CheckFspTolerance_(PetscReal t, Vec p) {
     const PetscReal *p_dev;
     VecGetDeviceArrayRead(p, &p_dev);
     int ierr = fsp_memcpy_d2h(sinks_of_p.memptr(), p_dev + (n_loc - K), sizeof(double) * K, comm_->stream);
+    if (!ierr && comm_->nccl) ierr = fspcomm_check(comm_->nccl);
     PACMENSLCHKERRTHROW(ierr);
   }
   for (int i = 0; i < K; ++i) sinks_[i] = sinks_of_p[i];

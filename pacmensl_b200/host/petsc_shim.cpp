@@ -55,7 +55,9 @@ static int host_allreduce(MPI_Comm comm, double *v, int n, bool is_max) {
   ierr = is_max ? fspcomm_allreduce_max(comm->nccl, g_scratch_dev, n, comm->stream)
                 : fspcomm_allreduce_sum(comm->nccl, g_scratch_dev, n, comm->stream);
   if (ierr) return ierr;
-  return fsp_memcpy_d2h(v, g_scratch_dev, sizeof(double) * n, comm->stream);
+  ierr = fsp_memcpy_d2h(v, g_scratch_dev, sizeof(double) * n, comm->stream);
+  // a device-side flag wait that timed out poisoned the result: report it where the host consumes it
+  return ierr ? ierr : fspcomm_check(comm->nccl);
 }
 int pacmensl_allreduce_sum(MPI_Comm comm, double *v, int n) { return host_allreduce(comm, v, n, false); }
 int pacmensl_allreduce_max(MPI_Comm comm, double *v, int n) { return host_allreduce(comm, v, n, true); }
@@ -340,6 +342,7 @@ PetscErrorCode VecGetOwnershipRange(Vec v, PetscInt *low, PetscInt *high) {
 PetscErrorCode VecGetArray(Vec v, PetscScalar **a) {
   v->host_mirror.resize((size_t) (v->n_local > 0 ? v->n_local : 1));
   int ierr = v->n_local > 0 ? fsp_memcpy_d2h(v->host_mirror.data(), v->d_data, sizeof(double) * v->n_local, S(v)) : 0;
+  if (!ierr && v->comm && v->comm->nccl) ierr = fspcomm_check(v->comm->nccl);
   v->mirror_mode = 2;
   *a = v->host_mirror.data();
   return ierr;
@@ -355,6 +358,7 @@ PetscErrorCode VecRestoreArray(Vec v, PetscScalar **a) {
 PetscErrorCode VecGetArrayRead(Vec v, const PetscScalar **a) {
   v->host_mirror.resize((size_t) (v->n_local > 0 ? v->n_local : 1));
   int ierr = v->n_local > 0 ? fsp_memcpy_d2h(v->host_mirror.data(), v->d_data, sizeof(double) * v->n_local, S(v)) : 0;
+  if (!ierr && v->comm && v->comm->nccl) ierr = fspcomm_check(v->comm->nccl);
   v->mirror_mode = 1;
   *a = v->host_mirror.data();
   return ierr;

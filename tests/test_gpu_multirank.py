@@ -33,3 +33,14 @@ def test_cpp_programs_two_ranks(cuda, prog):
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0 and "0 failed" in r.stdout
+
+
+def test_missing_peer_is_reported_not_silently_wrong(cuda):
+    # a device-side flag wait that times out must poison the outputs and end in a non-zero return code
+    if _ngpu(cuda) < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29561", os.path.join(ROOT, "tests", "multirank_timeout_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, FSP_SPIN_TIMEOUT_MS="300"))
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "TIMEOUT CHECK OK" in r.stdout
