@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-expand", action="store_true", help="skip the Expand() closure check of the lattice set")
     ap.add_argument("--no-solve", action="store_true", help="skip the solve-to-t_f side measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra single-GPU rooflines (TV lattice, BFS-ordered example sets)")
     ap.add_argument("--solve-lattice", type=int, default=0, help="lattice edge of the GPU solve-to-t_f measurement (0 = --lattice)")
     ap.add_argument("--cpu-solve-lattice", type=int, default=128, help="lattice edge of the bounded CPU solve sample")
     return ap.parse_args()
@@ -167,6 +168,63 @@ def cpu_baseline(args, steps=None, warmup=2):
                       % ("x".join(str(d) for d in dims), n, "the GPU arm's workload" if dims == lattice_dims(args) else "bounded sample", steps),
             "ms_per_step": med * 1e3, "dims": dims, "same_config": dims == lattice_dims(args), "build_seconds": round(t_gen, 2),
             "sum_y": float(y.sum())}
+
+
+EXTRA_WORKLOADS = [
+    # (key, fixture, bounds): time-varying lattice + the BFS-ordered example sets at the sizes the example solves end with
+    ("lattice_tv", "birth_death_3d_tv", None),
+    ("hog1p_bfs_23.9M", "hog1p", [3, 36, 73, 36, 58]),
+    ("hog1p_bfs_858k", "hog1p", [3, 17, 36, 13, 22]),
+    ("repressilator_bfs_3.95M", "repressilator", [151, 146, 176]),
+    ("transcr_reg_6d_bfs_1.64M", "transcr_reg_6d", [68, 119, 2, 2, 2, 32]),
+]
+
+
+def extra_workloads(args, steps=20, warmup=3, only=None):
+    """Action() on the other operators of BASELINE's configs, one GPU: the time-varying lattice (R_tv = 3, 120 B/row)
+    and the BFS-ordered example state sets, where the x[col] gathers are irregular.  Same metric, same roofline
+    arithmetic as the headline (algorithmic bytes = fspmat_action_bytes / CUDA-event time)."""
+    import numpy as np
+    import torch
+    from pacmensl_b200 import api
+    from pacmensl_b200.lattice import Lattice
+    peak, _ = measured_peak()
+    out = {}
+    for key, name, bounds in EXTRA_WORKLOADS:
+        if only and key not in only:
+            continue
+        try:
+            t0 = time.perf_counter()
+            if name.startswith("birth_death_3d"):
+                lat = Lattice([d - 1 for d in lattice_dims(args)], tv=name.endswith("_tv"), expand=False)
+                st, mat = lat.set, lat.mat
+            else:
+                st, mat = api.fixture_set_and_matrix(name, bounds=np.asarray(bounds, dtype=np.int32))
+            torch.cuda.synchronize()
+            t_build = time.perf_counter() - t0
+            n_rows, flops, nbytes = mat.info()
+            x = torch.rand(n_rows, dtype=torch.float64, device="cuda")
+            x /= x.sum()
+            y = torch.empty_like(x)
+            for _ in range(warmup):
+                assert mat.action(25.0, x, y) == 0
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(steps):
+                mat.action(25.0, x, y)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1) / steps
+            P = st.R
+            out[key] = {"states": st.n_global, "reactions": P, "bytes_per_row": round(nbytes / max(st.n_global, 1), 1),
+                        "ms_per_action": ms, "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                        "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "build_seconds": round(t_build, 2), "sum_y": float(y.sum())}
+            del mat, st, x, y
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"unavailable": repr(e)[:200]}
+    return out
 
 
 def solve_to_tf(args, rank, world, local_rank, port_base):
@@ -434,6 +492,9 @@ def main():
     if dist is not None:
         dist.barrier()
     del lat, x, y
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_extra:
+        line["roofline_other_operators"] = extra_workloads(args, steps=min(args.steps, 50))
     api.finalize()
     port_base = int(os.environ.get("MASTER_PORT", "29500")) + 101
     if dist is not None:
