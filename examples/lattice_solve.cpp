@@ -58,7 +58,9 @@ int main(int argc, char *argv[]) {
   auto AV = [&](PetscReal t, Vec x, Vec y) { return A.Action(t, x, y); };
   auto AVF = [&](PetscReal t, Vec x, Vec y, const fspmat_epilogue &ep) { return A.ActionFused(t, x, y, ep); };
   bool fused = true;
+  int  verbose = 0;
   for (int i = 1; i < argc; ++i) if (!std::strcmp(argv[i], "--no-fused")) fused = false;
+  for (int i = 1; i < argc; ++i) if (!std::strcmp(argv[i], "--verbose")) verbose = 1;
   double wall_best = 1e300, setup_best = 1e300, psum = 0.0, l1err = -1.0;
   long   nrhs = 0;
   int    stat = 0;
@@ -78,7 +80,7 @@ int main(int argc, char *argv[]) {
       CvodeFsp ode(PETSC_COMM_WORLD, CV_BDF);
       ode.SetFinalTime(t_final); ode.SetInitialSolution(&P); ode.SetRhs(AV); ode.SetTolerances(rtol, atol);
       if (fused) ode.SetFusedRhs(AVF);
-      ode.SetStatusOutput(0);
+      ode.SetStatusOutput(verbose);
       if (ode.SetUp()) return 1;
       fsp_device_sync();
       t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
@@ -90,7 +92,7 @@ int main(int argc, char *argv[]) {
       ode.SetFinalTime(t_final); ode.SetInitialSolution(&P); ode.SetRhs(AV); ode.SetFspMatPtr(&A);
       if (fused) ode.SetFusedRhs(AVF);
       ode.SetTolerances(rtol, atol);
-      ode.SetStatusOutput(0);
+      ode.SetStatusOutput(verbose);
       if (ode.SetUp()) return 1;
       fsp_device_sync();
       t_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();

@@ -818,6 +818,17 @@ ORC_API int orc_mat_generate_fixture(orc_mat *A, const orc_set *st, const char *
   return orc_mat_generate(A, st, f.num_tv, f.tv_reactions, f.prop_t, f.prop_x, 0, NULL, NULL, NULL);
 }
 
+/* parameters of a named workload (inputs, not algorithm): S, R, K, bounds[K], expansion[K], x0[S], t_final, fsp_tol, rtol, atol */
+ORC_API int orc_fixture_info(const char *name, int *dims, int *bounds, double *expansion, int *x0, double *params) {
+  fsp_fixture f;
+  if (fsp_fixture_get(name, &f)) return -1;
+  dims[0] = f.num_species; dims[1] = f.num_reactions; dims[2] = f.num_constr; dims[3] = f.num_tv;
+  for (int k = 0; k < f.num_constr; ++k) { bounds[k] = f.bounds[k]; expansion[k] = f.expansion[k]; }
+  for (int s = 0; s < f.num_species; ++s) x0[s] = f.x0[s];
+  params[0] = f.t_final; params[1] = f.fsp_tol; params[2] = f.rtol; params[3] = f.atol;
+  return 0;
+}
+
 ORC_API int orc_fixture_tcoef(const char *name, double t, double *out) {
   fsp_fixture f;
   if (fsp_fixture_get(name, &f)) return -1;

@@ -35,6 +35,7 @@ class KrylovOracle:
         self.n = A.nrows
         self.abs_tol = abs_tol
         self.m_min, self.m_max, self.m_next = m_min, m_max, m_min   # KrylovFsp.h:50-60, SetKrylovDimRange
+        self.m = 30                                                  # KrylovFsp.h:54
         self.q_iop = q_iop
         self.delta, self.gamma, self.btol, self.max_reject = 1.2, 0.9, 1.0e-14, 10000
         self.robust = robust
@@ -46,6 +47,7 @@ class KrylovOracle:
         self.num_rhs = 0
         self.num_steps = 0
         self.t_step_next = 0.0
+        self.trace = []   # (t_now, t_step, m, rejects, err_loc) per accepted step
 
     # -- helpers ------------------------------------------------------------------------------------------------
     def _ensure(self, count):
@@ -105,7 +107,8 @@ class KrylovOracle:
         ireject, m_start, kappa = 0, 0, 2.0
         m_old, t_step_old, omega, omega_old = 0, 0.0, 0.0, 0.0
         bsize_changed = False
-        self.m = min(self.m_max, max(self.m_min, self.m_next))
+        # KrylovFsp.cpp:119 precedes :122: `order` is seeded with the dimension of the PREVIOUS step (the header's initial
+        # m_ = 30, KrylovFsp.h:54, on the very first one), not with the dimension this step is about to use
         order = self.m / 4.0
         err_loc = 0.0
         while True:
@@ -179,7 +182,16 @@ class KrylovOracle:
         F0 = np.ascontiguousarray(self.beta * F[:mx, 0])
         self.L.orc_vec_maxpy(self.n, mx, _dp(F0), _dp(self.Vm), self.Vm.shape[1], _dp(v))
         self.num_steps += 1
+        self.trace.append((t_now, t_step, m, ireject, err_loc))
         return t_now + t_step
+
+    # -- KrylovFsp.cpp:364-400 (deg = 0): the solution at t inside the last step, from the stored basis ------------------
+    def get_dky(self, t, t_now, v):
+        with np.errstate(over="ignore", invalid="ignore"):
+            F = scipy.linalg.expm((t - t_now) * self.Hm)
+        mx = self.mb + max(0, self.k1 - 1)
+        F0 = np.ascontiguousarray(self.beta * F[:mx, 0])
+        self.L.orc_vec_maxpy(self.n, mx, _dp(F0), _dp(self.Vm), self.Vm.shape[1], _dp(v))
 
     # -- KrylovFsp.cpp:29-99 without a stop condition ---------------------------------------------------------------------
     def solve(self, p0, t_final, t_init=0.0):
@@ -188,3 +200,18 @@ class KrylovOracle:
         while t < t_final:
             t = self.advance_one_step(v, t, t_final)
         return v
+
+    # -- KrylovFsp.cpp:29-99 with the stop condition of the FSP driver ----------------------------------------------------
+    def solve_with_stop(self, v, t_init, t_final, stop_check):
+        """Integrates v in place from t_init; stop_check(t, v) -> error_excess.  Returns (stop, t_now): stop = 1 when
+        the check reported an excess after a step -- the reference then halves the step ten times WITHOUT re-evaluating
+        the excess (it is never updated inside that loop, :59-74), so it always ends at t_step_tmp = 0: the solution is
+        rolled back to t_now through GetDky(t_now) and t_now is not advanced."""
+        t_now = t_init
+        while t_now < t_final:
+            t_tmp = self.advance_one_step(v, t_now, t_final)
+            if stop_check is not None and stop_check(t_tmp, v) > 0.0:
+                self.get_dky(t_now, t_now, v)
+                return 1, t_now
+            t_now = t_tmp
+        return 0, t_now

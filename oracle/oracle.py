@@ -76,6 +76,7 @@ def lib():
             "orc_mat_generate_lattice": (ci, [vp, ci, ci, ci, ci]),
             "orc_set_num_threads": (None, [ci]),
             "orc_fixture_tcoef": (ci, [C.c_char_p, cd, dp]),
+            "orc_fixture_info": (ci, [C.c_char_p, ip, ip, dp, ip, dp]),
             "orc_num_threads": (ci, []),
             "orc_vec_dot": (cd, [C.c_long, dp, dp]),
             "orc_vec_axpy": (None, [C.c_long, cd, dp, dp]),
@@ -310,6 +311,18 @@ def fixture_tcoef(name, t, R):
     out = np.zeros(R, dtype=np.float64)
     ierr = lib().orc_fixture_tcoef(name.encode(), float(t), _dp(out))
     return ierr, out
+
+
+def fixture_info(name):
+    """Parameters of a named workload of pacmensl_b200/fixtures/fsp_models.h (the reference example's settings)."""
+    dims = np.zeros(4, np.int32)
+    bounds, x0 = np.zeros(16, np.int32), np.zeros(16, np.int32)
+    expansion, params = np.zeros(16), np.zeros(4)
+    if lib().orc_fixture_info(name.encode(), _ip(dims), _ip(bounds), _dp(expansion), _ip(x0), _dp(params)):
+        raise ValueError("unknown fixture " + name)
+    S, R, K, ntv = (int(v) for v in dims)
+    return dict(S=S, R=R, K=K, n_tv=ntv, bounds=bounds[:K].copy(), expansion=expansion[:K].copy(), x0=x0[:S].copy(),
+                t_final=float(params[0]), fsp_tol=float(params[1]), rtol=float(params[2]), atol=float(params[3]))
 
 
 def expand_vec(p_old, new_idx, n_new):

@@ -30,7 +30,7 @@ def _worker(rank, world, port, name, bounds, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from helpers import planes_from_oracle
     from oracle import oracle as O
-    from pacmensl_b200.partition import block_layout, fetch_x, ghost_plan
+    from partition_model import block_layout, fetch_x, ghost_plan
 
     # every rank builds the same (replicated) state directory, like the product does
     st = O.StateSet(fixture=name, bounds=bounds)
@@ -69,7 +69,7 @@ def _worker(rank, world, port, name, bounds, ret):
 
     # peer-memory form of the same exchange (fsphalo_*): every sender learns where its segment starts in the receiver's
     # ghost window (remote_off) and "stores" its values there, two parities, three epochs with changing x
-    from pacmensl_b200.partition import cta_issue_order, window_offsets
+    from partition_model import cta_issue_order, window_offsets
     recv_off = window_offsets(recv_counts)
     remote_off = torch.zeros(world, dtype=torch.int64)
     dist.all_to_all_single(remote_off, torch.from_numpy(recv_off[:world].copy()))
@@ -146,7 +146,7 @@ def test_two_rank_partitioned_action_matches_oracle(name, bounds):
 
 def test_block_layout_rule():
     sys.path.insert(0, ROOT)
-    from pacmensl_b200.partition import block_layout
+    from partition_model import block_layout
     assert block_layout(10, 4).tolist() == [0, 3, 6, 8, 10]
     assert block_layout(13, 2).tolist() == [0, 7, 13]
     assert block_layout(3, 8).tolist() == [0, 1, 2, 3, 3, 3, 3, 3, 3]
@@ -157,7 +157,7 @@ def test_epoch_protocol_two_parities_suffice_under_any_interleaving(world):
     """The peer-memory halo keeps only TWO ghost buffers per rank.  Randomised interleavings of the ranks' push/consume
     steps (including ranks racing ahead as far as the protocol lets them) never read overwritten data."""
     sys.path.insert(0, ROOT)
-    from pacmensl_b200.partition import EpochProtocol
+    from partition_model import EpochProtocol
     rng = np.random.default_rng(world)
     for trial in range(20):
         prot = EpochProtocol(world)
