@@ -18,9 +18,10 @@ inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, 
   std::string solver = "cvode", constraints = "default";
   double      t_final_override = -1.0;
   int         verbosity = 0;
-  bool        log_events = false;
+  bool        log_events = false, cold = false;
   for (int i = 1; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--log")) log_events = true;
+    if (!std::strcmp(argv[i], "--cold")) cold = true;  // re-create the BDF integrator after every expansion (reference behaviour)
     if (!std::strcmp(argv[i], "--solver") && i + 1 < argc) solver = argv[++i];
     else if (!std::strcmp(argv[i], "--constraints") && i + 1 < argc) constraints = argv[++i];
     else if (!std::strcmp(argv[i], "--tfinal") && i + 1 < argc) t_final_override = std::atof(argv[++i]);
@@ -50,6 +51,7 @@ inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, 
   fsp_solver.SetOdeTolerances(f.rtol, f.atol);
   fsp_solver.SetVerbosity(verbosity);
   fsp_solver.SetFromOptions();
+  if (cold) fsp_solver.SetWarmRestart(false);
   if (log_events) fsp_solver.SetLogging(PETSC_TRUE);
 
   auto t0 = std::chrono::steady_clock::now();
@@ -64,8 +66,8 @@ inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, 
   arma::Row<int> final_bounds = fss->GetShapeBounds();
   if (rank == 0) {
     std::printf("{\"example\": \"%s\", \"solver\": \"%s\", \"ranks\": %d, \"t_final\": %g, \"fsp_tol\": %g, \"wall_s\": %.4f, "
-                "\"expansions\": %d, \"final_states\": %d, \"action_calls\": %ld, \"sum_p\": %.12f, \"final_bounds\": [",
-                name, solver.c_str(), size, t_final, f.fsp_tol, wall, fsp_solver.GetNumExpansions(), fss->GetNumGlobalStates(),
+                "\"expansions\": %d, \"warm_restarts\": %d, \"final_states\": %d, \"action_calls\": %ld, \"sum_p\": %.12f, \"final_bounds\": [",
+                name, solver.c_str(), size, t_final, f.fsp_tol, wall, fsp_solver.GetNumExpansions(), fsp_solver.GetNumWarmRestarts(), fss->GetNumGlobalStates(),
                 fsp_solver.GetNumRhsEvals(), psum);
     for (arma::uword k = 0; k < final_bounds.n_elem; ++k) std::printf("%s%d", k ? ", " : "", final_bounds[k]);
     std::printf("]}\n");

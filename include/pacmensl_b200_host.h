@@ -86,6 +86,10 @@ FSP_API int pfsp_solver_set_initial_distribution(void *solver, int S, int m, con
 FSP_API int pfsp_solver_set_ode_tolerances(void *solver, double rtol, double atol);
 FSP_API int pfsp_solver_set_verbosity(void *solver, int level);
 FSP_API int pfsp_solver_set_krylov(void *solver, int q_iop, int m_min, int m_max);
+/* 1 (default): the BDF integrator keeps its history (step size, order, Nordsieck array) across FSP expansions;
+ * 0: it is re-created after every expansion like the reference's CVODE (src/Fsp/FspSolverMultiSinks.cpp:92-108) */
+FSP_API int pfsp_solver_set_warm_restart(void *solver, int on);
+FSP_API int pfsp_solver_num_warm_restarts(void *solver, int *n);
 FSP_API int pfsp_solver_setup(void *solver);
 /* Solve to t_final; *n_local receives the number of local states of the result (kept inside the handle) */
 FSP_API int pfsp_solver_solve(void *solver, double t_final, double fsp_tol, double t_init, int *n_local, int *n_species);

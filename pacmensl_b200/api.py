@@ -57,6 +57,8 @@ HOST_SIGNATURES = {
     "pfsp_solver_set_ode_tolerances": (ci, [vp, cd, cd]),
     "pfsp_solver_set_verbosity": (ci, [vp, ci]),
     "pfsp_solver_set_krylov": (ci, [vp, ci, ci, ci]),
+    "pfsp_solver_set_warm_restart": (ci, [vp, ci]),
+    "pfsp_solver_num_warm_restarts": (ci, [vp, ip]),
     "pfsp_solver_setup": (ci, [vp]),
     "pfsp_solver_solve": (ci, [vp, cd, cd, cd, ip, ip]),
     "pfsp_solver_copy_result": (ci, [vp, ip, dp]),
@@ -351,6 +353,14 @@ class FspSolver:
 
     def set_krylov(self, q_iop=2, m_min=25, m_max=60):
         return lib().pfsp_solver_set_krylov(self.h, q_iop, m_min, m_max)
+
+    def set_warm_restart(self, on):
+        return lib().pfsp_solver_set_warm_restart(self.h, 1 if on else 0)
+
+    def warm_restarts(self):
+        n = ci()
+        check(lib().pfsp_solver_num_warm_restarts(self.h, C.byref(n)), "num_warm_restarts")
+        return n.value
 
     def setup(self):
         return lib().pfsp_solver_setup(self.h)

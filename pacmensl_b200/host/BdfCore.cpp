@@ -1,6 +1,7 @@
 // BdfCore.cpp -- see BdfCore.h.  All vector work is done by the fused fp64 device kernels of
 // include/fsp_b200.h; only scalars (norms, Hessenberg columns) come back to the host.
 #include "BdfCore.h"
+#include "PetscWrap.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -817,6 +818,18 @@ int BdfCore::Step(double *t_reached, Vec yout, Vec *sout) {
     }
     break;
   }
+  if (accept_) {
+    bool reject = false;
+    if (accept_(tn_, y_, &reject) != 0) return BDF_RHS_FAIL;
+    if (reject) {
+      restore(saved_t);  // the history is the one of the last committed step again
+      if (vec_status_) return BDF_MEM_FAIL;
+      *t_reached = tn_;
+      if (yout) VCHK(VecCopy(zn_[0], yout));
+      if (sout) for (int is = 0; is < ns_; ++is) VCHK(VecCopy(znS_[is][0], sout[is]));
+      return STOPPED;
+    }
+  }
   complete_step();
   prepare_next_step(dsm);
   etamax_ = (nst_ <= SMALL_NST) ? ETAMX2 : ETAMX3;
@@ -846,6 +859,38 @@ int BdfCore::interpolate(double t, Vec *zn, Vec out) {
 }
 
 int BdfCore::GetDky(double t, Vec yout) { return interpolate(t, zn_, yout); }
+
+int BdfCore::Expand(const std::vector<PetscInt> &new_indices, PetscInt new_local_size) {
+  if (first_ || !zn_[0]) return 1;  // nothing worth keeping
+  vec_status_ = 0;
+  flush_scale();
+  if (vec_status_) return BDF_MEM_FAIL;
+  // persistent vectors: the Nordsieck array (all QMAX + 1 columns: column indx_acor_ may hold the saved correction of
+  // an order-increase decision) and the last correction / local error estimate
+  for (int j = 0; j <= QMAX; ++j) if (ExpandVec(zn_[j], new_indices, new_local_size)) return BDF_MEM_FAIL;
+  if (ExpandVec(acor_, new_indices, new_local_size)) return BDF_MEM_FAIL;
+  for (int is = 0; is < ns_; ++is) {
+    for (int j = 0; j <= QMAX; ++j) if (ExpandVec(znS_[is][j], new_indices, new_local_size)) return BDF_MEM_FAIL;
+    if (ExpandVec(acorS_[is], new_indices, new_local_size)) return BDF_MEM_FAIL;
+  }
+  // scratch vectors: new size, contents undefined
+  for (Vec *v : {&ewt_, &ewt_inv_, &y_, &tempv_, &ftemp_, &xcor_, &vtemp_, &delta_}) {
+    if (*v) VecDestroy(v);
+    if (alloc_like(zn_[0], v)) return BDF_MEM_FAIL;
+  }
+  for (auto &v : V_) if (v) VecDestroy(&v);
+  V_.clear();
+  for (int is = 0; is < ns_; ++is)
+    for (auto *vv : {&ewtS_, &ewtS_inv_, &yS_, &ftempS_}) {
+      if ((*vv)[is]) VecDestroy(&(*vv)[is]);
+      if (alloc_like(zn_[0], &(*vv)[is])) return BDF_MEM_FAIL;
+    }
+  n_local_ = zn_[0]->n_local;
+  PetscInt ng = 0;
+  VecGetSize(zn_[0], &ng);
+  n_global_ = (double) ng;
+  return 0;
+}
 int BdfCore::GetSensDky(double t, int is, Vec sout) { return interpolate(t, znS_[is].data(), sout); }
 
 }  // namespace pacmensl

@@ -31,6 +31,17 @@ class BdfCore {
   /// J v with a fused epilogue (FspMatrixBase::ActionFused); optional, used by the state GMRES loop when set
   using FusedJtvFn = std::function<int(double t, Vec v, Vec out, const fspmat_epilogue &ep)>;
   void SetFusedJtv(FusedJtvFn f) { fused_jtv_ = std::move(f); }
+  /// Consulted after a step has converged and passed its error test but BEFORE it is committed: (t_new, y_new).
+  /// *reject = true undoes the step (cvRestore: the history is back at the previous time, step size and order
+  /// unchanged) and Step returns STOPPED.  This is how the FSP driver's sink check stops the integrator without losing
+  /// its history (a check after the commit would need a copy of the whole Nordsieck array per step to roll back).
+  using AcceptFn = std::function<int(double t_new, Vec y_new, bool *reject)>;
+  void SetAcceptHook(AcceptFn f) { accept_ = std::move(f); }
+  static constexpr int STOPPED = 10;  ///< Step(): the accept hook rejected the step; state is at the previous time
+  /// Re-map the history onto an enlarged state space (entry i moves to new_indices[i], new entries are zero), keeping
+  /// step size, order and all controller state: the integrator continues instead of restarting at order 1.
+  int  Expand(const std::vector<PetscInt> &new_indices, PetscInt new_local_size);
+  long LocalSize() const { return n_local_; }
 
   explicit BdfCore(MPI_Comm comm);
   ~BdfCore();
@@ -77,6 +88,7 @@ class BdfCore {
   JtvFn     jtv_;
   SensRhsFn fs_;
   FusedJtvFn fused_jtv_;
+  AcceptFn   accept_;
 
   // Nordsieck history and work vectors
   Vec zn_[LMAX + 1] = {nullptr};

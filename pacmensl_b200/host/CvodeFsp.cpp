@@ -19,17 +19,40 @@ PacmenslErrorCode CvodeFsp::SetUp() {
   CHKERRQ(petsc_err);
   t_now_tmp = t_now_;
 
-  core_.reset(new BdfCore(comm_));
-  core_->SetTolerances(rel_tol_, abs_tol_);
-  core_->SetMaxConvFails(10000);     // CVodeSetMaxConvFails(cvode_mem, 10000)
-  core_->SetMaxNonlinIters(10000);   // CVodeSetMaxNonlinIters(cvode_mem, 10000)
-  core_->SetMaxKrylov(100);          // SUNLinSol_SPGMR(y, PREC_NONE, 100)
   auto f = [this](double t, Vec y, Vec ydot) { return EvaluateRHS(t, y, ydot); };  // J v == A(t) v (linear ODE)
-  if (fused_rhs_) core_->SetFusedJtv([this](double t, Vec v, Vec out, const fspmat_epilogue &ep) { return fused_rhs_(t, v, out, ep); });
-  cvode_stat = core_->Init(t_now_tmp, solution_work_, f, f, t_final_);
-  if (cvode_stat < 0) {
-    printf("\nBDF integrator error: initialisation failed with flag = %d\n\n", cvode_stat);
-    return -1;
+  const bool resume = warm_restart_ && carry_ && core_ && core_->LocalSize() == (*solution_)->n_local &&
+                      core_->CurrentTime() == t_now_;
+  carry_ = false;
+  if (!resume) {
+    core_.reset(new BdfCore(comm_));
+    core_->SetTolerances(rel_tol_, abs_tol_);
+    core_->SetMaxConvFails(10000);     // CVodeSetMaxConvFails(cvode_mem, 10000)
+    core_->SetMaxNonlinIters(10000);   // CVodeSetMaxNonlinIters(cvode_mem, 10000)
+    core_->SetMaxKrylov(100);          // SUNLinSol_SPGMR(y, PREC_NONE, 100)
+    if (fused_rhs_) core_->SetFusedJtv([this](double t, Vec v, Vec out, const fspmat_epilogue &ep) { num_rhs_evals_ += 1; return fused_rhs_(t, v, out, ep); });
+    cvode_stat = core_->Init(t_now_tmp, solution_work_, f, f, t_final_);
+    if (cvode_stat < 0) {
+      printf("\nBDF integrator error: initialisation failed with flag = %d\n\n", cvode_stat);
+      return -1;
+    }
+  }
+  // (resume: the integrator kept its history through BdfCore::Expand and simply goes on from t_now_)
+  if (warm_restart_ && stop_check_ != nullptr) {
+    // The stop condition is evaluated on the converged but not yet committed step, so a stop leaves the integrator at
+    // the last committed time with its history intact (the reference checks after the step and rolls back through
+    // CVodeGetDky, then throws the integrator away: src/OdeSolver/CvodeFsp.cpp:50-59, FspSolverMultiSinks.cpp:92-108).
+    core_->SetAcceptHook([this](double t, Vec y, bool *reject) {
+      *reject = false;
+      hook_checked_ = false;
+      if (t > t_final_) return 0;  // the last step is interpolated back to t_final first: checked after the step
+      int ierr = stop_check_(t, y, hook_excess_, stop_data_);
+      if (ierr) return ierr;
+      hook_checked_ = true;
+      *reject = hook_excess_ > 0.0;
+      return 0;
+    });
+  } else {
+    core_->SetAcceptHook(nullptr);
   }
   return 0;
 }
@@ -42,7 +65,15 @@ PetscInt CvodeFsp::Solve() {
   int               stop = 0;
   PetscReal         error_excess = 0.0;
   while (t_now_ < t_final_) {
+    hook_checked_ = false;
     cvode_stat = core_->Step(&t_now_tmp, solution_work_);
+    if (cvode_stat == BdfCore::STOPPED) {
+      // the accept hook saw the sinks exceed the tolerance: solution_work_ is the solution at t_now_ and the
+      // integrator can be carried over to the expanded state space (ExpandState)
+      stop = 1;
+      carry_ = true;
+      break;
+    }
     if (cvode_stat < 0) {
       int rank;
       MPI_Comm_rank(MPI_COMM_WORLD, &rank);
@@ -55,7 +86,7 @@ PetscInt CvodeFsp::Solve() {
       if (cvode_stat < 0) return -1;
       t_now_tmp = t_final_;
     }
-    if (stop_check_ != nullptr) {
+    if (stop_check_ != nullptr && !hook_checked_) {
       ierr = stop_check_(t_now_tmp, solution_work_, error_excess, stop_data_);
       PACMENSLCHKERRQ(ierr);
       if (error_excess > 0.0) {
@@ -81,9 +112,19 @@ PetscInt CvodeFsp::Solve() {
   return stop;
 }
 
+int CvodeFsp::ExpandState(const std::vector<PetscInt> &new_indices, PetscInt new_local_size) {
+  if (!warm_restart_ || !carry_ || !core_) return 1;
+  if (core_->Expand(new_indices, new_local_size) != 0) {
+    carry_ = false;
+    core_.reset();
+    return 1;
+  }
+  return 0;
+}
+
 int CvodeFsp::FreeWorkspace() {
   OdeSolverBase::FreeWorkspace();
-  core_.reset();
+  if (!(warm_restart_ && carry_)) core_.reset();  // a stopped integrator is kept for ExpandState + the next SetUp
   if (solution_work_ != nullptr) VecDestroy(&solution_work_);
   return 0;
 }

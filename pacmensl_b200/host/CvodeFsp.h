@@ -18,6 +18,9 @@ class PACMENSL_API CvodeFsp : public OdeSolverBase {
   PacmenslErrorCode SetUp() override;
   PetscInt Solve() override;
   int FreeWorkspace() override;
+  /// Warm restart across FSP expansions (SetWarmRestart(true)): the Nordsieck history, step size and order survive the
+  /// expansion (BdfCore::Expand) and the next SetUp()/Solve() continue the integration instead of restarting at order 1.
+  int ExpandState(const std::vector<PetscInt> &new_indices, PetscInt new_local_size) override;
   ~CvodeFsp();
 
   /// integrator statistics of the current/last workspace (extension)
@@ -29,5 +32,8 @@ class PACMENSL_API CvodeFsp : public OdeSolverBase {
   Vec       solution_work_ = nullptr;  ///< cvode_solution of the reference
   PetscReal t_now_tmp = 0.0;
   int       cvode_stat = 0;
+  bool      carry_ = false;        ///< core_ holds a history worth continuing (stopped by the accept hook at t_now_)
+  bool      hook_checked_ = false; ///< the accept hook already ran the stop condition for the step just taken
+  PetscReal hook_excess_ = 0.0;
 };
 }  // namespace pacmensl

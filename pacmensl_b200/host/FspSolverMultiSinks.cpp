@@ -129,6 +129,9 @@ DiscreteDistribution FspSolverMultiSinks::Advance_(PetscReal t_final, PetscReal 
       }
       ierr = ExpandVec(*p_, new_locations_vals, A_->GetNumLocalRows());
       PACMENSLCHKERRTHROW(ierr);
+      // warm restart: the integrator's own history follows the solution onto the enlarged state space (0 = carried
+      // over, 1 = this solver restarts cold at the next SetUp, as the reference always does)
+      if (ode_solver_->ExpandState(new_locations_vals, A_->GetNumLocalRows()) == 0) num_warm_restarts_ += 1;
       t_scatter_ += now_s() - t0;
     }
     t_now_ = ode_solver_->GetCurrentTime();
@@ -246,6 +249,8 @@ PacmenslErrorCode FspSolverMultiSinks::SetUp() {
         ode_solver_ = std::make_shared<TsFsp>(comm_);
     }
     ode_solver_->SetFspMatPtr(A_.get());
+    static const bool warm_env = [] { const char *e = std::getenv("FSP_WARM_RESTART"); return !(e && e[0] == '0'); }();
+    ode_solver_->SetWarmRestart(warm_restart_ && warm_env);
     if (logging_enabled) ode_solver_->EnableLogging();
   }
 

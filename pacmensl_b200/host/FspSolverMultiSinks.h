@@ -58,6 +58,12 @@ class PACMENSL_API FspSolverMultiSinks {
   PacmenslErrorCode SetKrylovOrthLength(int q);
   PacmenslErrorCode SetKrylovDimRange(int m_min, int m_max);
   PacmenslErrorCode SetOdeTolerances(PetscReal rel_tol, PetscReal abs_tol);
+  /// Extension.  true (default; FSP_WARM_RESTART=0 turns it off): after an expansion the BDF
+  /// integrator continues with its Nordsieck history, step size and order mapped onto the enlarged state space.
+  /// false: the reference's behaviour -- the integrator is re-created and restarts at order 1 with a fresh first step
+  /// (src/Fsp/FspSolverMultiSinks.cpp:92-108).  KrylovFsp always restarts as the reference does (its restart costs
+  /// one extra Action and is part of the step sequence the oracle reproduces).
+  PacmenslErrorCode SetWarmRestart(bool on) { warm_restart_ = on; if (ode_solver_) ode_solver_->SetWarmRestart(on); return 0; }
 
   std::shared_ptr<const StateSetBase> GetStateSet();
   std::shared_ptr<OdeSolverBase> GetOdeSolver();
@@ -72,6 +78,7 @@ class PACMENSL_API FspSolverMultiSinks {
 
   // ---- run statistics (extension; what the examples report) ----
   int  GetNumExpansions() const { return num_expansions_; }
+  int  GetNumWarmRestarts() const { return num_warm_restarts_; }
   long GetNumRhsEvals() const { return ode_solver_ ? ode_solver_->GetNumRhsEvals() + rhs_evals_retired_ : rhs_evals_retired_; }
 
  protected:
@@ -126,10 +133,11 @@ class PACMENSL_API FspSolverMultiSinks {
   bool        custom_ts_type_ = false;
   std::string ts_type_ = "";
   bool        custom_krylov_ = false;
+  bool        warm_restart_ = true;
   int         q_iop_ = -1;
   int         m_min_ = 25, m_max_ = 60;
 
-  int  num_expansions_ = 0;
+  int  num_expansions_ = 0, num_warm_restarts_ = 0;
   long rhs_evals_retired_ = 0;
 };
 }  // namespace pacmensl

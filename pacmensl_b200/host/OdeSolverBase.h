@@ -45,6 +45,15 @@ class PACMENSL_API OdeSolverBase {
   virtual PacmenslErrorCode FreeWorkspace() { solution_ = nullptr; return 0; }
   virtual ~OdeSolverBase();
 
+  /// Extension: keep the integrator's history across an FSP expansion instead of re-creating
+  /// the integrator as the reference does (src/Fsp/FspSolverMultiSinks.cpp:92-108).
+  void SetWarmRestart(bool on) { warm_restart_ = on; }
+  bool GetWarmRestart() const { return warm_restart_; }
+  /// Called by the FSP driver after an expansion and before the next SetUp(): entry i of the old local vector now
+  /// lives at new_indices[i] (same meaning as ExpandVec's argument).  0: the solver carried its history over to the
+  /// new state space; 1: this solver (or this situation) restarts cold.
+  virtual int ExpandState(const std::vector<PetscInt> &, PetscInt) { return 1; }
+
   /// number of right-hand-side (Action) evaluations since construction (extension, for reports)
   long GetNumRhsEvals() const { return num_rhs_evals_; }
 
@@ -70,5 +79,6 @@ class PACMENSL_API OdeSolverBase {
   PetscReal                   rel_tol_ = 1.0e-6;
   PetscReal                   abs_tol_ = 1.0e-14;
   long                        num_rhs_evals_ = 0;
+  bool                        warm_restart_ = false;
 };
 }  // namespace pacmensl

@@ -237,6 +237,8 @@ int pfsp_solver_set_krylov(void *solver, int q_iop, int m_min, int m_max) {
   if (ierr) return ierr;
   return s->SetKrylovDimRange(m_min, m_max);
 }
+int pfsp_solver_set_warm_restart(void *solver, int on) { return static_cast<SolverBox *>(solver)->solver->SetWarmRestart(on != 0); }
+int pfsp_solver_num_warm_restarts(void *solver, int *n) { *n = static_cast<SolverBox *>(solver)->solver->GetNumWarmRestarts(); return 0; }
 int pfsp_solver_setup(void *solver) {
   PFSP_TRY
   return static_cast<SolverBox *>(solver)->solver->SetUp();

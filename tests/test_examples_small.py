@@ -99,3 +99,44 @@ def test_fixed_set_solves_against_tight_reference(cuda, oracle, name, bounds, t_
         # KrylovFsp's controller aims at err <= 1.2 * atol * tau per step: it should sit near the roundoff floor
         assert diff <= (1e-10 if ode == api.KRYLOV else max(1e-6, 10 * fx["rtol"] * 1e-1))
         s.clear()
+
+
+def _l1_by_key(states_a, p_a, states_b, p_b):
+    da = {tuple(s): v for s, v in zip(states_a.tolist(), p_a)}
+    db = {tuple(s): v for s, v in zip(states_b.tolist(), p_b)}
+    return sum(abs(da.get(k, 0.0) - db.get(k, 0.0)) for k in set(da) | set(db))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,t_final", [("pure_birth", 10.0), ("repressilator", 0.5), ("transcr_reg_6d", 10.0), ("hog1p", 30.0)])
+def test_bdf_warm_restart_across_expansions(cuda, name, t_final):
+    """after an expansion the BDF integrator continues with its Nordsieck history mapped onto the enlarged
+    state space (default) instead of restarting at order 1 like the reference's CVODE (set_warm_restart(False)).
+    Same answer within the integrator's tolerance, fewer Action calls."""
+    import math
+    from pacmensl_b200 import api
+    api.init(0)
+    res = {}
+    for warm in (False, True):
+        s, m = api.fixture_solver(name, api.CVODE)
+        if name == "hog1p":
+            s.set_initial_bounds([3, 5, 5, 5, 5])
+        s.set_warm_restart(warm)
+        states, p = s.solve(t_final, m.fixture["fsp_tol"])
+        st = s.stats()
+        res[warm] = (states, p, st, s.warm_restarts())
+        s.clear()
+    (sc, pc, stc, wc), (sw, pw, stw, ww) = res[False], res[True]
+    diff = _l1_by_key(sc, pc, sw, pw)
+    rtol, fsp_tol = m.fixture["rtol"], m.fixture["fsp_tol"]
+    print("%s to t=%g: cold %d expansions / %d Actions / %d states | warm %d expansions (%d carried) / %d Actions / %d states | "
+          "||p_warm - p_cold||_1 = %.3e (rtol %g)" % (name, t_final, stc["expansions"], stc["rhs_evals"], stc["n_states"],
+                                                     stw["expansions"], ww, stw["rhs_evals"], stw["n_states"], diff, rtol))
+    assert wc == 0 and ww == stw["expansions"] and stw["expansions"] > 0
+    assert abs(pw.sum() - 1.0) <= fsp_tol * 1.01 + 1e-8 and pw.min() > -1e-8
+    assert diff <= 50 * rtol
+    assert stw["rhs_evals"] <= 0.75 * stc["rhs_evals"]
+    if name == "pure_birth":  # KAT-F4 (tests/test_fsp_solver.cpp:264-345) holds with the warm restart too
+        lam = 2.0 * t_final
+        pdf = np.array([math.exp(-lam) * lam ** int(n) / math.gamma(int(n) + 1) for n in sw[:, 0]])
+        assert np.abs(pw - pdf).sum() <= 1e-6
