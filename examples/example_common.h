@@ -9,6 +9,7 @@
 #include <string>
 
 #include "fsp_models.h"
+#include "fsp_models_device.h"
 #include "pacmensl_all.h"
 
 inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, const char *custom_fixture) {
@@ -18,9 +19,10 @@ inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, 
   std::string solver = "cvode", constraints = "default";
   double      t_final_override = -1.0;
   int         verbosity = 0;
-  bool        log_events = false, cold = false;
+  bool        log_events = false, cold = false, host_prop = false;
   for (int i = 1; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--log")) log_events = true;
+    if (!std::strcmp(argv[i], "--host-propensities")) host_prop = true;  // evaluate prop_x through the host callback only
     if (!std::strcmp(argv[i], "--cold")) cold = true;  // re-create the BDF integrator after every expansion (reference behaviour)
     if (!std::strcmp(argv[i], "--solver") && i + 1 < argc) solver = argv[++i];
     else if (!std::strcmp(argv[i], "--constraints") && i + 1 < argc) constraints = argv[++i];
@@ -36,6 +38,9 @@ inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, 
 
   arma::Mat<int> SM(f.SM, f.num_species, f.num_reactions);
   Model model(SM, f.prop_t, f.prop_x, nullptr, nullptr, std::vector<int>(f.tv_reactions, f.tv_reactions + f.num_tv));
+  // the reference's contract is the host callback prop_x; where the propensities are separable (hog1p, transcr_reg_6d)
+  // the same values are described in device-evaluable form so that matrix generation never leaves the GPU
+  const bool device_form = !host_prop && AttachDeviceForm(name, model);
   arma::Mat<int>       X0(f.x0, f.num_species, 1);
   arma::Col<PetscReal> p0 = {1.0};
   arma::Row<int>       bounds(f.bounds, f.num_constr);
@@ -65,9 +70,9 @@ inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, 
   auto fss = std::static_pointer_cast<const StateSetConstrained>(fsp_solver.GetStateSet());
   arma::Row<int> final_bounds = fss->GetShapeBounds();
   if (rank == 0) {
-    std::printf("{\"example\": \"%s\", \"solver\": \"%s\", \"ranks\": %d, \"t_final\": %g, \"fsp_tol\": %g, \"wall_s\": %.4f, "
+    std::printf("{\"example\": \"%s\", \"solver\": \"%s\", \"device_propensities\": %s, \"ranks\": %d, \"t_final\": %g, \"fsp_tol\": %g, \"wall_s\": %.4f, "
                 "\"expansions\": %d, \"warm_restarts\": %d, \"final_states\": %d, \"action_calls\": %ld, \"sum_p\": %.12f, \"final_bounds\": [",
-                name, solver.c_str(), size, t_final, f.fsp_tol, wall, fsp_solver.GetNumExpansions(), fsp_solver.GetNumWarmRestarts(), fss->GetNumGlobalStates(),
+                name, solver.c_str(), device_form ? "true" : "false", size, t_final, f.fsp_tol, wall, fsp_solver.GetNumExpansions(), fsp_solver.GetNumWarmRestarts(), fss->GetNumGlobalStates(),
                 fsp_solver.GetNumRhsEvals(), psum);
     for (arma::uword k = 0; k < final_bounds.n_elem; ++k) std::printf("%s%d", k ? ", " : "", final_bounds[k]);
     std::printf("]}\n");

@@ -220,6 +220,13 @@ FSP_API int fspset_add_box_lattice(fspset_t h, const int *upper_host);
  * ---------------------------------------------------------------------------------------------- */
 FSP_API int fspset_eval_mass_action(fspset_t h, double rate, const int *order_host /* S */, const int *nu_host,
                                     int sign, long first, long count, double *out_dev);
+/* The separable form: d_r(x) = rate * prod_s ff(x_s, ord_s) * T_s[min(x_s, len_s - 1)], with one optional factor table per
+ * species (len_s == 0: none; a negative coordinate gives 0).  tables_dev holds the tables back to back, tab_off_host[s]
+ * is where species s starts.  Covers gene-state switches and saturating (Hill-type) factors of a single species: the
+ * hog1p model of examples/hog1p.cpp:14-112 is evaluated entirely on the device this way. */
+FSP_API int fspset_eval_separable(fspset_t h, double rate, const int *order_host /* S */, const double *tables_dev,
+                                  const int *tab_off_host /* S */, const int *tab_len_host /* S */, const int *nu_host,
+                                  int sign, long first, long count, double *out_dev);
 
 /* ------------------------------------------------------------------------------------------------
  * The FSP operator A(t) = sum_r c_r(t) A_r (+ sink rows).

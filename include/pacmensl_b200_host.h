@@ -59,6 +59,12 @@ FSP_API int pfsp_model_from_fixture(void **model, const char *name, int *S, int 
                                     int *x0, double *t_final, double *fsp_tol, double *rtol, double *atol,
                                     pfsp_constr_fn *lhs);
 FSP_API int pfsp_model_set_mass_action(void *model, const double *rates, const int *orders_colmajor);
+/* adds the per-species factor values[min(x_species, len - 1)] to reaction `reaction` of the device-evaluable form
+ * (call after pfsp_model_set_mass_action; orders 0 and rate 1 give a pure table factor) */
+FSP_API int pfsp_model_set_factor_table(void *model, int species, int reaction, int len, const double *values);
+/* attaches the separable (device-evaluable) description of a named fixture's propensities, if one exists (0) or not (1):
+ * matrix generation then evaluates the propensities on the GPU instead of calling prop_x on the host */
+FSP_API int pfsp_model_attach_device_form(void *model, const char *fixture_name);
 /* copies the S x R stoichiometry matrix (column major: SM[r*S + s]) */
 FSP_API int pfsp_model_get_stoichiometry(void *model, int *SM_colmajor);
 FSP_API int pfsp_model_destroy(void *model);

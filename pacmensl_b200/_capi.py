@@ -119,6 +119,7 @@ SIGNATURES = {
     "fspset_copy_status": (ci, [vp, cl, cl, C.POINTER(C.c_byte)]),
     "fspset_add_box_lattice": (ci, [vp, ip]),
     "fspset_eval_mass_action": (ci, [vp, cd, ip, ip, ci, cl, cl, vp]),
+    "fspset_eval_separable": (ci, [vp, cd, ip, vp, ip, ip, ip, ci, cl, cl, vp]),
     "fspmat_create": (ci, [vpp]),
     "fspmat_destroy": (ci, [vp]),
     "fspmat_generate": (ci, [vp, C.POINTER(FspMatDesc)]),

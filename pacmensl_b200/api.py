@@ -37,6 +37,8 @@ HOST_SIGNATURES = {
     "pfsp_model_create": (ci, [vpp, ci, ci, ip, vp, vp, vp, vp, ci, ip]),
     "pfsp_model_from_fixture": (ci, [vpp, C.c_char_p, ip, ip, ip, ip, dp, ip, dp, dp, dp, dp, vpp]),
     "pfsp_model_set_mass_action": (ci, [vp, dp, ip]),
+    "pfsp_model_set_factor_table": (ci, [vp, ci, ci, ci, dp]),
+    "pfsp_model_attach_device_form": (ci, [vp, C.c_char_p]),
     "pfsp_model_get_stoichiometry": (ci, [vp, ip]),
     "pfsp_model_destroy": (ci, [vp]),
     "pfsp_mat_create": (ci, [vpp, ci]),
@@ -205,11 +207,14 @@ class StateSet:
 
 
 class Model:
-    def __init__(self, SM=None, prop_x=None, prop_t=None, tv=(), fixture=None):
+    def __init__(self, SM=None, prop_x=None, prop_t=None, tv=(), fixture=None, device_form=False):
+        """device_form (fixtures only): attach the separable description of the propensities so that matrix generation
+        evaluates them on the GPU (hog1p, transcr_reg_6d, birth_death_3d, pure_birth) instead of through prop_x."""
         L = lib()
         self._keep = []
         h = vp()
         self.fixture = None
+        self.device_form = False
         if fixture is not None:
             S, R, K = ci(), ci(), ci()
             bounds = np.zeros(16, np.int32)
@@ -249,6 +254,12 @@ class Model:
             check(L.pfsp_model_create(C.byref(h), self.S, self.R, _ip(sm), C.cast(px, vp) if px else None, None,
                                       C.cast(pt, vp) if pt else None, None, len(tvv), _ip(tvv)), "pfsp_model_create")
         self.h = h
+        if fixture is not None and device_form:
+            self.device_form = L.pfsp_model_attach_device_form(self.h, fixture.encode()) == 0
+
+    def set_factor_table(self, species, reaction, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        check(lib().pfsp_model_set_factor_table(self.h, int(species), int(reaction), len(v), _dp(v)), "SetFactorTable")
 
     def stoichiometry(self):
         """S x R matrix as written in the reference (one column per reaction)."""

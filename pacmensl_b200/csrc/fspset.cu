@@ -233,8 +233,10 @@ __global__ void lattice_kernel(long first, long m, int S, SmallVec dims, int *ou
   }
 }
 
+// separable propensity: rate * prod_s ff(x_s, order_s) * table_s[min(x_s, len_s - 1)]   (len_s == 0: no table factor)
 __global__ void mass_action_kernel(const int *states, long first, long count, int S, SmallVec nu, int sign,
-                                   SmallVec order, double rate, double *out) {
+                                   SmallVec order, double rate, const double *__restrict__ tabs, SmallVec tab_off,
+                                   SmallVec tab_len, double *out) {
   long j = (long) blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= count) return;
   double v = rate;
@@ -244,6 +246,8 @@ __global__ void mass_action_kernel(const int *states, long first, long count, in
     if (o == 1) v *= (double) x;
     else if (o == 2) v *= 0.5 * (double) x * (double) (x - 1);
     else if (o == 3) v *= (double) x * (double) (x - 1) * (double) (x - 2) / 6.0;
+    const int len = tab_len.v[s];
+    if (len > 0) v *= x < 0 ? 0.0 : __ldg(tabs + tab_off.v[s] + min(x, len - 1));
   }
   out[j] = v;
 }
@@ -643,17 +647,24 @@ int fspset_copy_status(fspset_t h, long first, long count, signed char *out) {
   return 0;
 }
 
-int fspset_eval_mass_action(fspset_t h, double rate, const int *order_host, const int *nu_host, int sign, long first,
-                            long count, double *out_dev) {
+int fspset_eval_separable(fspset_t h, double rate, const int *order_host, const double *tables_dev, const int *tab_off_host,
+                          const int *tab_len_host, const int *nu_host, int sign, long first, long count, double *out_dev) {
   if (count <= 0) return 0;
-  SmallVec nu, ord;
+  SmallVec nu, ord, off, len;
   for (int s = 0; s < kMaxS; ++s) {
     nu.v[s] = s < h->S ? nu_host[s] : 0;
     ord.v[s] = s < h->S ? order_host[s] : 0;
+    off.v[s] = (s < h->S && tables_dev && tab_off_host) ? tab_off_host[s] : 0;
+    len.v[s] = (s < h->S && tables_dev && tab_len_host) ? tab_len_host[s] : 0;
   }
-  mass_action_kernel<<<blocks_for(count), 256>>>(h->d_states, first, count, h->S, nu, sign, ord, rate, out_dev);
+  mass_action_kernel<<<blocks_for(count), 256>>>(h->d_states, first, count, h->S, nu, sign, ord, rate, tables_dev, off, len, out_dev);
   FSP_LAUNCH_CHECK();
   return 0;
+}
+
+int fspset_eval_mass_action(fspset_t h, double rate, const int *order_host, const int *nu_host, int sign, long first,
+                            long count, double *out_dev) {
+  return fspset_eval_separable(h, rate, order_host, nullptr, nullptr, nullptr, nu_host, sign, first, count, out_dev);
 }
 
 

@@ -155,17 +155,31 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
   const long          first = fsp.GetLocalStart();
 
   if (on_device) {
-    // device-evaluable (mass-action) propensities: everything stays on the GPU
+    // device-evaluable (separable: mass action x per-species factor tables) propensities: everything stays on the GPU
+    std::vector<double> tabs_host;
+    std::map<std::pair<int, int>, int> tab_at;
+    for (const auto &kv : mass_action_->table) {
+      tab_at[kv.first] = (int) tabs_host.size();
+      tabs_host.insert(tabs_host.end(), kv.second.begin(), kv.second.end());
+    }
+    DeviceBuffer<double> tabs;
+    if (!tabs_host.empty() && tabs.upload(tabs_host.data(), tabs_host.size())) PACMENSLCHKERRQ(-1);
     for (int p = 0; p < P && n > 0; ++p) {
       const int  r = planes[p];
       const int *nu = SM.colptr(r);
       FSPCHKERRQ(fspset_lookup_shifted(dset, nu, -1, first, n, col.get() + (size_t) p * ld));  // State2Index(x - nu), :133-134
-      std::vector<int> ord(n_species);
-      for (int s = 0; s < n_species; ++s) ord[s] = mass_action_->order(s, r);
-      FSPCHKERRQ(fspset_eval_mass_action(dset, mass_action_->rate[r], ord.data(), nu, -1, first, n, off.get() + (size_t) p * ld));
-      FSPCHKERRQ(fspset_eval_mass_action(dset, mass_action_->rate[r], ord.data(), zero_nu.data(), 0, first, n,
-                                         diag.get() + (size_t) p * ld));
+      std::vector<int> ord(n_species), toff(n_species, 0), tlen(n_species, 0);
+      for (int s = 0; s < n_species; ++s) {
+        ord[s] = mass_action_->order(s, r);
+        auto it = mass_action_->table.find({s, r});
+        if (it != mass_action_->table.end() && !it->second.empty()) { toff[s] = tab_at[{s, r}]; tlen[s] = (int) it->second.size(); }
+      }
+      FSPCHKERRQ(fspset_eval_separable(dset, mass_action_->rate[r], ord.data(), tabs.get(), toff.data(), tlen.data(), nu, -1, first, n,
+                                       off.get() + (size_t) p * ld));
+      FSPCHKERRQ(fspset_eval_separable(dset, mass_action_->rate[r], ord.data(), tabs.get(), toff.data(), tlen.data(), zero_nu.data(), 0,
+                                       first, n, diag.get() + (size_t) p * ld));
     }
+    FSPCHKERRQ(fsp_device_sync());  // the table buffer is released when this scope ends
   } else if (comm_size_ == 1) {
     // Single rank, host callbacks (API contract).  d_r(x_i) is evaluated on the host once per state -- with the
     // incremental cache only for states added since the previous generation -- and the off-diagonal values

@@ -52,19 +52,15 @@ void Model::SetMassAction(const std::vector<double> &rates, const arma::Mat<int>
     auto ma = mass_action_;
     prop_x_ = [ma](const int r, const int S, const int m, const int *X, double *out, void *) {
       if (r < 0 || r >= (int) ma->rate.size()) return -1;
-      for (int i = 0; i < m; ++i) {
-        double v = ma->rate[r];
-        for (int s = 0; s < S; ++s) {
-          const int x = X[i * S + s], o = ma->order(s, r);
-          if (o == 1) v *= (double) x;
-          else if (o == 2) v *= 0.5 * (double) x * (double) (x - 1);
-          else if (o == 3) v *= (double) x * (double) (x - 1) * (double) (x - 2) / 6.0;
-        }
-        out[i] = v;
-      }
+      for (int i = 0; i < m; ++i) out[i] = ma->eval(r, S, X + (size_t) i * S);
       return 0;
     };
   }
+}
+
+void Model::SetFactorTable(int species, int reaction, const std::vector<double> &values) {
+  if (!mass_action_) return;
+  mass_action_->table[{species, reaction}] = values;
 }
 
 }  // namespace pacmensl

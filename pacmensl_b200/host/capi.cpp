@@ -4,6 +4,7 @@
 
 #include "../../include/pacmensl_b200_host.h"
 #include "fsp_models.h"
+#include "fsp_models_device.h"
 #include "pacmensl_all.h"
 
 using namespace pacmensl;
@@ -150,6 +151,13 @@ int pfsp_model_set_mass_action(void *model, const double *rates, const int *orde
   const int S = (int) b->model.stoichiometry_matrix_.n_rows, R = (int) b->model.stoichiometry_matrix_.n_cols;
   b->model.SetMassAction(std::vector<double>(rates, rates + R), colmajor(orders, S, R));
   return 0;
+}
+int pfsp_model_set_factor_table(void *model, int species, int reaction, int len, const double *values) {
+  static_cast<ModelBox *>(model)->model.SetFactorTable(species, reaction, std::vector<double>(values, values + len));
+  return 0;
+}
+int pfsp_model_attach_device_form(void *model, const char *fixture_name) {
+  return AttachDeviceForm(fixture_name, static_cast<ModelBox *>(model)->model) ? 0 : 1;
 }
 int pfsp_model_get_stoichiometry(void *model, int *SM_colmajor) {
   const arma::Mat<int> &SM = static_cast<ModelBox *>(model)->model.stoichiometry_matrix_;

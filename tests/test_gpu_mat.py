@@ -285,3 +285,25 @@ def test_action_host_pipeline_equals_device_action(cuda, upper, tv):
             lat.action(t, xd, yd)
             torch.cuda.synchronize()
             assert torch.equal(yh, yd.cpu()), (upper, tv, pinned, t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,bounds,t", [("hog1p", [3, 6, 6, 5, 5], 25.0), ("transcr_reg_6d", [10, 6, 1, 2, 1, 1], 40.0),
+                                            ("pure_birth", [30], 0.0)])
+def test_device_propensity_form_is_bit_identical_to_host_callbacks(cuda, name, bounds, t):
+    """The separable (rate x falling factorials x per-species factor tables) description of a model's propensities,
+    evaluated on the GPU at generate time, must give exactly the operator the host callback prop_x gives."""
+    import numpy as np
+    from pacmensl_b200 import api
+    torch = cuda
+    api.init(0)
+    m_dev = api.Model(fixture=name, device_form=True)
+    assert m_dev.device_form
+    st_h, A_h = api.fixture_set_and_matrix(name, bounds=np.asarray(bounds, dtype=np.int32), model=api.Model(fixture=name))
+    st_d, A_d = api.fixture_set_and_matrix(name, bounds=np.asarray(bounds, dtype=np.int32), model=m_dev)
+    assert st_h.n_global == st_d.n_global and A_h.n_rows == A_d.n_rows and A_h.info()[1] == A_d.info()[1]
+    x = torch.rand(A_h.n_rows, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    y_h, y_d = torch.empty_like(x), torch.empty_like(x)
+    assert A_h.action(t, x, y_h) == 0 and A_d.action(t, x, y_d) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(y_h, y_d)
