@@ -148,6 +148,16 @@ FSP_API int fspvec_nordsieck(double *const *Z_dev_ptrs, int L, const double *sca
 FSP_API int fspvec_multi_axpy(double *const *Z_dev_ptrs, int L, const double *coef_host, const double *x_dev, long n,
                               void *stream);
 /* host-result conveniences (synchronise `stream`) */
+/* Post-processing on the device (src/Fsp/DiscreteDistribution.cpp:171-200, src/SensFsp/SensDiscreteDistribution.cpp:216-271):
+ *   marginal      out_dev[b] = sum of p over the states whose coordinate `species` equals b, b < M (deterministic order)
+ *   max_species   *out_neg_dev = -(largest coordinate `species` over the n states)
+ *   clamp_min     x_i = max(x_i, lo); *count_out_dev = number of entries raised (ComputeFIM's 1e-16 floor on p)
+ *   wdiv_dot      sum_i x_i y_i / w_i  (one Fisher-information entry: x = dp/dtheta_i, y = dp/dtheta_j, w = p) */
+FSP_API int fspvec_marginal(double *out_dev, int M, const double *p_dev, const int *states_dev, int S, int species, long n,
+                            void *stream);
+FSP_API int fspvec_max_species(double *out_neg_dev, const int *states_dev, int S, int species, long n, void *stream);
+FSP_API int fspvec_clamp_min(double *count_out_dev, double *x_dev, double lo, long n, void *stream);
+FSP_API int fspvec_wdiv_dot(double *out_dev, const double *x_dev, const double *y_dev, const double *w_dev, long n, void *stream);
 FSP_API int fspvec_dot_h(double *out_host, const double *x_dev, const double *y_dev, long n, void *stream);
 FSP_API int fspvec_norm2_h(double *out_host, const double *x_dev, long n, void *stream);
 FSP_API int fspvec_sum_h(double *out_host, const double *x_dev, long n, void *stream);
@@ -335,6 +345,15 @@ FSP_API int fspmat_set_variant(fspmat_t h, int variant);
 FSP_API int fspmat_build_ghosts(int *col_dev, long n_entries, int own_start, int own_end, int **ghost_gid_dev_out,
                                 long *n_ghost);
 FSP_API int fspmat_shift_indices(int *idx_dev, long n, int delta);
+/* Assembled A(t) in CSR form on the device (the PETSc Mat of CreateRHSJacobian / ComputeRHSJacobian,
+ * src/Matrix/FspMatrixBase.cpp:308-427, FspMatrixConstrained.cpp:304-445): (P + 1) slots per state row (diagonal, then
+ * one per reaction plane; entries on the same (i, j) stay separate slots and simply add in a product), the K sink rows
+ * behind them.  structure != 0 writes row_ptr (n_rows + 1) and col as well; structure == 0 only refreshes val. */
+FSP_API int fspmat_csr_size(fspmat_t h, long *nnz, int *n_rows);
+FSP_API int fspmat_csr_export(fspmat_t h, const double *coef_host, int structure, int *row_ptr_dev, int *col_dev,
+                              double *val_dev, void *stream);
+FSP_API int fspmat_csr_spmv(int n_rows, const int *row_ptr_dev, const int *col_dev, const double *val_dev,
+                            const double *x_dev, double *y_dev, void *stream);
 /* dense export for tests: out_host is n_rows x n_rows column-major (ghost columns dropped) */
 FSP_API int fspmat_dense(fspmat_t h, const double *coef_host, double *out_host);
 

@@ -95,6 +95,10 @@ SIGNATURES = {
     "fspvec_newton_update": (ci, [vp, vp, vp, vp, vp, vp, vp, cl, vp]),
     "fspvec_nordsieck": (ci, [vp, ci, vp, ci, cl, vp]),
     "fspvec_multi_axpy": (ci, [vp, ci, vp, vp, cl, vp]),
+    "fspvec_marginal": (ci, [vp, ci, vp, vp, ci, ci, cl, vp]),
+    "fspvec_max_species": (ci, [vp, vp, ci, ci, cl, vp]),
+    "fspvec_clamp_min": (ci, [vp, vp, cd, cl, vp]),
+    "fspvec_wdiv_dot": (ci, [vp, vp, vp, vp, cl, vp]),
     "fspvec_dot_h": (ci, [dp, vp, vp, cl, vp]),
     "fspvec_norm2_h": (ci, [dp, vp, cl, vp]),
     "fspvec_sum_h": (ci, [dp, vp, cl, vp]),
@@ -140,6 +144,9 @@ SIGNATURES = {
     "fspmat_action_bytes": (ci, [vp, dp]),
     "fspmat_set_variant": (ci, [vp, ci]),
     "fspmat_dense": (ci, [vp, dp, dp]),
+    "fspmat_csr_size": (ci, [vp, lp, ip]),
+    "fspmat_csr_export": (ci, [vp, dp, ci, vp, vp, vp, vp]),
+    "fspmat_csr_spmv": (ci, [ci, vp, vp, vp, vp, vp, vp]),
     "fspmat_build_ghosts": (ci, [vp, cl, ci, ci, vpp, lp]),
     "fspmat_shift_indices": (ci, [vp, cl, ci]),
     "fspcomm_unique_id": (ci, [C.c_char_p]),

@@ -794,6 +794,38 @@ __global__ void mark_chunk_kernel(const int *__restrict__ rows, long n_rows, lon
   long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n_rows) flag[rows[q] / chunk_rows] = 1;
 }
+// ---- assembled Jacobian in CSR form (CreateRHSJacobian / ComputeRHSJacobian) ---------------------------------------
+// state row i: slot 0 = diagonal, slot 1 + p = plane p (an absent neighbour keeps column i with value 0); P + 1 slots
+__global__ void csr_state_rows_kernel(MatView m, Coefs cf, int structure, int *__restrict__ row_ptr, int *__restrict__ col,
+                                      double *__restrict__ val) {
+  const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m.n) return;
+  const long base = i * (m.P + 1);
+  double     d = 0.0;
+  for (int g = 0; g < m.ND; ++g) d = fma(cf.cd[g], m.diag[(size_t) g * m.ld + i], d);
+  if (structure) { row_ptr[i] = (int) base; col[base] = (int) i; }
+  val[base] = -d;
+  for (int p = 0; p < m.P; ++p) {
+    const int c = m.col[(size_t) p * m.ld + i];
+    if (structure) col[base + 1 + p] = c >= 0 ? c : (int) i;
+    val[base + 1 + p] = c >= 0 ? cf.c[p] * m.off[(size_t) p * m.ld + i] : 0.0;
+  }
+}
+__global__ void csr_sink_segment_kernel(const int *__restrict__ idx, const double *__restrict__ v, long count, double coef,
+                                        int structure, int *__restrict__ col, double *__restrict__ val) {
+  const long q = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  if (structure) col[q] = idx[q];
+  val[q] = coef * v[q];
+}
+__global__ void csr_spmv_kernel(int n_rows, const int *__restrict__ row_ptr, const int *__restrict__ col,
+                                const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  double acc = 0.0;
+  for (int q = row_ptr[i]; q < row_ptr[i + 1]; ++q) acc = fma(val[q], __ldg(x + col[q]), acc);
+  y[i] = acc;
+}
 struct RowHasGhost {
   const int *col; long ld; int P;
   __host__ __device__ bool operator()(const int &i) const {
@@ -1400,6 +1432,62 @@ int fspmat_build_ghosts(int *col, long n, int lo, int hi, int **ghost_out, long 
 int fspmat_shift_indices(int *idx, long n, int delta) {
   if (n <= 0) return 0;
   shift_idx_kernel<<<(unsigned) ((n + 255) / 256), 256>>>(idx, n, delta);
+  FSP_LAUNCH_CHECK();
+  return 0;
+}
+
+// Assembled A(t) as CSR on the device (src/Matrix/FspMatrixBase.cpp:308-427, FspMatrixConstrained.cpp:304-445).
+// Layout: every state row has P + 1 slots (diagonal first, then one per reaction plane); the K sink rows list the
+// boundary entries of their constraint group by group.  structure != 0 also writes row_ptr / col (CreateRHSJacobian);
+// structure == 0 refreshes the values for new coefficients only (ComputeRHSJacobian).
+int fspmat_csr_size(fspmat_t h, long *nnz, int *n_rows) {
+  long z = (long) h->n * (h->P + 1);
+  if (h->K > 0 && h->owns_sinks) z += h->sink_nnz;
+  *nnz = h->has_values ? z : 0;
+  *n_rows = h->n_rows;
+  return 0;
+}
+int fspmat_csr_export(fspmat_t h, const double *coef_host, int structure, int *row_ptr, int *col, double *val, void *stream) {
+  cudaStream_t st = resolve_stream(stream);
+  if (h->n_ghost > 0) { set_error("fspmat_csr_export: operators with ghost columns have no assembled form"); return -1; }
+  if (!h->has_values) {
+    if (structure) FSP_CUDA_CHECK(cudaMemsetAsync(row_ptr, 0, sizeof(int) * ((size_t) h->n_rows + 1), st));
+    return 0;
+  }
+  Coefs cf; MatView m;
+  fill_coefs_view(h, coef_host, cf, m);
+  if (h->n > 0) {
+    csr_state_rows_kernel<<<(unsigned) ((h->n + 255) / 256), 256, 0, st>>>(m, cf, structure, row_ptr, col, val);
+    FSP_LAUNCH_CHECK();
+  }
+  const long base = (long) h->n * (h->P + 1);
+  std::vector<int> tail;  // row_ptr[n .. n_rows]
+  long at = base;
+  if (h->K > 0 && h->owns_sinks) {
+    for (int k = 0; k < h->K; ++k) {
+      tail.push_back((int) at);
+      for (int g = 0; g < h->ND; ++g) {
+        const long b = h->seg_ptr[(size_t) g * h->K + k], e = h->seg_ptr[(size_t) g * h->K + k + 1];
+        if (e > b) {
+          csr_sink_segment_kernel<<<(unsigned) ((e - b + 255) / 256), 256, 0, st>>>(h->d_sink_idx + b, h->d_sink_val + b, e - b, cf.cd[g],
+                                                                                   structure, col + at, val + at);
+          FSP_LAUNCH_CHECK();
+          at += e - b;
+        }
+      }
+    }
+  } else {
+    for (int r = h->n; r < h->n_rows; ++r) tail.push_back((int) at);
+  }
+  tail.push_back((int) at);
+  if (structure)
+    FSP_CUDA_CHECK(cudaMemcpyAsync(row_ptr + h->n, tail.data(), sizeof(int) * tail.size(), cudaMemcpyHostToDevice, st));
+  FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+int fspmat_csr_spmv(int n_rows, const int *row_ptr, const int *col, const double *val, const double *x, double *y, void *stream) {
+  if (n_rows <= 0) return 0;
+  csr_spmv_kernel<<<(unsigned) ((n_rows + 255) / 256), 256, 0, resolve_stream(stream)>>>(n_rows, row_ptr, col, val, x, y);
   FSP_LAUNCH_CHECK();
   return 0;
 }

@@ -438,6 +438,68 @@ int launch_map2(F2 f, long n2, void *stream) {
   return 0;
 }
 
+// ---- post-processing on the device (DiscreteDistribution / SensDiscreteDistribution) ------------------------------
+struct ClampCountF {  // x_i = max(x_i, lo); counts the entries that were raised
+  double *x; double lo;
+  __device__ void operator()(long i, double (&acc)[1]) const {
+    if (x[i] < lo) { x[i] = lo; acc[0] += 1.0; }
+  }
+};
+struct WdivDotF {  // sum_i x_i y_i / w_i
+  const double *x, *y, *w;
+  __device__ void operator()(long i, double (&acc)[1]) const { acc[0] += x[i] * y[i] / w[i]; }
+};
+
+// 1-D marginal: out[b] = sum_{i : states[i][species] == b} p[i].  Deterministic: every warp owns a contiguous slice of
+// the states and a private row of bins in shared memory; inside a warp the lanes that hit the same bin are combined in
+// lane order by the lowest such lane (match_any + shuffles), so no two lanes ever update the same bin concurrently;
+// the per-warp rows are then added in warp order, the per-CTA rows in CTA order (second kernel).
+constexpr int kMargWarps = 8;
+__global__ void __launch_bounds__(kMargWarps * 32) marginal_partial_kernel(const double *__restrict__ p, const int *__restrict__ states,
+                                                                           int S, int species, long n, int M, long per_cta,
+                                                                           double *__restrict__ partial) {
+  extern __shared__ double bins[];  // [kMargWarps][M]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double   *mine = bins + (size_t) warp * M;
+  for (int b = lane; b < M; b += 32) mine[b] = 0.0;
+  __syncwarp();
+  const long begin = (long) blockIdx.x * per_cta, end = min(n, begin + per_cta);
+  const long per_warp = (per_cta + kMargWarps - 1) / kMargWarps;
+  const long wb = begin + (long) warp * per_warp, we = min(end, wb + per_warp);
+  for (long base = wb; base < we; base += 32) {
+    const long i = base + lane;
+    const bool ok = i < we;
+    const int  b = ok ? states[(size_t) i * S + species] : -1;
+    const double v = ok ? p[i] : 0.0;
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int      leader = __ffs(peers) - 1;
+    double         s = 0.0;
+    for (unsigned m = peers; m; m &= m - 1) {  // lane order; every lane runs the loop of ITS peer group
+      const int src = __ffs(m) - 1;
+      s += __shfl_sync(peers, v, src);
+    }
+    if (lane == leader && b >= 0 && b < M) mine[b] += s;
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < M; b += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < kMargWarps; ++w) s += bins[(size_t) w * M + b];
+    partial[(size_t) blockIdx.x * M + b] = s;
+  }
+}
+__global__ void marginal_final_kernel(const double *__restrict__ partial, int n_cta, int M, double *__restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= M) return;
+  double s = 0.0;
+  for (int c = 0; c < n_cta; ++c) s += partial[(size_t) c * M + b];
+  out[b] = s;
+}
+struct MaxSpeciesF {  // min of the negated value == max (RED_MIN machinery)
+  const int *states; int S, species;
+  __device__ void operator()(long i, double (&acc)[1]) const { acc[0] = fmin(acc[0], -(double) states[(size_t) i * S + species]); }
+};
+
 template <int M>
 int mdot_impl(double *out, const double *x, const double *const *Y, long n, void *stream) {
   MdotF<M> f;
@@ -519,6 +581,37 @@ int fspvec_mdot(double *out, const double *x, int m, const double *const *Y, lon
     case 8: return mdot_impl<8>(out, x, Y, n, s);
     default: set_error("fspvec_mdot: m=%d out of range (1..8)", m); return -1;
   }
+}
+
+// ---- post-processing (src/Fsp/DiscreteDistribution.cpp:171-200, src/SensFsp/SensDiscreteDistribution.cpp:216-271) ----
+int fspvec_clamp_min(double *count_out, double *x, double lo, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(ClampCountF{x, lo}, n, count_out, s);
+}
+int fspvec_wdiv_dot(double *out, const double *x, const double *y, const double *w, long n, void *s) {
+  return launch_reduce<1, RED_SUM>(WdivDotF{x, y, w}, n, out, s);
+}
+int fspvec_max_species(double *out_neg, const int *states, int S, int species, long n, void *s) {
+  return launch_reduce<1, RED_MIN>(MaxSpeciesF{states, S, species}, n, out_neg, s);
+}
+int fspvec_marginal(double *out, int M, const double *p, const int *states, int S, int species, long n, void *stream) {
+  if (M <= 0) return 0;
+  cudaStream_t st = resolve_stream(stream);
+  if ((size_t) M * kMargWarps * sizeof(double) > 96 * 1024) { set_error("fspvec_marginal: %d bins exceed the shared-memory rows", M); return -1; }
+  if (n <= 0) { FSP_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * M, st)); return 0; }
+  const int  n_cta = (int) std::max<long>(1, std::min<long>((n + 4095) / 4096, 4L * sm_count()));
+  const long per_cta = (n + n_cta - 1) / n_cta;
+  double    *partial = nullptr;
+  FSP_CUDA_CHECK(pmalloc(&partial, sizeof(double) * (size_t) n_cta * M));
+  const size_t smem = (size_t) M * kMargWarps * sizeof(double);
+  if (smem > 48 * 1024)
+    FSP_CUDA_CHECK(cudaFuncSetAttribute(marginal_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  marginal_partial_kernel<<<n_cta, kMargWarps * 32, smem, st>>>(p, states, S, species, n, M, per_cta, partial);
+  FSP_LAUNCH_CHECK();
+  marginal_final_kernel<<<(M + 127) / 128, 128, 0, st>>>(partial, n_cta, M, out);
+  FSP_LAUNCH_CHECK();
+  FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+  pfree(partial);
+  return 0;
 }
 
 int fspvec_dot(double *out, const double *x, const double *y, long n, void *s) {

@@ -12,6 +12,9 @@ struct PACMENSL_API DiscreteDistribution {
   double         t_ = 0.0;
   arma::Mat<int> states_;
   Vec            p_ = nullptr;
+  /// device copy of states_ (taken from the state set's device array at construction, shared between copies): lets the
+  /// post-processing reductions (Compute1DMarginal, Compute1DSensMarginal) run on the GPU next to p_
+  std::shared_ptr<DeviceBuffer<int>> states_dev_;
 
   DiscreteDistribution();
   DiscreteDistribution(MPI_Comm comm, double t, const StateSetBase *state_set, const Vec &p);
@@ -30,4 +33,6 @@ struct PACMENSL_API DiscreteDistribution {
 };
 
 PACMENSL_API arma::Col<PetscReal> Compute1DMarginal(const DiscreteDistribution &dist, int species);
+/// shared implementation: marginal of an arbitrary device vector v (p_ or a sensitivity) over dist's states
+PACMENSL_API PacmenslErrorCode ComputeMarginalOf(const DiscreteDistribution &dist, Vec v, int species, arma::Col<PetscReal> &out);
 }  // namespace pacmensl

@@ -5,20 +5,9 @@
 #include <cstdlib>
 
 PetscErrorCode MatMult(Mat A, Vec x, Vec y) {
-  // dense host product for the small test matrices produced by ComputeRHSJacobian
-  const PetscScalar *xa;
-  PetscScalar       *ya;
-  PetscErrorCode     ierr = VecGetArrayRead(x, &xa);
-  if (ierr) return ierr;
-  std::vector<double> xs(xa, xa + x->n_local);
-  VecRestoreArrayRead(x, &xa);
-  ierr = VecGetArray(y, &ya);
-  if (ierr) return ierr;
-  const arma::Mat<double> &J = A->dense;
-  for (arma::uword i = 0; i < J.n_rows; ++i) ya[i] = 0.0;
-  for (arma::uword j = 0; j < J.n_cols; ++j)
-    for (arma::uword i = 0; i < J.n_rows; ++i) ya[i] += J(i, j) * xs[j];
-  return VecRestoreArray(y, &ya);
+  // y = J x with the assembled CSR Jacobian (device SpMV)
+  if (!A || x->n_local != A->n_rows || y->n_local != A->n_rows) return -1;
+  return fspmat_csr_spmv(A->n_rows, A->row_ptr.get(), A->col.get(), A->val.get(), x->d_data, y->d_data, x->comm ? x->comm->stream : nullptr);
 }
 PetscErrorCode MatDestroy(Mat *A) {
   if (A && *A) delete *A;
@@ -729,26 +718,39 @@ PacmenslErrorCode FspMatrixBase::ActionHostPartitioned_(const double *coefs, con
   return 0;
 }
 
-// src/Matrix/FspMatrixBase.cpp:308-427 -- dense host stand-in (tests only)
+// src/Matrix/FspMatrixBase.cpp:308-427 (+ FspMatrixConstrained.cpp:304-445 for the sink rows): the assembled A(t) as a
+// CSR matrix on the device.  Single rank only: the multi-GPU operator keeps ghost slots, not global columns.
 PacmenslErrorCode FspMatrixBase::CreateRHSJacobian(Mat *A) {
-  if (comm_size_ > 1 || num_rows_local_ > 20000) {
-    printf("CreateRHSJacobian: the assembled Jacobian is only provided for small single-rank problems.\n");
+  if (comm_size_ > 1) {
+    printf("CreateRHSJacobian: the assembled Jacobian is provided on a single rank only.\n");
     return -1;
   }
-  *A = new _p_Mat();
-  (*A)->comm = comm_;
-  (*A)->dense.zeros(num_rows_local_, num_rows_local_);
+  if (!dmat_) return -1;
+  Mat J = new _p_Mat();
+  J->comm = comm_;
+  FSPCHKERRQ(fspmat_csr_size(dmat_, &J->nnz, &J->n_rows));
+  J->n_rows = num_rows_local_;
+  if (J->row_ptr.resize((size_t) J->n_rows + 1) || J->col.resize((size_t) std::max<long>(J->nnz, 1)) ||
+      J->val.resize((size_t) std::max<long>(J->nnz, 1))) { delete J; return -1; }
+  time_coefficients_.fill(1.0);
+  if (fspmat_csr_export(dmat_, time_coefficients_.memptr(), 1, J->row_ptr.get(), J->col.get(), J->val.get(), comm_ ? comm_->stream : nullptr)) {
+    delete J;
+    return -1;
+  }
+  *A = J;
   return 0;
 }
 PacmenslErrorCode FspMatrixBase::ComputeRHSJacobian(PetscReal t, Mat A) {
-  if (!A) return -1;
+  if (!A || !dmat_) return -1;
   if (!tv_reactions_.empty()) {
     int ierr = t_fun_(t, num_reactions_, time_coefficients_.memptr(), t_fun_args_);
     PACMENSLCHKERRQ(ierr);
   }
-  A->dense.zeros(num_rows_local_, num_rows_local_);
-  if (has_values_ == PETSC_FALSE) return 0;
-  FSPCHKERRQ(fspmat_dense(dmat_, time_coefficients_.memptr(), A->dense.memptr()));
+  long nnz = 0;
+  int  nr = 0;
+  FSPCHKERRQ(fspmat_csr_size(dmat_, &nnz, &nr));
+  if (nnz != A->nnz || num_rows_local_ != A->n_rows) return -1;  // the operator was regenerated: create a new Jacobian
+  FSPCHKERRQ(fspmat_csr_export(dmat_, time_coefficients_.memptr(), 0, A->row_ptr.get(), A->col.get(), A->val.get(), comm_ ? comm_->stream : nullptr));
   return 0;
 }
 

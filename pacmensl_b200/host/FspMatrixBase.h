@@ -9,11 +9,14 @@
 #include "StateSetConstrained.h"
 #include "Sys.h"
 
-// Small dense host matrix standing in for PETSc's Mat in CreateRHSJacobian/ComputeRHSJacobian
-// (only used by tests on small problems; the assembled-Jacobian TsFsp path is out of scope).
+// The PETSc Mat of CreateRHSJacobian / ComputeRHSJacobian (src/Matrix/FspMatrixBase.cpp:308-427): the assembled
+// A(t) in CSR form on the device (fspmat_csr_export), applied by MatMult with a device SpMV.
 struct _p_Mat {
-  arma::Mat<double> dense;
-  MPI_Comm          comm = nullptr;
+  MPI_Comm                           comm = nullptr;
+  int                                n_rows = 0;
+  long                               nnz = 0;
+  pacmensl::DeviceBuffer<int>        row_ptr, col;
+  pacmensl::DeviceBuffer<double>     val;
 };
 typedef _p_Mat *Mat;
 extern "C" {

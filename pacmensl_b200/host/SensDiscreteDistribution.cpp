@@ -70,14 +70,35 @@ PacmenslErrorCode SensDiscreteDistribution::WeightedAverage(
 
 PacmenslErrorCode Compute1DSensMarginal(const SensDiscreteDistribution &dist, int is, int species, arma::Col<PetscReal> &out) {
   if (is < 0 || is >= (int) dist.dp_.size()) return -1;
-  double mx = 0.0;
-  for (arma::uword i = 0; i < dist.states_.n_cols; ++i) mx = std::max(mx, (double) dist.states_(species, i));
-  pacmensl_allreduce_max(dist.comm_, &mx, 1);
-  out = arma::Col<PetscReal>((arma::uword) mx + 1, arma::fill::zeros);
-  const PetscReal *p_dat;
-  VecGetArrayRead(dist.dp_[is], &p_dat);
-  for (arma::uword i{0}; i < dist.states_.n_cols; ++i) out(dist.states_(species, i)) += p_dat[i];
-  VecRestoreArrayRead(dist.dp_[is], &p_dat);
-  return pacmensl_allreduce_sum(dist.comm_, out.memptr(), (int) out.n_elem);
+  return ComputeMarginalOf(dist, dist.dp_[is], species, out);  // device segmented reduction (DiscreteDistribution.cpp)
+}
+
+// src/SensFsp/SensDiscreteDistribution.cpp:216-271: FIM(i, j) = sum_x s_i(x) s_j(x) / p(x), with the reference's in-place
+// floor p(x) := max(p(x), 1e-16) (it writes the floored values back through its array view) and its warning.  Here each
+// entry is one fused device reduction over (s_i, s_j, p) with a fixed summation shape; nothing but P(P+1)/2 scalars
+// crosses to the host.
+PacmenslErrorCode ComputeFIM(SensDiscreteDistribution &dist, arma::Mat<PetscReal> &fim) {
+  const int P = (int) dist.dp_.size();
+  if (!fim.is_empty() && ((int) fim.n_rows != P || (int) fim.n_cols != P)) return -1;
+  if (fim.is_empty()) fim.set_size(P, P);
+  if (P == 0) return 0;
+  void      *stream = dist.comm_ ? dist.comm_->stream : nullptr;
+  const long n = dist.p_->n_local;
+  DeviceBuffer<double> tmp((size_t) P * P + 1);
+  FSPCHKERRQ(fspvec_clamp_min(tmp.get() + (size_t) P * P, dist.p_->d_data, 1.0e-16, n, stream));
+  for (int i = 0; i < P; ++i)
+    for (int j = 0; j <= i; ++j)
+      FSPCHKERRQ(fspvec_wdiv_dot(tmp.get() + (size_t) j * P + i, dist.dp_[i]->d_data, dist.dp_[j]->d_data, dist.p_->d_data, n, stream));
+  std::vector<double> host((size_t) P * P + 1, 0.0);
+  FSPCHKERRQ(fsp_memcpy_d2h(host.data(), tmp.get(), sizeof(double) * host.size(), stream));
+  std::vector<double> low;
+  for (int i = 0; i < P; ++i) for (int j = 0; j <= i; ++j) low.push_back(n > 0 ? host[(size_t) j * P + i] : 0.0);
+  low.push_back(n > 0 ? host[(size_t) P * P] : 0.0);
+  int ierr = pacmensl_allreduce_sum(dist.comm_, low.data(), (int) low.size());
+  PACMENSLCHKERRQ(ierr);
+  size_t q = 0;
+  for (int i = 0; i < P; ++i) for (int j = 0; j <= i; ++j) { fim(i, j) = low[q]; fim(j, i) = low[q]; ++q; }
+  if (low[q] > 0.0) PetscPrintf(dist.comm_, "Warning: rounding was done in FIM computation.\n");
+  return 0;
 }
 }  // namespace pacmensl

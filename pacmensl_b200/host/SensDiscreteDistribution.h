@@ -26,4 +26,7 @@ class PACMENSL_API SensDiscreteDistribution : public DiscreteDistribution {
 
 PACMENSL_API PacmenslErrorCode Compute1DSensMarginal(const SensDiscreteDistribution &dist, int is, int species,
                                                      arma::Col<PetscReal> &out);
+/// Fisher information matrix of the distribution w.r.t. its parameters (src/SensFsp/SensDiscreteDistribution.cpp:216-271),
+/// computed on the device; like the reference it floors p at 1e-16 IN PLACE and warns when it had to.
+PACMENSL_API PacmenslErrorCode ComputeFIM(SensDiscreteDistribution &dist, arma::Mat<PetscReal> &fim);
 }  // namespace pacmensl

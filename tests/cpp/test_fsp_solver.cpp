@@ -200,3 +200,38 @@ TEST_F(FspPoissonTest, solve_tspan_and_restart_from_distribution) {
   DiscreteDistribution p_final = fsp2.Solve(5.0, fsp_tol, 0);
   ASSERT_LE(poisson_l1_error(p_final), 3 * fsp_tol);
 }
+
+// Device-side post-processing: Compute1DMarginal (src/Fsp/DiscreteDistribution.cpp:171-200) as a
+// deterministic segmented reduction on the GPU must equal the reference's host loop over (states_, p_).
+TEST_F(FspTest, device_marginals_equal_the_host_loop) {
+  FspSolverMultiSinks fsp(PETSC_COMM_WORLD);
+  ASSERT_FALSE(fsp.SetModel(toggle_model));
+  ASSERT_FALSE(fsp.SetInitialBounds(fsp_size));
+  ASSERT_FALSE(fsp.SetExpansionFactors(expansion_factors));
+  ASSERT_FALSE(fsp.SetInitialDistribution(X0, p0));
+  ASSERT_FALSE(fsp.SetOdesType(KRYLOV));
+  DiscreteDistribution d = fsp.Solve(20.0, 1.0e-6, 0);
+  fsp.ClearState();
+  ASSERT_TRUE((bool) d.states_dev_);
+  const PetscScalar *p;
+  ASSERT_FALSE(VecGetArrayRead(d.p_, &p));
+  for (int species = 0; species < 2; ++species) {
+    arma::Col<PetscReal> md = Compute1DMarginal(d, species);
+    int mx = 0;
+    for (arma::uword i = 0; i < d.states_.n_cols; ++i) mx = std::max(mx, d.states_(species, i));
+    std::vector<double> ref((size_t) mx + 1, 0.0);
+    for (arma::uword i = 0; i < d.states_.n_cols; ++i) ref[(size_t) d.states_(species, i)] += p[i];
+    pacmensl_allreduce_sum(PETSC_COMM_WORLD, ref.data(), (int) ref.size());
+    ASSERT_EQ((int) md.n_elem, mx + 1);
+    double gap = 0.0, tot = 0.0;
+    for (int b = 0; b <= mx; ++b) { gap = std::max(gap, std::fabs(md[b] - ref[(size_t) b])); tot += md[b]; }
+    std::printf("    marginal of species %d: %d bins, max |device - host| = %.2e, sum = %.12f\n", species, mx + 1, gap, tot);
+    ASSERT_LE(gap, 1.0e-15);
+    ASSERT_NEAR(tot, 1.0, 1.0e-5);
+    // a second evaluation gives the same bits (fixed summation order)
+    arma::Col<PetscReal> md2 = Compute1DMarginal(d, species);
+    for (int b = 0; b <= mx; ++b) ASSERT_TRUE(md[b] == md2[b]);
+  }
+  VecRestoreArrayRead(d.p_, &p);
+}
+

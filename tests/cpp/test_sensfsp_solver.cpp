@@ -73,6 +73,40 @@ TEST_F(SensFspToggleTest, toggle_sens_solve_with_cvode) {
     ASSERT_FALSE(VecSum(p_final_bdf.dp_[i], &stmp));
     ASSERT_LE(std::abs(stmp), 1.0e-6);
   }
+  // device-side post-processing: the Fisher information matrix and a sensitivity marginal against the
+  // reference's host loops (src/SensFsp/SensDiscreteDistribution.cpp:170-271)
+  const int n = (int) p_final_bdf.states_.n_cols;
+  std::vector<std::vector<double>> s(6);
+  std::vector<double>              p(n);
+  {
+    const PetscScalar *a;
+    ASSERT_FALSE(VecGetArrayRead(p_final_bdf.p_, &a));
+    for (int k = 0; k < n; ++k) p[k] = std::max(a[k], 1.0e-16);
+    VecRestoreArrayRead(p_final_bdf.p_, &a);
+    for (int i = 0; i < 6; ++i) {
+      ASSERT_FALSE(VecGetArrayRead(p_final_bdf.dp_[i], &a));
+      s[i].assign(a, a + n);
+      VecRestoreArrayRead(p_final_bdf.dp_[i], &a);
+    }
+  }
+  arma::Mat<PetscReal> fim;
+  ASSERT_FALSE(ComputeFIM(p_final_bdf, fim));
+  double worst = 0.0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) {
+      double ref = 0.0;
+      for (int k = 0; k < n; ++k) ref += s[i][k] * s[j][k] / p[k];
+      pacmensl_allreduce_sum(PETSC_COMM_WORLD, &ref, 1);
+      worst = std::max(worst, std::fabs(fim(i, j) - ref) / (std::fabs(ref) + 1e-300));
+    }
+  std::printf("    FIM on the device vs host loop: max relative difference %.2e (fim(0,0) = %.6e)\n", worst, fim(0, 0));
+  ASSERT_LE(worst, 1.0e-12);
+  arma::Col<PetscReal> sm;
+  ASSERT_FALSE(Compute1DSensMarginal(p_final_bdf, 2, 0, sm));
+  std::vector<double> ref(sm.n_elem, 0.0);
+  for (int k = 0; k < n; ++k) ref[(size_t) p_final_bdf.states_(0, k)] += s[2][k];
+  pacmensl_allreduce_sum(PETSC_COMM_WORLD, ref.data(), (int) ref.size());
+  for (arma::uword b = 0; b < sm.n_elem; ++b) ASSERT_NEAR(sm[b], ref[b], 1.0e-14 * (1.0 + std::fabs(ref[b])));
 }
 
 class SensFspPoissonTest : public ::testing::Test {

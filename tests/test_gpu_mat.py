@@ -307,3 +307,44 @@ def test_device_propensity_form_is_bit_identical_to_host_callbacks(cuda, name, b
     assert A_h.action(t, x, y_h) == 0 and A_d.action(t, x, y_d) == 0
     torch.cuda.synchronize()
     assert torch.equal(y_h, y_d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,bounds", [("hog1p", [3, 9, 9, 8, 8]), ("birth_death_3d_tv", [30, 20, 25]), ("toggle_custom", [40, 40, 60])])
+def test_csr_jacobian_export_equals_action(cuda, oracle, name, bounds):
+    """The assembled Jacobian (CreateRHSJacobian / ComputeRHSJacobian, reference src/Matrix/FspMatrixBase.cpp:308-427,
+    FspMatrixConstrained.cpp:304-445) as a device CSR matrix: J(t) x == Action(t, x) to rounding (KAT-M5's property) on
+    sets well beyond the 20 000-row limit of round 1's dense stand-in, with time-varying coefficients refreshed in place."""
+    import ctypes as C
+    import numpy as np
+    from helpers import device_matrix_from_oracle, rel_err
+    from pacmensl_b200 import _capi
+    torch = cuda
+    O = oracle
+    L = _capi.lib()
+    so = O.StateSet(fixture=name, bounds=bounds)
+    assert so.expand() == 0
+    A = O.FspMatrix(constrained=True)
+    assert A.generate_fixture(so, name) == 0
+    M = device_matrix_from_oracle(A, so.R)
+    nnz, nr = C.c_long(), C.c_int()
+    assert L.fspmat_csr_size(M.h, C.byref(nnz), C.byref(nr)) == 0
+    assert nr.value == A.nrows and nnz.value > 0
+    row_ptr = torch.empty(nr.value + 1, dtype=torch.int32, device="cuda")
+    col = torch.empty(nnz.value, dtype=torch.int32, device="cuda")
+    val = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
+    x = torch.rand(nr.value, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(11))
+    y_csr, y_act = torch.empty_like(x), torch.empty_like(x)
+    vp = C.c_void_p
+    for k, t in enumerate((0.0, 0.7, 30.0)):
+        coef = np.ascontiguousarray(O.fixture_tcoef(name, t, so.R)[1])
+        assert L.fspmat_csr_export(M.h, coef.ctypes.data_as(C.POINTER(C.c_double)), 1 if k == 0 else 0, vp(row_ptr.data_ptr()),
+                                   vp(col.data_ptr()), vp(val.data_ptr()), None) == 0
+        assert L.fspmat_csr_spmv(nr.value, vp(row_ptr.data_ptr()), vp(col.data_ptr()), vp(val.data_ptr()), vp(x.data_ptr()),
+                                 vp(y_csr.data_ptr()), None) == 0
+        M.action(coef, x, y_act)
+        torch.cuda.synchronize()
+        assert int(row_ptr[-1]) == nnz.value and int(col.min()) >= 0 and int(col.max()) < nr.value
+        assert rel_err(y_csr.cpu().numpy(), y_act.cpu().numpy()) <= 1e-14
+        ierr, y_or = A.action(t, x.cpu().numpy())
+        assert rel_err(y_csr.cpu().numpy(), y_or) <= 1e-12
