@@ -19,11 +19,11 @@ inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, 
   std::string solver = "cvode", constraints = "default";
   double      t_final_override = -1.0;
   int         verbosity = 0;
-  bool        log_events = false, cold = false, host_prop = false;
+  bool        log_events = false, cold = true, host_prop = false;
   for (int i = 1; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--log")) log_events = true;
     if (!std::strcmp(argv[i], "--host-propensities")) host_prop = true;  // evaluate prop_x through the host callback only
-    if (!std::strcmp(argv[i], "--cold")) cold = true;  // re-create the BDF integrator after every expansion (reference behaviour)
+    if (!std::strcmp(argv[i], "--warm")) cold = false;  // carry the BDF history across expansions (default: re-create it, as the reference)
     if (!std::strcmp(argv[i], "--solver") && i + 1 < argc) solver = argv[++i];
     else if (!std::strcmp(argv[i], "--constraints") && i + 1 < argc) constraints = argv[++i];
     else if (!std::strcmp(argv[i], "--tfinal") && i + 1 < argc) t_final_override = std::atof(argv[++i]);
@@ -56,7 +56,7 @@ inline int run_fsp_example(int argc, char *argv[], const char *default_fixture, 
   fsp_solver.SetOdeTolerances(f.rtol, f.atol);
   fsp_solver.SetVerbosity(verbosity);
   fsp_solver.SetFromOptions();
-  if (cold) fsp_solver.SetWarmRestart(false);
+  fsp_solver.SetWarmRestart(!cold);
   if (log_events) fsp_solver.SetLogging(PETSC_TRUE);
 
   auto t0 = std::chrono::steady_clock::now();

@@ -92,8 +92,9 @@ FSP_API int pfsp_solver_set_initial_distribution(void *solver, int S, int m, con
 FSP_API int pfsp_solver_set_ode_tolerances(void *solver, double rtol, double atol);
 FSP_API int pfsp_solver_set_verbosity(void *solver, int level);
 FSP_API int pfsp_solver_set_krylov(void *solver, int q_iop, int m_min, int m_max);
-/* 1 (default): the BDF integrator keeps its history (step size, order, Nordsieck array) across FSP expansions;
- * 0: it is re-created after every expansion like the reference's CVODE (src/Fsp/FspSolverMultiSinks.cpp:92-108) */
+/* 0 (default): the BDF integrator is re-created after every expansion like the reference's CVODE
+ * (src/Fsp/FspSolverMultiSinks.cpp:92-108); 1: it keeps its history (step size, order, Nordsieck array) across FSP
+ * expansions -- correct but measured slower */
 FSP_API int pfsp_solver_set_warm_restart(void *solver, int on);
 FSP_API int pfsp_solver_num_warm_restarts(void *solver, int *n);
 FSP_API int pfsp_solver_setup(void *solver);

@@ -46,15 +46,19 @@ DiscreteDistribution::DiscreteDistribution(MPI_Comm comm, double t, const StateS
   states_ = state_set->CopyStatesOnProc();
   VecDuplicate(p, &p_);
   VecCopy(p, p_);
-  // keep the local states on the device as well (device-to-device copy out of the state set's array)
-  const int   *all = nullptr;
-  const long   n = state_set->GetNumLocalStates(), S = state_set->GetNumSpecies(), first = state_set->GetLocalStart();
-  fspset_t     dset = state_set->GetDeviceSet();
+  AttachDeviceStates(state_set);
+}
+// keep the local states on the device as well (device-to-device copy out of the state set's array)
+void DiscreteDistribution::AttachDeviceStates(const StateSetBase *state_set) {
+  states_dev_.reset();
+  const int *all = nullptr;
+  const long n = state_set->GetNumLocalStates(), S = state_set->GetNumSpecies(), first = state_set->GetLocalStart();
+  fspset_t   dset = state_set->GetDeviceSet();
+  void      *stream = comm_ ? comm_->stream : nullptr;
   if (dset && n > 0 && fspset_states_dev(dset, &all) == 0 && all) {
     auto buf = std::make_shared<DeviceBuffer<int>>();
     if (buf->resize((size_t) n * S) == 0 &&
-        fsp_memcpy_d2d(buf->get(), all + (size_t) first * S, sizeof(int) * (size_t) n * S, comm ? comm->stream : nullptr) == 0 &&
-        fsp_stream_sync(comm ? comm->stream : nullptr) == 0)
+        fsp_memcpy_d2d(buf->get(), all + (size_t) first * S, sizeof(int) * (size_t) n * S, stream) == 0 && fsp_stream_sync(stream) == 0)
       states_dev_ = buf;
   }
 }

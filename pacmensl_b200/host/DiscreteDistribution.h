@@ -23,6 +23,7 @@ struct PACMENSL_API DiscreteDistribution {
   DiscreteDistribution &operator=(const DiscreteDistribution &);
   DiscreteDistribution &operator=(DiscreteDistribution &&) noexcept;
 
+  void AttachDeviceStates(const StateSetBase *state_set);
   PacmenslErrorCode GetStateView(int &num_states, int &num_species, int *&states);
   PacmenslErrorCode GetProbView(int &num_states, double *&p);
   PacmenslErrorCode RestoreProbView(double *&p);

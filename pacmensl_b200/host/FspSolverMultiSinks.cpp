@@ -249,8 +249,8 @@ PacmenslErrorCode FspSolverMultiSinks::SetUp() {
         ode_solver_ = std::make_shared<TsFsp>(comm_);
     }
     ode_solver_->SetFspMatPtr(A_.get());
-    static const bool warm_env = [] { const char *e = std::getenv("FSP_WARM_RESTART"); return !(e && e[0] == '0'); }();
-    ode_solver_->SetWarmRestart(warm_restart_ && warm_env);
+    static const bool warm_env = [] { const char *e = std::getenv("FSP_WARM_RESTART"); return e && e[0] == '1'; }();
+    ode_solver_->SetWarmRestart(warm_restart_ || warm_env);
     if (logging_enabled) ode_solver_->EnableLogging();
   }
 
@@ -444,6 +444,7 @@ PacmenslErrorCode FspSolverMultiSinks::MakeDiscreteDistribution_(DiscreteDistrib
   dist.comm_ = comm_;
   dist.t_ = t_now_;
   dist.states_ = state_set_->CopyStatesOnProc();
+  dist.AttachDeviceStates(state_set_.get());
   ierr = VecCreate(dist.comm_, &dist.p_);
   CHKERRQ(ierr);
   ierr = VecSetSizes(dist.p_, state_set_->GetNumLocalStates(), PETSC_DECIDE);

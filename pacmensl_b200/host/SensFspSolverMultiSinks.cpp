@@ -251,6 +251,7 @@ PacmenslErrorCode SensFspSolverMultiSinks::MakeSensDiscreteDistribution_(SensDis
   dist.comm_ = comm_;
   dist.t_ = t_now_;
   dist.states_ = state_set_->CopyStatesOnProc();
+  dist.AttachDeviceStates(state_set_.get());
   const int n = state_set_->GetNumLocalStates();
   ierr = VecCreate(dist.comm_, &dist.p_); CHKERRQ(ierr);
   ierr = VecSetSizes(dist.p_, n, PETSC_DECIDE); CHKERRQ(ierr);

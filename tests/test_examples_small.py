@@ -110,9 +110,11 @@ def _l1_by_key(states_a, p_a, states_b, p_b):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,t_final", [("pure_birth", 10.0), ("repressilator", 0.5), ("transcr_reg_6d", 10.0), ("hog1p", 30.0)])
 def test_bdf_warm_restart_across_expansions(cuda, name, t_final):
-    """after an expansion the BDF integrator continues with its Nordsieck history mapped onto the enlarged
-    state space (default) instead of restarting at order 1 like the reference's CVODE (set_warm_restart(False)).
-    Same answer within the integrator's tolerance, fewer Action calls."""
+    """with set_warm_restart(True) the BDF integrator continues after an expansion with its Nordsieck
+    history mapped onto the enlarged state space instead of restarting at order 1 like the reference's CVODE (default).
+    Asserted: every expansion carried over, same answer within the integrator's tolerance.  NOT asserted: fewer Action
+    calls -- measured on B200 it needs 8 .. 50 % MORE (the counts are printed; see DESIGN.md for why), which is why it is
+    opt-in."""
     import math
     from pacmensl_b200 import api
     api.init(0)
@@ -135,7 +137,6 @@ def test_bdf_warm_restart_across_expansions(cuda, name, t_final):
     assert wc == 0 and ww == stw["expansions"] and stw["expansions"] > 0
     assert abs(pw.sum() - 1.0) <= fsp_tol * 1.01 + 1e-8 and pw.min() > -1e-8
     assert diff <= 50 * rtol
-    assert stw["rhs_evals"] <= 0.75 * stc["rhs_evals"]
     if name == "pure_birth":  # KAT-F4 (tests/test_fsp_solver.cpp:264-345) holds with the warm restart too
         lam = 2.0 * t_final
         pdf = np.array([math.exp(-lam) * lam ** int(n) / math.gamma(int(n) + 1) for n in sw[:, 0]])
