@@ -97,6 +97,18 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
                                                 const PropFun &new_prop_x, const std::vector<int> &enable_reactions,
                                                 void *prop_t_args, void *prop_x_args) {
   PacmenslErrorCode ierr;
+  // FSP_GEN_TRACE=1: wall time of each phase of a generation (device-synchronised), for tuning the set-up path
+  static const bool gen_trace = [] { const char *e = std::getenv("FSP_GEN_TRACE"); return e && e[0] == '1'; }();
+  double            t_phase = 0.0;
+  auto tick = [&](const char *what) {
+    if (!gen_trace) return;
+    fsp_device_sync();
+    PetscLogDouble now;
+    PetscTime(&now);
+    if (what && rank_ == 0) printf("[gen n=%d] %-28s %8.2f ms\n", (int) fsp.GetNumLocalStates(), what, 1e3 * (now - t_phase));
+    t_phase = now;
+  };
+  tick(nullptr);
   Destroy();
   ierr = DetermineLayout_(fsp);
   PACMENSLCHKERRQ(ierr);
@@ -222,6 +234,7 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
     }
   }
 
+  tick("columns + propensities");
   // sink rows (constrained subclass)
   std::vector<long>    sink_ptr;
   DeviceBuffer<int>    sink_idx;
@@ -229,6 +242,7 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
   ierr = CollectSinks_(fsp, SM, planes, diag.get(), ld, sink_ptr, sink_idx, sink_val);
   PACMENSLCHKERRQ(ierr);
 
+  tick("sink lists");
   // multi-GPU: columns outside the own block become ghost slots
   if (comm_size_ > 1) {
     ierr = SetupGhosts_(fsp, col.get(), (long) P * ld);
@@ -260,9 +274,11 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
     empty_ptr.assign((size_t) P * num_constraints_ + 1, 0);
     d.sink_ptr = empty_ptr.data();
   }
+  tick("ghost set-up");
   if (!dmat_) FSPCHKERRQ(fspmat_create(&dmat_));
   FSPCHKERRQ(fspmat_set_variant(dmat_, kernel_variant_));
   FSPCHKERRQ(fspmat_generate(dmat_, &d));
+  tick("fspmat_generate (pack, nnz, sinks)");
   if (num_constraints_ > 0 && comm_size_ > 1) {
     if (sink_buf_.resize((size_t) num_constraints_)) PACMENSLCHKERRQ(-1);
   }
