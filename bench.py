@@ -442,9 +442,34 @@ def main():
             tt = torch.tensor([dt, 0.0 if e2e_ok else 1.0], dtype=torch.float64, device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt, e2e_ok = float(tt[0].item()), tt[1].item() == 0.0
+        # what the host <-> device links of THIS box carry when every rank moves the same bytes both ways at once and
+        # nothing is computed (two streams, the same pinned buffers): the floor of any e2e step on this machine
+        dx = torch.empty_like(x)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        link = []
+        for rep in range(4):
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s_up):
+                dx.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                yh.copy_(y, non_blocking=True)
+            torch.cuda.synchronize()
+            link.append(time.perf_counter() - t0)
+        dl = min(link[1:])
+        if dist is not None:
+            tt = torch.tensor([dl], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dl = float(tt.item())
+        del dx
         e2e = {"value": bytes_total / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(n_rows * 8),
                "d2h_bytes_per_step": int(n_rows * 8), "ms_per_step": dt * 1e3, "steps": k2,
                "bit_identical_to_device_action": e2e_ok,
+               "copies_only_ms_per_step": dl * 1e3, "frac_of_link_floor": dl / dt,
+               "link_note": "copies_only = the same H2D + D2H bytes on all ranks at once with no compute (max over ranks): "
+                            "the PCIe / host-memory floor of this box; e2e cannot scale beyond the box's aggregate host links",
                "call": "pfsp_mat_action_host (include/pacmensl_b200_host.h) with pinned host x, y"}
         del xh, yh
 

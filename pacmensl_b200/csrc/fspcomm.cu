@@ -503,7 +503,9 @@ int fsphalo_create(fspcomm_t c, fsphalo_t *out, const int *send_idx_dev, const l
       }
     }
     if (!found) {
-      size_t cap = ((cap_need + cap_need / 4 + 1024) + 31) / 32 * 32;
+      // generous growth: a new window costs a cudaMalloc, an IPC handle exchange and one cudaIpcOpenMemHandle per peer
+      // (tens of milliseconds), and the adaptive FSP regenerates its operator dozens of times with a growing halo
+      size_t cap = ((std::max<size_t>(2 * cap_need, (size_t) 1 << 20)) + 31) / 32 * 32;  // >= 16 MB per window: never re-created for small sets
       // consistent on all ranks (window_create agrees internally); the pool is untouched when it fails
       if (window_create(c, sizeof(HaloHeader) + 2 * cap * sizeof(double), &h->w.win)) agreed = 1;
       h->w.cap = cap;
