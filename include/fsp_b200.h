@@ -336,6 +336,10 @@ FSP_API int fspmat_flops(fspmat_t h, long *nflops);
 FSP_API int fspmat_num_rows(fspmat_t h, int *n_rows);
 /* algorithmic bytes of one Action: n*(16 + 12 P + 8 (n_tv + [n_ti>0])) + 12 nnz_sink + 8 K */
 FSP_API int fspmat_action_bytes(fspmat_t h, double *bytes);
+/* Coefficient applied to the time-invariant reactions by every later action of this operator (default 1; the reference
+ * gives them coefficient 1, FspMatrixBase.cpp:58).  0 turns the operator into sum_{r in TV} coef[r] A_r -- what the j-th
+ * time derivative of A(t) is when coef holds the j-th derivatives of the time coefficients. */
+FSP_API int fspmat_set_ti_coef(fspmat_t h, double c);
 /* kernel variant selection for tuning/benchmarks: 0 = default */
 FSP_API int fspmat_set_variant(fspmat_t h, int variant);
 /* Multi-GPU set-up (the analogue of PETSc's VecScatter creation for MATMPISELL): col_dev holds GLOBAL column

@@ -142,6 +142,7 @@ SIGNATURES = {
     "fspmat_flops": (ci, [vp, lp]),
     "fspmat_num_rows": (ci, [vp, ip]),
     "fspmat_action_bytes": (ci, [vp, dp]),
+    "fspmat_set_ti_coef": (ci, [vp, cd]),
     "fspmat_set_variant": (ci, [vp, ci]),
     "fspmat_dense": (ci, [vp, dp, dp]),
     "fspmat_csr_size": (ci, [vp, lp, ip]),

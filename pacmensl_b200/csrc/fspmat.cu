@@ -863,6 +863,7 @@ struct fspmat_s {
   long     flops = 0;
   double   bytes = 0.0;
   int      variant = 0;
+  double   ti_coef = 1.0;              // coefficient of the time-invariant reactions (1; 0 while a time derivative of A(t) is applied)
   int     *d_cta_order = nullptr;      // CTA issue order of the single-kernel peer-memory action
   int      n_ctas = 0, n_interior_ctas = 0;
   int      rot = 0, n_fast = 0;        // fused halo action: CTA rotation (longest ghost-free run first) and its length
@@ -898,6 +899,11 @@ int fspmat_destroy(fspmat_t h) {
 }
 
 int fspmat_clear(fspmat_t h) { return free_values(h); }
+
+int fspmat_set_ti_coef(fspmat_t h, double c) {
+  h->ti_coef = c;
+  return 0;
+}
 
 int fspmat_set_variant(fspmat_t h, int variant) {
   h->variant = variant;
@@ -1108,8 +1114,8 @@ static int launch_action(fspmat_t h, const double *coef_host, const double *x, c
   if (!h->has_values) return 0;  // FspMatrixBase.cpp:41 -- an operator without values acts as zero
   Coefs cf;
   for (int g = 0; g < h->n_tv; ++g) { cf.c[g] = coef_host[h->tv[g]]; cf.cd[g] = cf.c[g]; }
-  for (int q = 0; q < h->n_ti; ++q) cf.c[h->n_tv + q] = 1.0;
-  if (h->n_ti > 0) cf.cd[h->n_tv] = 1.0;
+  for (int q = 0; q < h->n_ti; ++q) cf.c[h->n_tv + q] = h->ti_coef;
+  if (h->n_ti > 0) cf.cd[h->n_tv] = h->ti_coef;
 
   MatView m;
   m.n = h->n; m.n_rows_main = h->n; m.P = h->P; m.ND = h->ND; m.ld = h->ld;
@@ -1170,8 +1176,8 @@ int fspmat_num_boundary_rows(fspmat_t h, long *n) { *n = h->n_boundary; return 0
 
 static void fill_coefs_view(fspmat_t h, const double *coef_host, Coefs &cf, MatView &m) {
   for (int g = 0; g < h->n_tv; ++g) { cf.c[g] = coef_host[h->tv[g]]; cf.cd[g] = cf.c[g]; }
-  for (int q = 0; q < h->n_ti; ++q) cf.c[h->n_tv + q] = 1.0;
-  if (h->n_ti > 0) cf.cd[h->n_tv] = 1.0;
+  for (int q = 0; q < h->n_ti; ++q) cf.c[h->n_tv + q] = h->ti_coef;
+  if (h->n_ti > 0) cf.cd[h->n_tv] = h->ti_coef;
   m.n = h->n; m.n_rows_main = h->n; m.P = h->P; m.ND = h->ND; m.ld = h->ld;
   m.col = h->d_col; m.off = h->d_off; m.diag = h->d_diag;
   m.K = h->K; m.G = h->ND;

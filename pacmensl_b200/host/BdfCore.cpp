@@ -860,6 +860,42 @@ int BdfCore::interpolate(double t, Vec *zn, Vec out) {
 
 int BdfCore::GetDky(double t, Vec yout) { return interpolate(t, zn_, yout); }
 
+int BdfCore::TaylorRestart(const DerivOpFn &dop, int max_time_deriv) {
+  if (first_ || !zn_[0] || ns_ > 0) return 1;  // (sensitivities keep the plain carry-over)
+  vec_status_ = 0;
+  scale_pending_ = false;  // zn_[1..q] are rebuilt from scratch: a pending rescale of the old history is moot
+  static const double binom[6][6] = {{1, 0, 0, 0, 0, 0}, {1, 1, 0, 0, 0, 0}, {1, 2, 1, 0, 0, 0},
+                                     {1, 3, 3, 1, 0, 0}, {1, 4, 6, 4, 1, 0}, {1, 5, 10, 10, 5, 1}};
+  // unscaled derivatives Y_k = y^(k)(t_n) in zn_[k]
+  for (int k = 0; k < q_; ++k) {
+    nfe_ += 1;
+    if (dop(0, tn_, zn_[k], zn_[k + 1]) != 0) return BDF_RHS_FAIL;
+    for (int j = 1; j <= k && j <= max_time_deriv; ++j) {
+      nfe_ += 1;
+      if (dop(j, tn_, zn_[k - j], tempv_) != 0) return BDF_RHS_FAIL;
+      VCHK(fspvec_axpy(zn_[k + 1]->d_data, binom[k][j], tempv_->d_data, n_local_, stream_));
+    }
+  }
+  double fac = 1.0;
+  for (int k = 1; k <= q_; ++k) {
+    fac *= h_ / k;
+    VCHK(fspvec_scale(zn_[k]->d_data, fac, n_local_, stream_));
+  }
+  for (int k = q_ + 1; k <= QMAX; ++k) VCHK(fspvec_set(zn_[k]->d_data, 0.0, n_local_, stream_));
+  VCHK(fspvec_set(acor_->d_data, 0.0, n_local_, stream_));
+  // controller state of a uniform history at step h_: no order change for q + 1 steps, normal growth limits
+  hscale_ = hprime_ = next_h_ = h_;
+  eta_ = 1.0;
+  qprime_ = q_;
+  L_ = q_ + 1;
+  qwait_ = L_;
+  nscon_ = 0;
+  indx_acor_ = QMAX;
+  for (int j = 1; j <= LMAX; ++j) tau_[j] = h_;
+  etamax_ = ETAMX3;
+  return 0;
+}
+
 int BdfCore::Expand(const std::vector<PetscInt> &new_indices, PetscInt new_local_size) {
   if (first_ || !zn_[0]) return 1;  // nothing worth keeping
   vec_status_ = 0;

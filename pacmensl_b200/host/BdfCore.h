@@ -42,6 +42,15 @@ class BdfCore {
   /// step size, order and all controller state: the integrator continues instead of restarting at order 1.
   int  Expand(const std::vector<PetscInt> &new_indices, PetscInt new_local_size);
   long LocalSize() const { return n_local_; }
+  /// Taylor restart (after Expand): rebuild the Nordsieck array at the current (t_n, h, q) from the exact time
+  /// derivatives of the solution of the LINEAR system y' = A(t) y,
+  ///     y^(k+1) = sum_{j=0..k} C(k, j) A^(j)(t_n) y^(k-j),    zn[k] = h^k y^(k) / k!,
+  /// with dop(j, t, v, out) = A^(j)(t) v (j = 0: the right-hand side; j >= 1 only while j <= max_time_deriv: 0 for a
+  /// time-invariant operator).  q Actions for a time-invariant operator, q(q+1)/2 at most otherwise.  The new
+  /// components then carry their full derivative history, so the integrator continues at (nearly) its old step size
+  /// and order instead of climbing back from order 1 and a first step sized for the atol = 1e-14 weights.
+  using DerivOpFn = std::function<int(int j, double t, Vec v, Vec out)>;
+  int  TaylorRestart(const DerivOpFn &dop, int max_time_deriv);
 
   explicit BdfCore(MPI_Comm comm);
   ~BdfCore();

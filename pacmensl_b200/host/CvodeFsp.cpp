@@ -1,5 +1,9 @@
 #include "CvodeFsp.h"
 
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
 namespace pacmensl {
 
 CvodeFsp::CvodeFsp(MPI_Comm _comm, int lmm) : OdeSolverBase(_comm) { lmm_ = lmm; }
@@ -109,6 +113,13 @@ PetscInt CvodeFsp::Solve() {
   }
   petsc_err = VecCopy(solution_work_, *solution_);
   CHKERRQ(petsc_err);
+  static const bool bdf_trace = [] { const char *e = std::getenv("FSP_BDF_TRACE"); return e && e[0] == '1'; }();
+  if (bdf_trace && my_rank_ == 0) {
+    // cumulative counters of this integrator object (they continue across a warm restart, restart from 0 after a cold one)
+    printf("[bdf] segment ends at t=%.5e stop=%d n=%d | steps %ld  Actions(rhs) %ld  J*v %ld  err-test fails %ld  conv fails %ld  h_last %.3e  q_last %d\n",
+           t_now_, stop, (*solution_)->n_local, core_->NumSteps(), core_->NumRhsEvals(), core_->NumLinIters(), core_->NumErrTestFails(),
+           core_->NumConvFails(), core_->LastStep(), core_->LastOrder());
+  }
   return stop;
 }
 
@@ -118,6 +129,24 @@ int CvodeFsp::ExpandState(const std::vector<PetscInt> &new_indices, PetscInt new
     carry_ = false;
     core_.reset();
     return 1;
+  }
+  // Taylor restart: with the operator at hand the history of ALL components (the new ones included) is rebuilt from
+  // exact derivatives at the current step size and order; FSP_WARM_RESTART=carry keeps the plain carry-over
+  static const bool carry_only = [] { const char *e = std::getenv("FSP_WARM_RESTART"); return e && !std::strcmp(e, "carry"); }();
+  if (fspmat_ && !carry_only) {
+    const double h = std::fabs(core_->LastStep());
+    const double delta = std::max(0.02 * h, 1.0e-7 * std::max(1.0, std::fabs(t_now_)));
+    auto dop = [this, delta](int j, double t, Vec v, Vec out) -> int {
+      num_rhs_evals_ += 1;
+      if (j == 0) return rhs_(t, v, out);
+      return fspmat_->ActionTimeDerivative(j, t, v, out, delta);
+    };
+    int rc = core_->TaylorRestart(dop, fspmat_->HasTimeVaryingReactions() ? 4 : 0);
+    if (rc < 0) {
+      carry_ = false;
+      core_.reset();
+      return 1;
+    }
   }
   return 0;
 }

@@ -149,6 +149,7 @@ PacmenslErrorCode FspMatrixBase::GenerateValues(const StateSetBase &fsp, const a
   DeviceBuffer<double> off((size_t) P * ld), diag((size_t) P * ld);
   if (!col.get() || !off.get() || !diag.get()) PACMENSLCHKERRQ(-1);
 
+  tick("destroy + plane buffers");
   std::vector<int>    shifted;
   std::vector<double> vals;
   const bool          on_device = (bool) mass_action_;
@@ -443,6 +444,33 @@ PacmenslErrorCode FspMatrixBase::ActionFused(PetscReal t, Vec x, Vec y, const fs
     FSPCHKERRQ(fspvec_mdot(ep.dot_out_dev, y->d_data, ep.n_dots, vecs, n, stream));
   }
   return 0;
+}
+
+PacmenslErrorCode FspMatrixBase::ActionTimeDerivative(int j, PetscReal t, Vec x, Vec y, PetscReal delta) {
+  if (j == 0) return Action(t, x, y);
+  if (j < 0 || j > 4 || !(delta > 0.0)) return -1;
+  if (has_values_ == PETSC_FALSE || tv_reactions_.empty()) return VecSet(y, 0.0);
+  // central finite-difference weights on the offsets -3..3 (Fornberg), derivative orders 1..4
+  static const double W[4][7] = {{-1.0 / 60, 3.0 / 20, -3.0 / 4, 0.0, 3.0 / 4, -3.0 / 20, 1.0 / 60},
+                                 {1.0 / 90, -3.0 / 20, 3.0 / 2, -49.0 / 18, 3.0 / 2, -3.0 / 20, 1.0 / 90},
+                                 {1.0 / 8, -1.0, 13.0 / 8, 0.0, -13.0 / 8, 1.0, -1.0 / 8},
+                                 {-1.0 / 6, 2.0, -13.0 / 2, 28.0 / 3, -13.0 / 2, 2.0, -1.0 / 6}};
+  arma::Row<PetscReal> cj((arma::uword) num_reactions_), tmp((arma::uword) num_reactions_);
+  cj.fill(0.0);
+  for (int k = -3; k <= 3; ++k) {
+    const double w = W[j - 1][k + 3];
+    if (w == 0.0) continue;
+    tmp.fill(1.0);
+    int ierr = t_fun_(t + k * delta, num_reactions_, tmp.memptr(), t_fun_args_);
+    PACMENSLCHKERRQ(ierr);
+    for (int r = 0; r < num_reactions_; ++r) cj[r] += w * tmp[r];
+  }
+  const double scale = 1.0 / std::pow(delta, j);
+  for (int r = 0; r < num_reactions_; ++r) cj[r] *= scale;
+  FSPCHKERRQ(fspmat_set_ti_coef(dmat_, 0.0));
+  PacmenslErrorCode ierr = ActionWithCoefficients(cj.memptr(), x, y);
+  fspmat_set_ti_coef(dmat_, 1.0);
+  return ierr;
 }
 
 PacmenslErrorCode FspMatrixBase::ActionWithCoefficients(const double *coefs, Vec x, Vec y) {

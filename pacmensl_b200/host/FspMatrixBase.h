@@ -51,6 +51,11 @@ class PACMENSL_API FspMatrixBase {
   /// Extension: the same operator on HOST vectors (n local rows each): chunked upload / compute / download pipeline
   /// on a single GPU, plain H2D + Action + D2H otherwise.  FSP_HOST_CHUNKS (default 32; <= 1 disables the pipeline).
   PacmenslErrorCode ActionHost(PetscReal t, const double *x_host, double *y_host);
+  /// Extension: y = (d^j A / dt^j)(t) x = sum_{r in TV} c_r^(j)(t) A_r x for j >= 1 (j = 0: Action).  The derivatives of
+  /// the time coefficients are central finite differences of the t_fun callback on a 7-point stencil of spacing delta
+  /// (6th/4th-order accurate for j <= 2 / j <= 4).  Used by the Taylor restart of the BDF integrator (BdfCore.h).
+  PacmenslErrorCode ActionTimeDerivative(int j, PetscReal t, Vec x, Vec y, PetscReal delta);
+  bool HasTimeVaryingReactions() const { return !tv_reactions_.empty(); }
   /// y = (sum_r coef[r] A_r) x with the coefficient vector supplied directly (used by SensFspMatrix).
   PacmenslErrorCode ActionWithCoefficients(const double *coefs, Vec x, Vec y);
 

@@ -60,11 +60,13 @@ class PACMENSL_API FspSolverMultiSinks {
   PacmenslErrorCode SetOdeTolerances(PetscReal rel_tol, PetscReal abs_tol);
   /// Extension.  false (default): the reference's behaviour -- the integrator is re-created
   /// after every expansion and restarts at order 1 with a fresh first step (src/Fsp/FspSolverMultiSinks.cpp:92-108).
-  /// true (or FSP_WARM_RESTART=1): the BDF integrator continues with its Nordsieck history, step size and order mapped
-  /// onto the enlarged state space.  Correct (same answers within the integrator's tolerance) but MEASURED SLOWER on
-  /// every example (+30 .. +50 % Action calls): the new states enter at exactly 0 with weights 1/atol = 1e14,
-  /// so the carried-over step fails the error test until the step size is as small as a cold start would choose anyway.
-  /// KrylovFsp always restarts as the reference does.
+  /// true (or FSP_WARM_RESTART=1): the BDF integrator survives the expansion -- its Nordsieck array is mapped onto the
+  /// enlarged state space and rebuilt from exact derivatives of the linear system at the current step size and order
+  /// (Taylor restart, BdfCore.h).  Same answers within the integrator's tolerance; measured -13 % Action calls on the
+  /// repressilator example (-30 .. -40 % at short horizons), +3 .. +5 % on the time-varying hog1p / transcr_reg_6d
+  /// (DESIGN.md section 7).  FSP_WARM_RESTART=carry keeps the plain carry-over of the old history (measured +30 .. +50 %:
+  /// the new states enter at 0 with weights 1/atol and no derivative history).  KrylovFsp always restarts as the
+  /// reference does.
   PacmenslErrorCode SetWarmRestart(bool on) { warm_restart_ = on; if (ode_solver_) ode_solver_->SetWarmRestart(on); return 0; }
 
   std::shared_ptr<const StateSetBase> GetStateSet();
