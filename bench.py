@@ -511,7 +511,7 @@ def main():
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_local},
             "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks, "parity": parity,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only; `--impl reference` is the CPU arm at every N
             cb = cpu_baseline(args)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "same_config")}
     if dist is not None:
