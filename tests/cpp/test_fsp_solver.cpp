@@ -212,13 +212,15 @@ TEST_F(FspTest, device_marginals_equal_the_host_loop) {
   ASSERT_FALSE(fsp.SetOdesType(KRYLOV));
   DiscreteDistribution d = fsp.Solve(20.0, 1.0e-6, 0);
   fsp.ClearState();
-  ASSERT_TRUE((bool) d.states_dev_);
+  ASSERT_TRUE((bool) d.states_dev_ || d.states_.n_cols == 0);
   const PetscScalar *p;
   ASSERT_FALSE(VecGetArrayRead(d.p_, &p));
   for (int species = 0; species < 2; ++species) {
     arma::Col<PetscReal> md = Compute1DMarginal(d, species);
-    int mx = 0;
-    for (arma::uword i = 0; i < d.states_.n_cols; ++i) mx = std::max(mx, d.states_(species, i));
+    double mxd = 0.0;
+    for (arma::uword i = 0; i < d.states_.n_cols; ++i) mxd = std::max(mxd, (double) d.states_(species, i));
+    pacmensl_allreduce_max(PETSC_COMM_WORLD, &mxd, 1);  // the bins cover the largest count on ANY rank
+    const int mx = (int) mxd;
     std::vector<double> ref((size_t) mx + 1, 0.0);
     for (arma::uword i = 0; i < d.states_.n_cols; ++i) ref[(size_t) d.states_(species, i)] += p[i];
     pacmensl_allreduce_sum(PETSC_COMM_WORLD, ref.data(), (int) ref.size());
