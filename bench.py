@@ -414,6 +414,28 @@ def main():
     # so the per-launch duration of the dominant kernel is the event-timed step.
     kms = ms_per_step
 
+    # ---- N > 1: the halo exchange alone (push CTAs + finishing CTA, no rows): what crosses NVLink per Action ----------
+    halo = None
+    if dist is not None and api.p2p_enabled():
+        for _ in range(5):
+            sent = lat.mat.halo_only(x, y)
+        torch.cuda.synchronize()
+        dist.all_reduce(tick)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(50):
+            lat.mat.halo_only(x, y)
+        h1.record()
+        torch.cuda.synchronize()
+        th = torch.tensor([h0.elapsed_time(h1) / 50.0, float(sent)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        us = float(th[0].item()) * 1e3
+        halo = {"us_per_exchange": us, "bytes_pushed_per_rank_max": int(th[1].item()),
+                "GBps_per_direction": float(th[1].item()) / (us * 1e-6) / 1e9 if us > 0 else None,
+                "what": "pack + store into the peers' windows over NVLink + epoch flag + wait for every peer's flag, one launch, "
+                        "back to back (latency-bound: 2 planes of 465^2 doubles per interior rank); nvidia-smi nvlink counters "
+                        "report N/A on this pool"}
+
     # ---- e2e: the same Action through the C ABI with HOST buffers (H2D x, D2H y inside the timed region) -----
     e2e = None
     if not args.no_e2e:
@@ -509,7 +531,7 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": kernel + " (pacmensl_b200/csrc/fspmat.cu)",
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": bytes_local},
-            "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks, "parity": parity,
+            "e2e": e2e, "gpu_launches": int(launches_total), "clocks": clocks, "parity": parity, "halo_exchange": halo,
         }
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only; `--impl reference` is the CPU arm at every N
             cb = cpu_baseline(args)

@@ -78,6 +78,9 @@ FSP_API int pfsp_mat_set_variant(void *mat, int variant);
 FSP_API int pfsp_mat_info(void *mat, int *n_rows_local, long *flops, double *action_bytes);
 /* y = A(t) x with DEVICE buffers of n_rows_local doubles */
 FSP_API int pfsp_mat_action(void *mat, double t, const double *x_dev, double *y_dev);
+/* diagnostics, multi-GPU: only the halo exchange of an Action (push CTAs + finishing CTA, no rows); *bytes_sent = bytes
+ * this rank stores into its peers' windows per exchange */
+FSP_API int pfsp_mat_halo_only(void *mat, const double *x_dev, double *y_dev, long *bytes_sent);
 /* the same call with HOST buffers (pinned or pageable): H2D copy of x, Action, D2H copy of y */
 FSP_API int pfsp_mat_action_host(void *mat, double t, const double *x_host, double *y_host);
 

@@ -49,6 +49,7 @@ HOST_SIGNATURES = {
     "pfsp_mat_info": (ci, [vp, ip, lp, dp]),
     "pfsp_mat_action": (ci, [vp, cd, vp, vp]),
     "pfsp_mat_action_host": (ci, [vp, cd, vp, vp]),
+    "pfsp_mat_halo_only": (ci, [vp, vp, vp, lp]),
     "pfsp_solver_create": (ci, [vpp, ci]),
     "pfsp_solver_destroy": (ci, [vp]),
     "pfsp_solver_set_model": (ci, [vp, vp]),
@@ -313,6 +314,12 @@ class FspMatrix:
     def action(self, t, x, y):
         """x, y: torch float64 CUDA tensors with n_rows entries."""
         return lib().pfsp_mat_action(self.h, float(t), vp(x.data_ptr()), vp(y.data_ptr()))
+
+    def halo_only(self, x, y):
+        """Diagnostics (multi-GPU): only the halo exchange of an Action; returns the bytes this rank pushes."""
+        b = cl()
+        check(lib().pfsp_mat_halo_only(self.h, vp(x.data_ptr()), vp(y.data_ptr()), C.byref(b)), "halo_only")
+        return b.value
 
     def action_host(self, t, x, y):
         """x, y: host buffers (numpy arrays or pinned torch tensors)."""

@@ -446,6 +446,17 @@ PacmenslErrorCode FspMatrixBase::ActionFused(PetscReal t, Vec x, Vec y, const fs
   return 0;
 }
 
+PacmenslErrorCode FspMatrixBase::HaloExchangeOnly(Vec x, Vec y, long *bytes_sent) {
+  if (bytes_sent) *bytes_sent = 8L * n_send_;
+  if (comm_size_ == 1 || !halo_ || has_values_ == PETSC_FALSE) return 0;
+  fsphalo_epoch ep;
+  fsphalo_push  push;
+  FSPCHKERRQ(fsphalo_next(halo_, &ep, &push));
+  FSPCHKERRQ(fspmat_action_halo_part(dmat_, time_coefficients_.memptr(), x->d_data, y->d_data, &ep, &push, 1 | 4, 0, 0, 0, nullptr,
+                                     comm_ ? comm_->stream : nullptr));
+  return 0;
+}
+
 PacmenslErrorCode FspMatrixBase::ActionTimeDerivative(int j, PetscReal t, Vec x, Vec y, PetscReal delta) {
   if (j == 0) return Action(t, x, y);
   if (j < 0 || j > 4 || !(delta > 0.0)) return -1;
@@ -774,6 +785,7 @@ PacmenslErrorCode FspMatrixBase::CreateRHSJacobian(Mat *A) {
   J->comm = comm_;
   FSPCHKERRQ(fspmat_csr_size(dmat_, &J->nnz, &J->n_rows));
   J->n_rows = num_rows_local_;
+  J->n_state_rows = num_states_local_;
   if (J->row_ptr.resize((size_t) J->n_rows + 1) || J->col.resize((size_t) std::max<long>(J->nnz, 1)) ||
       J->val.resize((size_t) std::max<long>(J->nnz, 1))) { delete J; return -1; }
   time_coefficients_.fill(1.0);

@@ -13,7 +13,7 @@
 // A(t) in CSR form on the device (fspmat_csr_export), applied by MatMult with a device SpMV.
 struct _p_Mat {
   MPI_Comm                           comm = nullptr;
-  int                                n_rows = 0;
+  int                                n_rows = 0, n_state_rows = 0;  ///< state rows come first; their first slot is the diagonal
   long                               nnz = 0;
   pacmensl::DeviceBuffer<int>        row_ptr, col;
   pacmensl::DeviceBuffer<double>     val;
@@ -56,6 +56,9 @@ class PACMENSL_API FspMatrixBase {
   /// (6th/4th-order accurate for j <= 2 / j <= 4).  Used by the Taylor restart of the BDF integrator (BdfCore.h).
   PacmenslErrorCode ActionTimeDerivative(int j, PetscReal t, Vec x, Vec y, PetscReal delta);
   bool HasTimeVaryingReactions() const { return !tv_reactions_.empty(); }
+  /// Diagnostics (multi-GPU, peer-memory path): ONLY the exchange of an Action -- push CTAs (pack + store to the peers +
+  /// flag) and the finishing CTA (wait for every peer) in one launch, no rows.  *bytes_sent = doubles pushed * 8.
+  PacmenslErrorCode HaloExchangeOnly(Vec x, Vec y, long *bytes_sent);
   /// y = (sum_r coef[r] A_r) x with the coefficient vector supplied directly (used by SensFspMatrix).
   PacmenslErrorCode ActionWithCoefficients(const double *coefs, Vec x, Vec y);
 

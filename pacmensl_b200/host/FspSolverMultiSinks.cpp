@@ -244,8 +244,8 @@ PacmenslErrorCode FspSolverMultiSinks::SetUp() {
         }
         break;
       default:
-        // ODESolverType::PETSC: TsFsp keeps the reference's interface and integrates with the matrix-free BDF
-        // integrator (PETSc TS with assembled Jacobians is outside this build's scope), see TsFsp.h
+        // ODESolverType::PETSC: TsFsp = Rosenbrock-W (RA34PW2, PETSc's TSROSW default scheme) on the assembled CSR
+        // Jacobian, see TsFsp.h
         ode_solver_ = std::make_shared<TsFsp>(comm_);
     }
     ode_solver_->SetFspMatPtr(A_.get());

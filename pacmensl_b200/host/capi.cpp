@@ -200,6 +200,18 @@ int pfsp_mat_action(void *mat, double t, const double *x_dev, double *y_dev) {
   return A->Action(t, &x, &y);
   PFSP_CATCH
 }
+int pfsp_mat_halo_only(void *mat, const double *x_dev, double *y_dev, long *bytes_sent) {
+  PFSP_TRY
+  auto  *A = static_cast<FspMatrixBase *>(mat);
+  _p_Vec x, y;
+  x.comm = y.comm = MPI_COMM_WORLD;
+  x.n_local = y.n_local = A->GetNumLocalRows();
+  x.d_data = const_cast<double *>(x_dev);
+  y.d_data = y_dev;
+  x.owns_data = y.owns_data = false;
+  return A->HaloExchangeOnly(&x, &y, bytes_sent);
+  PFSP_CATCH
+}
 int pfsp_mat_action_host(void *mat, double t, const double *x_host, double *y_host) {
   PFSP_TRY
   return static_cast<FspMatrixBase *>(mat)->ActionHost(t, x_host, y_host);

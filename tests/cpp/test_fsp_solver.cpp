@@ -3,8 +3,8 @@
 //   KAT-F2 a prop_t_ returning -1 makes Solve / SolveTspan throw std::runtime_error   (:134-177)
 //   KAT-F4/F5 pure birth (lambda = 2, t_f = 10, bounds {5}, expansion 0.1, fsp_tol 1e-6):
 //          sum_n |p_n - Poisson(lambda t)(n)| <= 1e-6 for CVODE and KRYLOV            (:264-345)
-//   (KAT-F3 uses ODESolverType::PETSC, whose TsFsp back end is outside this build; the driver maps it to the
-//    BDF integrator, and the same Poisson bound is checked.)
+//   (KAT-F3 uses ODESolverType::PETSC = TsFsp: here the Rosenbrock-W scheme RA34PW2 -- PETSc's TSROSW default -- on the
+//    assembled CSR Jacobian, host/TsFsp.h; the same Poisson bound is checked.)
 #include "fsp_models.h"
 #include "pacmensl_test_env.h"
 

@@ -88,7 +88,8 @@ def test_fixed_set_solves_against_tight_reference(cuda, oracle, name, bounds, t_
     p0 = np.zeros(A.nrows)
     p0[so.state2index(fx["x0"].reshape(1, -1))[0]] = 1.0
     p_ref, nfev = tight_reference(A, p0, t_final)
-    for ode, label in ((api.CVODE, "CvodeFsp"),) + (((api.KRYLOV, "KrylovFsp"),) if krylov_too else ()):
+    for ode, label in ((api.CVODE, "CvodeFsp"), (api.PETSC, "TsFsp (Rosenbrock-W RA34PW2, assembled CSR Jacobian)")) + (
+            ((api.KRYLOV, "KrylovFsp"),) if krylov_too else ()):
         s, m = api.fixture_solver(name, ode)
         s.set_initial_bounds(bounds)
         states, p = s.solve(t_final, -1.0)  # fsp_tol <= 0: fixed state set (FspSolverMultiSinks.cpp:76-85)
