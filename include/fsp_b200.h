@@ -148,6 +148,12 @@ FSP_API int fspvec_nordsieck(double *const *Z_dev_ptrs, int L, const double *sca
 FSP_API int fspvec_multi_axpy(double *const *Z_dev_ptrs, int L, const double *coef_host, const double *x_dev, long n,
                               void *stream);
 /* host-result conveniences (synchronise `stream`) */
+/* KrylovFsp's incomplete orthogonalisation of one basis vector (src/OdeSolver/KrylovFsp.cpp:302-309, q_iop <= 2) in ONE
+ * cooperative launch: h_0 = <w,u0>; [w -= h_0 u0; h_1 = <w,u1>;] w -= h_last u_last; s2 = <w,w>; w /= sqrt(s2), with w held in
+ * registers across the phases when it fits (read and written once) and grid-wide barriers between them.  nvec = 1 uses
+ * u1 only.  h_dev: nvec coefficients, then s2.  Returns 1 without launching if the device cannot do it. */
+FSP_API int fspvec_iop_orth(double *w_dev, int nvec, const double *u0_dev, const double *u1_dev, double *h_dev, long n,
+                            void *stream);
 /* Post-processing on the device (src/Fsp/DiscreteDistribution.cpp:171-200, src/SensFsp/SensDiscreteDistribution.cpp:216-271):
  *   marginal      out_dev[b] = sum of p over the states whose coordinate `species` equals b, b < M (deterministic order)
  *   max_species   *out_neg_dev = -(largest coordinate `species` over the n states)

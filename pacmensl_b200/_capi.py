@@ -95,6 +95,7 @@ SIGNATURES = {
     "fspvec_newton_update": (ci, [vp, vp, vp, vp, vp, vp, vp, cl, vp]),
     "fspvec_nordsieck": (ci, [vp, ci, vp, ci, cl, vp]),
     "fspvec_multi_axpy": (ci, [vp, ci, vp, vp, cl, vp]),
+    "fspvec_iop_orth": (ci, [vp, ci, vp, vp, vp, cl, vp]),
     "fspvec_marginal": (ci, [vp, ci, vp, vp, ci, ci, cl, vp]),
     "fspvec_max_species": (ci, [vp, vp, ci, ci, cl, vp]),
     "fspvec_clamp_min": (ci, [vp, vp, cd, cl, vp]),

@@ -5,6 +5,8 @@
 // All kernels are HBM-bound streaming passes: grid-stride loops with 128-bit loads where the base
 // pointers allow it, grids sized as a multiple of the SM count, and two-stage fixed-shape reductions
 // (per-block partials -> last block sums them in a fixed order), so results are deterministic.
+#include <cooperative_groups.h>
+
 #include "fsp_common.cuh"
 
 using namespace fspb;
@@ -438,6 +440,89 @@ int launch_map2(F2 f, long n2, void *stream) {
   return 0;
 }
 
+// ---- incomplete orthogonalisation of one Krylov basis vector in ONE cooperative launch --------------------------
+// KrylovFsp's column step after w = A v_j (src/OdeSolver/KrylovFsp.cpp:302-309, q_iop <= 2):
+//     h_0 = <w, u_0>;  [w -= h_0 u_0;  h_1 = <w, u_1>;]  w -= h_last u_last;  s2 = <w, w>;  w *= 1/sqrt(s2)
+// was 4 launches (dot, 2 x axpy+dot, scale) that each re-read w.  Here every thread owns up to kOrthRows rows of w in
+// REGISTERS for the whole sequence (w is read and written once), the inner products are per-CTA partials combined by
+// every CTA in the same fixed order after a grid-wide barrier (deterministic, identical in all CTAs), and nothing
+// returns to the host.  Vectors too long for the register file (n > grid * 256 * kOrthRows) take the same phases with w
+// re-read from memory: still one launch instead of four.
+constexpr int kOrthRows = 8;
+struct OrthArgs {
+  double       *w;
+  const double *u[2];     // u[0] unused when nvec == 1
+  double       *h;        // outputs: h[0..nvec-1] coefficients, h[nvec] = ||w||^2 before the scaling
+  double       *partials; // [3][gridDim.x]
+  long          n;
+  int           nvec;
+};
+template <bool IN_REGS>
+__global__ void __launch_bounds__(kThreads, 4) iop_orth_kernel(OrthArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double smem[32];
+  __shared__ double bcast;
+  const long stride = (long) gridDim.x * blockDim.x;
+  const long i0 = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  double     wr[IN_REGS ? kOrthRows : 1];
+  if (IN_REGS) {
+#pragma unroll
+    for (int r = 0; r < kOrthRows; ++r) {
+      const long i = i0 + r * stride;
+      wr[r] = i < a.n ? a.w[i] : 0.0;
+    }
+  }
+  double coef = 0.0;  // coefficient of the pending axpy
+  // phases: p = 0 .. nvec: dot with u[first + p] (p < nvec) or with w itself (p == nvec), after applying the pending axpy
+  const double *d0 = a.nvec == 2 ? a.u[0] : a.u[1], *d1 = a.u[1];  // (no dynamic indexing of the parameter struct)
+  for (int p = 0; p <= a.nvec; ++p) {
+    const double *ax = p == 0 ? nullptr : (p == 1 ? d0 : d1);        // w -= coef * ax
+    const double *dv = p == a.nvec ? nullptr : (p == 0 ? d0 : d1);   // dot partner (null: w itself)
+    double        acc = 0.0;
+    if (IN_REGS) {
+#pragma unroll
+      for (int r = 0; r < kOrthRows; ++r) {
+        const long i = i0 + r * stride;
+        if (i < a.n) {
+          if (ax) wr[r] = fma(-coef, ax[i], wr[r]);
+          acc = fma(wr[r], dv ? dv[i] : wr[r], acc);
+        }
+      }
+    } else {
+      for (long i = i0; i < a.n; i += stride) {
+        double wi = a.w[i];
+        if (ax) { wi = fma(-coef, ax[i], wi); a.w[i] = wi; }
+        acc = fma(wi, dv ? dv[i] : wi, acc);
+      }
+    }
+    const double r = block_sum(acc, smem);
+    if (threadIdx.x == 0) a.partials[(size_t) p * gridDim.x + blockIdx.x] = r;
+    grid.sync();
+    double v = 0.0;
+    for (int b = threadIdx.x; b < (int) gridDim.x; b += blockDim.x) v += __ldcg(a.partials + (size_t) p * gridDim.x + b);
+    const double tot = block_sum(v, smem);
+    if (threadIdx.x == 0) {
+      bcast = tot;
+      if (blockIdx.x == 0) a.h[p] = tot;
+    }
+    __syncthreads();
+    coef = bcast;
+    __syncthreads();
+  }
+  // coef == ||w||^2 now
+  const double s = 1.0 / sqrt(coef);
+  if (IN_REGS) {
+#pragma unroll
+    for (int r = 0; r < kOrthRows; ++r) {
+      const long i = i0 + r * stride;
+      if (i < a.n) a.w[i] = wr[r] * s;
+    }
+  } else {
+    for (long i = i0; i < a.n; i += stride) a.w[i] *= s;
+  }
+}
+
 // ---- post-processing on the device (DiscreteDistribution / SensDiscreteDistribution) ------------------------------
 struct ClampCountF {  // x_i = max(x_i, lo); counts the entries that were raised
   double *x; double lo;
@@ -581,6 +666,49 @@ int fspvec_mdot(double *out, const double *x, int m, const double *const *Y, lon
     case 8: return mdot_impl<8>(out, x, Y, n, s);
     default: set_error("fspvec_mdot: m=%d out of range (1..8)", m); return -1;
   }
+}
+
+// Orthogonalise-and-normalise w against nvec (1 or 2) vectors in one cooperative launch; see iop_orth_kernel.
+// h_dev receives nvec coefficients followed by ||w||^2 (before the scaling).  Returns 1 (no launch) when the device
+// cannot run the cooperative kernel, so that callers fall back to the separate passes.
+int fspvec_iop_orth(double *w, int nvec, const double *u0, const double *u1, double *h_dev, long n, void *stream) {
+  if (nvec < 1 || nvec > 2 || n <= 0) return 1;
+  static thread_local int coop = -1, max_blocks_regs = 0, max_blocks_mem = 0;
+  static thread_local double *partials = nullptr;
+  if (coop < 0) {
+    int dev = 0, flag = 0;
+    FSP_CUDA_CHECK(cudaGetDevice(&dev));
+    FSP_CUDA_CHECK(cudaDeviceGetAttribute(&flag, cudaDevAttrCooperativeLaunch, dev));
+    int per_sm_r = 0, per_sm_m = 0;
+    if (flag) {
+      FSP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, iop_orth_kernel<true>, kThreads, 0));
+      FSP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_m, iop_orth_kernel<false>, kThreads, 0));
+    }
+    max_blocks_regs = per_sm_r * sm_count();
+    max_blocks_mem = per_sm_m * sm_count();
+    coop = (flag && max_blocks_regs > 0 && max_blocks_mem > 0) ? 1 : 0;
+    if (coop) FSP_CUDA_CHECK(pmalloc(&partials, sizeof(double) * 3 * (size_t) std::max(max_blocks_regs, max_blocks_mem)));
+  }
+  if (!coop) return 1;
+  OrthArgs a;
+  a.w = w; a.u[0] = u0; a.u[1] = u1; a.h = h_dev; a.partials = partials; a.n = n; a.nvec = nvec;
+  if (nvec == 1) { a.u[1] = u1 ? u1 : u0; a.u[0] = nullptr; }
+  // Only the register-resident regime: a vector too long for it is bandwidth-bound, where four streaming kernels with
+  // twice the resident threads do better than one persistent kernel that re-reads w in every phase.
+  const long threads_needed = (n + kOrthRows - 1) / kOrthRows;
+  if (threads_needed > (long) max_blocks_regs * kThreads) return 1;
+  (void) max_blocks_mem;
+  void *args[] = {&a};
+  // as many CTAs as give every thread >= 1 row, at most the co-resident maximum
+  const int grid = (int) std::max<long>(1, std::min<long>(max_blocks_regs, (n + kThreads - 1) / kThreads));
+  cudaError_t e = cudaLaunchCooperativeKernel((void *) iop_orth_kernel<true>, dim3(grid), dim3(kThreads), args, 0, resolve_stream(stream));
+  if (e != cudaSuccess) {
+    set_error("fspvec_iop_orth: cooperative launch failed: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return -1;
+  }
+  count_launch();
+  return 0;
 }
 
 // ---- post-processing (src/Fsp/DiscreteDistribution.cpp:171-200, src/SensFsp/SensDiscreteDistribution.cpp:216-271) ----

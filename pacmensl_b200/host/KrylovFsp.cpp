@@ -240,6 +240,8 @@ int KrylovFsp::BasisColumns_(int m_start) {
     // The fused form saves 8 of 184 bytes per row and no launch here (the partial reduction replaces the dot kernel):
     // measured neutral, so it is opt-in for this solver (FSP_KRYLOV_FUSED=1); the BDF/GMRES loop is where it pays.
     static const bool krylov_fused = [] { const char *e = std::getenv("FSP_KRYLOV_FUSED"); return e && e[0] == '1'; }();
+    static const bool orth_on = [] { const char *e = std::getenv("FSP_KRYLOV_ORTH"); return !(e && e[0] == '0'); }();
+    const int nvec = j - istart + 1;
     if (fused_rhs_ && krylov_fused) {
       // w = A V_j and the first coefficient <w, V_istart> in one pass over w
       fspmat_epilogue ep{};
@@ -250,6 +252,15 @@ int KrylovFsp::BasisColumns_(int m_start) {
     } else {
       ierr = rhs_(0.0, Vm[j], Vm[j + 1]);
       PACMENSLCHKERRQ(ierr);
+      if (!multi && orth_on && nvec <= 2) {
+        // Single rank, vector small enough to live in registers: the whole orthogonalisation of this column is ONE
+        // cooperative launch -- w read and written once, the three inner products separated by grid-wide barriers
+        // instead of kernel boundaries.  This is the launch-bound regime of the adaptive examples (hog1p + KrylovFsp:
+        // 53 000 columns on <= 7e5 states).  rc == 1: not applicable (vector too long / no cooperative launch).
+        int rc = fspvec_iop_orth(w, nvec, Vm[istart]->d_data, Vm[j]->d_data, hcol, n, stream);
+        if (rc < 0) FSPCHKERRQ(rc);
+        if (rc == 0) continue;
+      }
       // first coefficient: plain dot
       FSPCHKERRQ(fspvec_dot(hcol + 0, w, Vm[istart]->d_data, n, stream));
     }
@@ -334,12 +345,13 @@ int KrylovFsp::GenerateBasis(const Vec &v, int m_start, PetscBool *happy_breakdo
         void *saved = comm_->stream;
         comm_->stream = capture_stream_;  // everything this rank submits now goes to the capturing stream
         long rhs_before = num_rhs_evals_;
+        const long launches_before = fsp_launch_count();
         int  cerr = fsp_graph_begin_capture(capture_stream_);
         if (cerr == 0) cerr = BasisColumns_(m_start);
         comm_->stream = saved;
         fsp_graph_t g = nullptr;
-        long        nk = 0, expect = 0;
-        for (int j = m_start; j < m_; ++j) expect += 3 + (j - ((q_iop > 0 && j - q_iop + 1 >= 0) ? j - q_iop + 1 : 0) + 1);
+        long        nk = 0;
+        const long  expect = fsp_launch_count() - launches_before;  // every launch of the column loop must be in the graph
         if (cerr != 0) {
           fsp_graph_abort_capture(capture_stream_);
         } else if (fsp_graph_end_capture(capture_stream_, &g) == 0) {
