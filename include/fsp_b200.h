@@ -453,6 +453,8 @@ FSP_API int fspmat_action_halo(fspmat_t h, const double *coef_host, const double
  *                    bit 1: the K partial sink sums of this rank (needs all of x_dev) -> owner's slots + flag;
  *                    bit 2: the finishing CTA (waits for every peer's flag; sink owner: slots -> y[n..n+K)).  Every
  *                    Action must run it exactly once, last: it paces the reuse of the two ghost buffers.
+ *                    bit 3: this exchange carries no sink sums on any rank (halo-only diagnostics): the finishing CTA
+ *                    then waits for the halo flags only.
  *   rows             [row_begin, row_end) of y; rows_have_ghosts != 0: the CTAs wait for the peers' flags first. */
 FSP_API int fspmat_action_halo_part(fspmat_t h, const double *coef_host, const double *x_dev, double *y_dev,
                                     const fsphalo_epoch *e, const fsphalo_push *push, int parts, long row_begin,

@@ -1340,7 +1340,8 @@ static int launch_halo(fspmat_t h, const double *coef_host, const double *x, dou
   hv.halo_flags = e->halo_flags; hv.sink_flags = e->sink_flags; hv.sink_slots = e->sink_slots;
   hv.ghost = e->ghost; hv.sink_slot_remote = e->sink_slot_remote; hv.sink_flag_remote = e->sink_flag_remote;
   hv.err = e->error_flag;
-  hv.finish_sinks = (h->K > 0 && h->owns_sinks) ? 1 : 0;
+  // bit 3 of parts: no rank publishes sink sums in this exchange (halo-only diagnostics): the finishing CTA must not wait for them
+  hv.finish_sinks = (h->K > 0 && h->owns_sinks && !(parts & 8)) ? 1 : 0;
   if (whole) {
     hv.rot = (h->rot < m.main_blocks) ? h->rot : 0;
     // operators without ghost columns on this rank: every CTA is ghost-free

@@ -452,7 +452,7 @@ PacmenslErrorCode FspMatrixBase::HaloExchangeOnly(Vec x, Vec y, long *bytes_sent
   fsphalo_epoch ep;
   fsphalo_push  push;
   FSPCHKERRQ(fsphalo_next(halo_, &ep, &push));
-  FSPCHKERRQ(fspmat_action_halo_part(dmat_, time_coefficients_.memptr(), x->d_data, y->d_data, &ep, &push, 1 | 4, 0, 0, 0, nullptr,
+  FSPCHKERRQ(fspmat_action_halo_part(dmat_, time_coefficients_.memptr(), x->d_data, y->d_data, &ep, &push, 1 | 4 | 8, 0, 0, 0, nullptr,
                                      comm_ ? comm_->stream : nullptr));
   return 0;
 }
