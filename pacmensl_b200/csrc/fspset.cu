@@ -511,14 +511,11 @@ int fspset_add_box_lattice(fspset_t h, const int *upper) {
   return 0;
 }
 
-int fspset_expand(fspset_t h) {
-  if (h->n == 0) return 0;
-  if ((int) h->bounds.size() != h->K || h->K == 0) { set_error("fspset_expand: shape not set"); return -1; }
+// the BFS loop; the two scratch buffers belong to the caller, which frees them on every path (error returns included)
+static int expand_impl(fspset_t h, int *&d_frontier, signed char *&d_fstatus) {
   const int use_default = h->lhs ? 0 : 1;
   reactivate_kernel<<<blocks_for(h->n), 256>>>(h->d_status, h->n);  // :137-149
   FSP_LAUNCH_CHECK();
-  int         *d_frontier = nullptr;
-  signed char *d_fstatus = nullptr;
   long         fcap = 0;
   std::vector<int>         cand_host, fval;
   std::vector<signed char> valid_host;
@@ -534,6 +531,7 @@ int fspset_expand(fspset_t h) {
     if (nF == 0) break;
     if (nF > fcap) {
       pfree(d_frontier); pfree(d_fstatus);
+      d_frontier = nullptr; d_fstatus = nullptr;
       fcap = nF + nF / 2;
       FSP_CUDA_CHECK(pmalloc(&d_frontier, sizeof(int) * fcap));
       FSP_CUDA_CHECK(pmalloc(&d_fstatus, fcap));
@@ -563,6 +561,15 @@ int fspset_expand(fspset_t h) {
     set_frontier_status_kernel<<<blocks_for(nF), 256>>>(h->d_status, d_frontier, d_fstatus, nF);  // :198
     FSP_LAUNCH_CHECK();
   }
+  return rc;
+}
+
+int fspset_expand(fspset_t h) {
+  if (h->n == 0) return 0;
+  if ((int) h->bounds.size() != h->K || h->K == 0) { set_error("fspset_expand: shape not set"); return -1; }
+  int         *d_frontier = nullptr;
+  signed char *d_fstatus = nullptr;
+  const int    rc = expand_impl(h, d_frontier, d_fstatus);
   pfree(d_frontier); pfree(d_fstatus);
   if (rc == 0) { h->expanded = true; h->expanded_bounds = h->bounds; }
   return rc;

@@ -370,6 +370,9 @@ PacmenslErrorCode FspSolverMultiSinks::CheckFspTolerance_(PetscReal t, Vec p, Pe
 
 PacmenslErrorCode FspSolverMultiSinks::SetModel(Model &model) {
   FspSolverMultiSinks::model_ = model;
+  // a new model invalidates the propensity values cached for incremental regeneration (they are keyed on the number
+  // of reactions and states only, not on the callback)
+  if (A_) A_->ResetGenerationCache();
   return 0;
 }
 
