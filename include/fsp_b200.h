@@ -33,6 +33,11 @@ FSP_API int         fsp_device_set(int device);
 FSP_API int         fsp_device_get(int *device);
 FSP_API int         fsp_device_sm_count(int *count);
 FSP_API const char *fsp_last_error(void);
+/* Device memory comes from the stream-ordered pool of the LEGACY stream 0 (cudaMallocAsync / cudaFreeAsync on stream 0).
+ * The library's own streams are non-blocking and do not order against stream 0: every path that hands pool memory to
+ * another stream synchronises first (e.g. the host-vector pipeline calls fsp_stream_sync(NULL) before its copy streams
+ * touch the buffers), and callers that pass their own non-blocking stream to fspmat_ / fspvec_ functions must do the
+ * same after an fsp_malloc and before an fsp_free of memory that stream uses. */
 FSP_API int         fsp_malloc(void **ptr_dev, size_t bytes);
 FSP_API int         fsp_free(void *ptr_dev);
 FSP_API int         fsp_malloc_host(void **ptr_host, size_t bytes); /* pinned */
