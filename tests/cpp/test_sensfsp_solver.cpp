@@ -109,6 +109,97 @@ TEST_F(SensFspToggleTest, toggle_sens_solve_with_cvode) {
   for (arma::uword b = 0; b < sm.n_elem; ++b) ASSERT_NEAR(sm[b], ref[b], 1.0e-14 * (1.0 + std::fabs(ref[b])));
 }
 
+// Parity of the sensitivity solve beyond the KATs: ForwardSensCvodeFsp (BDF + staggered-1 corrector with
+// sensitivity error control) against an INDEPENDENT integrator -- classical RK4 with a small fixed step -- of the same
+// system  p' = A p,  s_i' = A s_i + (dA/dtheta_i) p  on a fixed state set (fsp_tol <= 0: no expansion), using the
+// sensitivity operator that KAT-SM1/SM2 and the finite-difference check of tests/cpp/test_sensmat.cpp pin.
+TEST_F(SensFspToggleTest, sens_solve_matches_independent_rk4_on_a_fixed_set) {
+  const double   T = 1.0;
+  arma::Row<int> big = {25, 25};
+  SensFspSolverMultiSinks fsp(PETSC_COMM_WORLD);
+  ASSERT_FALSE(fsp.SetModel(toggle_model));
+  ASSERT_FALSE(fsp.SetInitialBounds(big));
+  ASSERT_FALSE(fsp.SetExpansionFactors(expansion_factors));
+  ASSERT_FALSE(fsp.SetInitialDistribution(X0, p0, dp0));
+  ASSERT_FALSE(fsp.SetUp());
+  SensDiscreteDistribution d = fsp.Solve(T, -1.0);
+  fsp.ClearState();
+
+  // the same state set (same deterministic construction => same ordering) and operators
+  StateSetConstrained set(PETSC_COMM_WORLD);
+  set.SetStoichiometryMatrix(toggle_cme::SM);
+  set.SetShapeBounds(big);
+  set.SetUp();
+  ASSERT_FALSE(set.AddStates(X0));
+  ASSERT_FALSE(set.Expand());
+  ASSERT_EQ((int) set.GetNumLocalStates(), (int) d.states_.n_cols);
+  SensFspMatrix<FspMatrixConstrained> A(PETSC_COMM_WORLD);
+  ASSERT_FALSE(A.GenerateValues(set, toggle_model));
+  const int nr = A.GetNumLocalRows(), n = set.GetNumLocalStates(), P = 6;
+  auto mk = [&]() { Vec v; VecCreate(PETSC_COMM_WORLD, &v); VecSetSizes(v, nr, PETSC_DECIDE); VecSetUp(v); VecSet(v, 0.0); return v; };
+  std::vector<Vec> y(P + 1), k(P + 1), acc(P + 1), st(P + 1);
+  for (int i = 0; i <= P; ++i) { y[i] = mk(); k[i] = mk(); acc[i] = mk(); st[i] = mk(); }
+  Vec tmp = mk();
+  {  // p(0) = delta at X0 (local index of the initial state), s(0) = 0
+    arma::Row<int> idx = set.State2Index(X0);
+    int lo, hi;
+    VecGetOwnershipRange(y[0], &lo, &hi);
+    if (idx[0] >= lo && idx[0] < hi) VecSetValue(y[0], idx[0], 1.0, INSERT_VALUES);
+    VecAssemblyBegin(y[0]);
+    VecAssemblyEnd(y[0]);
+  }
+  auto rhs = [&](double t, std::vector<Vec> &in, std::vector<Vec> &out) {
+    A.Action(t, in[0], out[0]);
+    for (int i = 0; i < P; ++i) {
+      A.Action(t, in[i + 1], out[i + 1]);
+      A.SensAction(i, t, in[0], tmp);
+      VecAXPY(out[i + 1], 1.0, tmp);
+    }
+  };
+  const int    steps = 2000;
+  const double h = T / steps;
+  for (int s = 0; s < steps; ++s) {
+    const double t = s * h;
+    const double cw[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6}, cs[4] = {0.0, 0.5, 0.5, 1.0};
+    for (int i = 0; i <= P; ++i) VecSet(acc[i], 0.0);
+    for (int stage = 0; stage < 4; ++stage) {
+      for (int i = 0; i <= P; ++i) {
+        VecCopy(y[i], st[i]);
+        if (stage > 0) VecAXPY(st[i], cs[stage] * h, k[i]);
+      }
+      rhs(t + cs[stage] * h, st, k);
+      for (int i = 0; i <= P; ++i) VecAXPY(acc[i], cw[stage], k[i]);
+    }
+    for (int i = 0; i <= P; ++i) VecAXPY(y[i], h, acc[i]);
+  }
+  auto l1_first_n = [&](Vec a, Vec b) {  // 1-norm of the difference over the n state entries (the distribution has no sinks)
+    const PetscScalar *pa, *pb;
+    VecGetArrayRead(a, &pa);
+    std::vector<double> ca(pa, pa + n);
+    VecRestoreArrayRead(a, &pa);
+    VecGetArrayRead(b, &pb);
+    double e = 0.0;
+    for (int q = 0; q < n; ++q) e += std::fabs(ca[q] - pb[q]);
+    VecRestoreArrayRead(b, &pb);
+    pacmensl_allreduce_sum(PETSC_COMM_WORLD, &e, 1);
+    return e;
+  };
+  const double ep = l1_first_n(y[0], d.p_);
+  double       es = 0.0, smax = 0.0;
+  for (int i = 0; i < P; ++i) {
+    es = std::max(es, l1_first_n(y[i + 1], d.dp_[i]));
+    double nrm;
+    VecNorm(d.dp_[i], NORM_1, &nrm);
+    smax = std::max(smax, nrm);
+  }
+  std::printf("    fixed-set toggle sens (n = %d, t_f = %g): ||p_bdf - p_rk4||_1 = %.3e, max_i ||s_i,bdf - s_i,rk4||_1 = %.3e (max ||s_i||_1 = %.3e)\n",
+              n, T, ep, es, smax);
+  ASSERT_LE(ep, 1.0e-6);             // the reference's own bound for this solver (KAT-SF2: 1e-7 on p at rtol 1e-6 ... 1e-6 on s)
+  ASSERT_LE(es, 1.0e-5 * (1.0 + smax));
+  for (int i = 0; i <= P; ++i) { VecDestroy(&y[i]); VecDestroy(&k[i]); VecDestroy(&acc[i]); VecDestroy(&st[i]); }
+  VecDestroy(&tmp);
+}
+
 class SensFspPoissonTest : public ::testing::Test {
  protected:
   void SetUp() override {
