@@ -232,6 +232,26 @@ FSP_API int fspset_copy_status(fspset_t h, long first, long count, signed char *
  * Sys/pacmenMath.h:33-59 convention) -- the synthetic workload of SURVEY.md section 8(d). */
 FSP_API int fspset_add_box_lattice(fspset_t h, const int *upper_host);
 
+/* Sharded construction over N GPUs of one node (the reference distributes the frontier and the directory over the MPI
+ * ranks: src/StateSet/StateSetBase.cpp:134-154,188-258 with Zoltan_DD, and migrates states after load balancing:
+ * src/Partitioner/StatePartitionerBase.cpp:136-239).  After fspset_set_sharded (before any state is added; `comm` must
+ * have peer memory enabled) the set holds ONLY the local block of states; the hash directory is striped over the ranks'
+ * HBM (shard = hash % N) and probed / claimed through NVLink peer loads and system-scope atomics; add_states,
+ * add_box_lattice and expand become COLLECTIVE (every rank explores the frontier states it owns), and end with a
+ * re-balance to the contiguous equal-count BLOCK layout (rank r owns global indices [starts[r], starts[r+1])) followed
+ * by a rebuild of the directory.  Global index = starts[owner] + local position; unlike the replicated set it changes
+ * when the set grows (as in the reference), so callers that keep vectors re-map them through
+ * fspset_remember_local / fspset_remembered_indices.  `first` arguments of the per-row functions stay GLOBAL indices
+ * and must address local rows.  fspset_num_states returns the global count. */
+struct fspcomm_s;
+FSP_API int fspset_set_sharded(fspset_t h, struct fspcomm_s *comm);
+FSP_API int fspset_is_sharded(fspset_t h);
+FSP_API int fspset_layout(fspset_t h, long *starts_host /* n_ranks + 1 */, long *n_local);
+/* keep a device copy of the local block of states / afterwards: their current global indices (host array of the
+ * remembered length), the copy is released.  StateSetBase::State2Index(states_old) of FspSolverMultiSinks.cpp:174-205. */
+FSP_API int fspset_remember_local(fspset_t h);
+FSP_API int fspset_remembered_indices(fspset_t h, int *idx_host, long n_expected);
+
 /* ------------------------------------------------------------------------------------------------
  * Propensity evaluation on the device for models given in mass-action form
  *   d_r(x) = rate[r] * prod_s binom-like falling factorial of x_s of order ord[r*S+s] (0,1,2)
@@ -439,6 +459,15 @@ FSP_API int fsphalo_next(fsphalo_t h, fsphalo_epoch *out, fsphalo_push *push);
  * since then were poisoned with NaN by the waiting kernels.  Call after a synchronisation that consumes results. */
 FSP_API int fsphalo_check(fsphalo_t h);
 FSP_API int fspcomm_check(fspcomm_t c);
+/* General peer-memory windows (used by the sharded state set).  create / destroy are collective; peers[p] is this
+ * process' mapping of rank p's `bytes` bytes (peers[rank] = the local allocation).  retire is local: the window is
+ * pooled for a later create of the same size and freed with the communicator. */
+FSP_API int fspcomm_window_create(fspcomm_t c, size_t bytes, void **peers);
+FSP_API int fspcomm_window_destroy(fspcomm_t c, void **peers);
+FSP_API int fspcomm_window_retire(fspcomm_t c, void **peers, size_t bytes);
+/* stream-ordered barrier over all ranks / synchronising gather of one integer per rank */
+FSP_API int fspcomm_barrier(fspcomm_t c, void *stream);
+FSP_API int fspcomm_gather_long(fspcomm_t c, long mine, long *all_host);
 /* The whole multi-GPU Action (src/Matrix/FspMatrixBase.cpp:36-62 with the ghost VecScatter of MatMult on MATMPISELL,
  * and the sink VecScatter ADD of FspMatrixConstrained.cpp:57-60) as ONE launch on one stream, no events, no NCCL:
  *   leading CTAs   push: pack the boundary entries of x, store them into the peers' ghost windows, publish the epoch

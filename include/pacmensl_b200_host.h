@@ -41,6 +41,16 @@ FSP_API const char *pfsp_last_error(void);
 /* ---- state set ---- */
 FSP_API int pfsp_set_create(void **set);
 FSP_API int pfsp_set_destroy(void *set);
+/* Extension (multi-GPU): distributed construction as in src/StateSet/StateSetBase.cpp:134-154,188-258 -- every rank
+ * keeps and expands only its block of states, the directory is striped over the GPUs (fsp_b200.h: fspset_set_sharded).
+ * Call before the first pfsp_set_add_states; a no-op on one rank or without peer memory.  FSP_SHARDED_SET=1 in the
+ * environment turns it on for every set. */
+FSP_API int pfsp_set_set_sharded(void *set, int on);
+FSP_API int pfsp_set_is_sharded(void *set);
+/* State2Index(states_old) of src/Fsp/FspSolverMultiSinks.cpp:174-176 on the device: remember the local block before
+ * pfsp_set_expand, ask for the global indices those n states have afterwards */
+FSP_API int pfsp_set_remember_local(void *set);
+FSP_API int pfsp_set_remembered_indices(void *set, int n, int *idx);
 FSP_API int pfsp_set_stoichiometry(void *set, int S, int R, const int *SM_colmajor);
 FSP_API int pfsp_set_shape(void *set, int K, const int *bounds, pfsp_constr_fn lhs_or_null, void *args);
 FSP_API int pfsp_set_shape_bounds(void *set, int K, const int *bounds);
@@ -100,6 +110,8 @@ FSP_API int pfsp_solver_set_krylov(void *solver, int q_iop, int m_min, int m_max
  * expansions -- correct but measured slower */
 FSP_API int pfsp_solver_set_warm_restart(void *solver, int on);
 FSP_API int pfsp_solver_num_warm_restarts(void *solver, int *n);
+/* Extension: build the solver's state set sharded over the ranks (pfsp_set_set_sharded); before pfsp_solver_setup */
+FSP_API int pfsp_solver_set_sharded_state_set(void *solver, int on);
 FSP_API int pfsp_solver_setup(void *solver);
 /* Solve to t_final; *n_local receives the number of local states of the result (kept inside the handle) */
 FSP_API int pfsp_solver_solve(void *solver, double t_final, double fsp_tol, double t_init, int *n_local, int *n_species);

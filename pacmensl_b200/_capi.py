@@ -123,6 +123,11 @@ SIGNATURES = {
     "fspset_copy_states": (ci, [vp, cl, cl, ip]),
     "fspset_copy_status": (ci, [vp, cl, cl, C.POINTER(C.c_byte)]),
     "fspset_add_box_lattice": (ci, [vp, ip]),
+    "fspset_set_sharded": (ci, [vp, vp]),
+    "fspset_is_sharded": (ci, [vp]),
+    "fspset_layout": (ci, [vp, lp, lp]),
+    "fspset_remember_local": (ci, [vp]),
+    "fspset_remembered_indices": (ci, [vp, ip, cl]),
     "fspset_eval_mass_action": (ci, [vp, cd, ip, ip, ci, cl, cl, vp]),
     "fspset_eval_separable": (ci, [vp, cd, ip, vp, ip, ip, ip, ci, cl, cl, vp]),
     "fspmat_create": (ci, [vpp]),
@@ -170,6 +175,11 @@ SIGNATURES = {
     "fsphalo_next": (ci, [vp, vp, vp]),
     "fsphalo_check": (ci, [vp]),
     "fspcomm_check": (ci, [vp]),
+    "fspcomm_window_create": (ci, [vp, C.c_size_t, vpp]),
+    "fspcomm_window_destroy": (ci, [vp, vpp]),
+    "fspcomm_window_retire": (ci, [vp, vpp, C.c_size_t]),
+    "fspcomm_barrier": (ci, [vp, vp]),
+    "fspcomm_gather_long": (ci, [vp, cl, lp]),
     "fspmat_action_halo": (ci, [vp, dp, vp, vp, vp, vp, vp]),
     "fspmat_halo_fused_supported": (ci, [vp]),
     "fspmat_action_halo_part": (ci, [vp, dp, vp, vp, vp, vp, ci, cl, cl, ci, vp, vp]),

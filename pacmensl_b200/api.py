@@ -61,6 +61,11 @@ HOST_SIGNATURES = {
     "pfsp_solver_set_verbosity": (ci, [vp, ci]),
     "pfsp_solver_set_krylov": (ci, [vp, ci, ci, ci]),
     "pfsp_solver_set_warm_restart": (ci, [vp, ci]),
+    "pfsp_solver_set_sharded_state_set": (ci, [vp, ci]),
+    "pfsp_set_set_sharded": (ci, [vp, ci]),
+    "pfsp_set_is_sharded": (ci, [vp]),
+    "pfsp_set_remember_local": (ci, [vp]),
+    "pfsp_set_remembered_indices": (ci, [vp, ci, ip]),
     "pfsp_solver_num_warm_restarts": (ci, [vp, ip]),
     "pfsp_solver_setup": (ci, [vp]),
     "pfsp_solver_solve": (ci, [vp, cd, cd, cd, ip, ip]),
@@ -134,13 +139,15 @@ def p2p_enabled():
 
 
 class StateSet:
-    def __init__(self, SM):
+    def __init__(self, SM, sharded=False):
         SM = np.asarray(SM, dtype=np.int32)  # S x R as written in the reference
         self.S, self.R = SM.shape
         self._sm = np.ascontiguousarray(SM.T)
         h = vp()
         check(lib().pfsp_set_create(C.byref(h)), "pfsp_set_create")
         self.h = h
+        if sharded:  # multi-GPU: distributed construction, striped directory (a no-op on one rank)
+            check(lib().pfsp_set_set_sharded(self.h, 1), "SetSharded")
         check(lib().pfsp_set_stoichiometry(self.h, self.S, self.R, _ip(self._sm)), "SetStoichiometryMatrix")
         self._keep = []
 
@@ -181,6 +188,18 @@ class StateSet:
 
     def expand(self):
         return lib().pfsp_set_expand(self.h)
+
+    def is_sharded(self):
+        return bool(lib().pfsp_set_is_sharded(self.h))
+
+    def remember_local(self):
+        self._n_rem = self.n_local
+        return lib().pfsp_set_remember_local(self.h)
+
+    def remembered_indices(self):
+        out = np.empty(self._n_rem, dtype=np.int32)
+        check(lib().pfsp_set_remembered_indices(self.h, self._n_rem, _ip(out)), "RememberedIndices")
+        return out
 
     def sizes(self):
         a, b, c = ci(), ci(), ci()
@@ -372,6 +391,9 @@ class FspSolver:
     def set_krylov(self, q_iop=2, m_min=25, m_max=60):
         return lib().pfsp_solver_set_krylov(self.h, q_iop, m_min, m_max)
 
+    def set_sharded_state_set(self, on=True):
+        return lib().pfsp_solver_set_sharded_state_set(self.h, 1 if on else 0)
+
     def set_warm_restart(self, on):
         return lib().pfsp_solver_set_warm_restart(self.h, 1 if on else 0)
 
@@ -401,11 +423,11 @@ class FspSolver:
         return lib().pfsp_solver_clear(self.h)
 
 
-def fixture_set_and_matrix(name, bounds=None, model=None, constrained=True):
+def fixture_set_and_matrix(name, bounds=None, model=None, constrained=True, sharded=False):
     """StateSetConstrained (x0 added, Expand()ed within `bounds`) + generated FspMatrix of a named workload."""
     m = model or Model(fixture=name)
     fx = m.fixture
-    st = StateSet(m.stoichiometry())
+    st = StateSet(m.stoichiometry(), sharded=sharded)
     b = fx["bounds"] if bounds is None else bounds
     ierr = st.set_shape(b, lhs_c=fx["lhs"])
     assert ierr == 0, ierr

@@ -121,6 +121,8 @@ struct fspcomm_s {
   double            *stage = nullptr;     // small device staging buffer of the set-up collectives (handles, agreement flags)
   struct PooledHalo { PeerWindow win; size_t cap = 0; unsigned long long epoch = 0; };
   std::vector<PooledHalo> halo_pool;  // windows returned by fsphalo_destroy, identical order/capacity on all ranks
+  std::vector<PeerWindow> retired;    // general windows given back without a collective (fspcomm_window_retire)
+  double            *coll = nullptr;  // device scratch of fspcomm_barrier / fspcomm_gather_long (kMaxRanks + 1 doubles)
 };
 
 struct fsphalo_s {
@@ -351,6 +353,10 @@ int fspcomm_destroy(fspcomm_t c) {
     }
     for (auto &w : c->halo_pool) window_destroy(c, &w.win);
     c->halo_pool.clear();
+    for (auto &w : c->retired) window_destroy(c, &w);
+    c->retired.clear();
+    if (c->coll) cudaFree(c->coll);
+    c->coll = nullptr;
     window_destroy(c, &c->ctrl);
     if (c->err_host) cudaFreeHost(c->err_host);
     c->p2p = false;
@@ -588,5 +594,78 @@ int fsphalo_next(fsphalo_t h, fsphalo_epoch *out, fsphalo_push *push) {
 int fsphalo_check(fsphalo_t h) { return h ? check_peer_error(h->c, "fsphalo_check") : 0; }
 
 int fspcomm_check(fspcomm_t c) { return (c && c->p2p) ? check_peer_error(c, "fspcomm_check") : 0; }
+
+// ---- general peer-memory windows (sharded state set: fspset.cu) ------------------------------------
+// Collective.  peers[p] = this process' mapping of rank p's window (peers[rank] = the local allocation), all of
+// `bytes` bytes.  A retired window of the same size is reused when there is one (identical sequence on all ranks).
+int fspcomm_window_create(fspcomm_t c, size_t bytes, void **peers) {
+  if (!c || !c->p2p) { set_error("fspcomm_window_create: peer memory is not enabled on this communicator"); return -1; }
+  for (size_t i = 0; i < c->retired.size(); ++i)
+    if (c->retired[i].bytes == bytes) {
+      for (int p = 0; p < c->size; ++p) peers[p] = c->retired[i].peer[p];
+      c->retired.erase(c->retired.begin() + (long) i);
+      return 0;
+    }
+  PeerWindow w;
+  if (window_create(c, bytes, &w)) return -1;
+  for (int p = 0; p < c->size; ++p) peers[p] = w.peer[p];
+  return 0;
+}
+
+// Collective: every rank has finished using the window (its own part AND the peers' parts).
+int fspcomm_window_destroy(fspcomm_t c, void **peers) {
+  if (!c || !peers || !peers[c->rank]) return 0;
+  cudaDeviceSynchronize();
+  int rc = agree(c, true);  // nobody is still reading or writing through a mapping
+  PeerWindow w;
+  w.local = peers[c->rank];
+  for (int p = 0; p < c->size; ++p) { w.peer[p] = peers[p]; if (p != c->rank && peers[p]) cudaIpcCloseMemHandle(peers[p]); w.peer[p] = nullptr; }
+  if (agree(c, true) < 0) rc = -1;  // every mapping is closed before the memory goes away
+  cudaFree(w.local);
+  for (int p = 0; p < c->size; ++p) peers[p] = nullptr;
+  cudaGetLastError();
+  return rc < 0 ? -1 : 0;
+}
+
+// NOT collective: the window goes to the communicator's pool (reused by a later fspcomm_window_create of the same size,
+// unmapped and freed by fspcomm_destroy).  For destructors, whose order between ranks is not defined.
+int fspcomm_window_retire(fspcomm_t c, void **peers, size_t bytes) {
+  if (!c || !peers || !peers[c->rank]) return 0;
+  PeerWindow w;
+  w.bytes = bytes;
+  w.local = peers[c->rank];
+  for (int p = 0; p < c->size; ++p) { w.peer[p] = peers[p]; peers[p] = nullptr; }
+  c->retired.push_back(w);
+  return 0;
+}
+
+static int coll_scratch(fspcomm_s *c) {
+  if (c->coll) return 0;
+  FSP_CUDA_CHECK(cudaMalloc(&c->coll, sizeof(double) * (kMaxRanks + 1)));
+  FSP_CUDA_CHECK(cudaMemset(c->coll, 0, sizeof(double) * (kMaxRanks + 1)));
+  return 0;
+}
+
+// Stream-ordered barrier: work enqueued after it on `stream` starts only when every rank's work enqueued before its own
+// barrier call has finished (one small all-reduce kernel over peer memory; NCCL otherwise).
+int fspcomm_barrier(fspcomm_t c, void *stream) {
+  if (!c || c->size == 1) return 0;
+  if (coll_scratch(c)) return -1;
+  return fspcomm_allreduce_sum(c, c->coll + kMaxRanks, 1, stream);
+}
+
+// Collective, synchronising: all_host[p] = the value rank p passed (|value| < 2^53).
+int fspcomm_gather_long(fspcomm_t c, long mine, long *all_host) {
+  if (!c || c->size == 1) { all_host[0] = mine; return 0; }
+  if (c->size > kMaxRanks) { set_error("fspcomm_gather_long: more than %d ranks", kMaxRanks); return -1; }
+  if (coll_scratch(c)) return -1;
+  double v[kMaxRanks];
+  for (int p = 0; p < c->size; ++p) v[p] = p == c->rank ? (double) mine : 0.0;
+  FSP_CUDA_CHECK(cudaMemcpy(c->coll, v, sizeof(double) * c->size, cudaMemcpyHostToDevice));
+  if (fspcomm_allreduce_sum(c, c->coll, c->size, nullptr)) return -1;
+  FSP_CUDA_CHECK(cudaMemcpy(v, c->coll, sizeof(double) * c->size, cudaMemcpyDeviceToHost));
+  for (int p = 0; p < c->size; ++p) all_host[p] = (long) v[p];
+  return check_peer_error(c, "fspcomm_gather_long");
+}
 
 }  // extern "C"

@@ -17,6 +17,17 @@
 // duplicate keys with atomicMin on the id, so the FIRST occurrence wins regardless of thread timing;
 // winners are then compacted in order (prefix sum) -> the appended order is first-discovery order,
 // identical to the CPU oracle (oracle/fsp_oracle.c: orc_set_expand).
+//
+// Sharded mode (fspset_set_sharded, N GPUs of one node): each rank keeps only its block of states; the directory is a
+// table of 64-bit slots striped over the ranks' HBM (shard = hash % N) inside CUDA-IPC peer windows, probed with NVLink
+// peer loads and claimed with system-scope atomicCAS / atomicMin.  A slot holds (is_candidate, rank, position): the key
+// is read from the owner's state list -- or, while a batch is in flight, from the owner's candidate buffer -- through
+// the same peer mapping.  Every rank expands the frontier states it owns; duplicates across ranks are resolved by
+// atomicMin (existing states beat candidates, then the lowest rank, then the lowest position: deterministic for a given
+// N); winners are appended on the discovering rank.  Three stream-ordered barriers per batch (candidates written /
+// claims complete / final values stored) are the only synchronisation.  The set is then re-balanced to the contiguous
+// equal-count BLOCK layout by peer-to-peer copies that preserve the rank-concatenated order, and the directory is
+// rebuilt with the new positions.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -285,6 +296,157 @@ struct NotFlag {
   __host__ __device__ int operator()(int i) const { return sat[i] == 0 ? 1 : 0; }
 };
 
+// ---- sharded directory (see the file header) -------------------------------------------------------------------
+constexpr int                kMaxRanksS = FSP_P2P_MAX_RANKS;
+constexpr unsigned long long kEmpty64 = ~0ull;
+constexpr unsigned long long kCandBit = 1ull << 62;       // the slot names a candidate of the batch in flight
+constexpr unsigned long long kIdxMask = (1ull << 40) - 1;  // position inside the owner's state list / candidate buffer
+
+struct ShardView {
+  int                 size, rank, S;
+  unsigned long long  mask;  // slots per shard - 1
+  unsigned long long *table[kMaxRanksS];
+  const int          *states[kMaxRanksS];
+  const int          *cand[kMaxRanksS];
+  int                 starts[kMaxRanksS + 1];
+  int                *err;
+};
+
+__device__ __forceinline__ const int *sh_key_of(const ShardView &v, unsigned long long val) {
+  const int r = (int) ((val >> 40) & 0xFFFFull);
+  return ((val & kCandBit) ? v.cand[r] : v.states[r]) + (size_t) (val & kIdxMask) * v.S;
+}
+// `there` may live in a peer's HBM and may have been written by a kernel of that peer: read through L2, not L1
+__device__ __forceinline__ bool sh_key_equal(const int *there, const int *key, int S) {
+  for (int s = 0; s < S; ++s)
+    if (__ldcg(there + s) != key[s]) return false;
+  return true;
+}
+__device__ __forceinline__ void sh_home(const ShardView &v, const int *key, int &shard, unsigned long long &slot) {
+  const unsigned long long h = hash_state(key, v.S);
+  shard = (int) ((h >> 40) % (unsigned long long) v.size);
+  slot = h & v.mask;
+}
+__device__ __forceinline__ unsigned long long sh_load(const unsigned long long *p) {
+  return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// Claim: first pass of a batch.  Candidate c of this rank carries the value (candidate, rank, c).
+__global__ void sh_insert_kernel(const __grid_constant__ ShardView v, long m, const signed char *valid) {
+  const long c = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  if (valid && !valid[c]) return;
+  const int               *key = v.cand[v.rank] + (size_t) c * v.S;
+  const unsigned long long me = kCandBit | ((unsigned long long) v.rank << 40) | (unsigned long long) c;
+  int                      shard;
+  unsigned long long       slot;
+  sh_home(v, key, shard, slot);
+  unsigned long long *table = v.table[shard];
+  for (unsigned long long probe = 0; probe <= v.mask; ++probe) {
+    unsigned long long cur = sh_load(table + slot);
+    if (cur == kEmpty64) {
+      const unsigned long long prev = atomicCAS_system(table + slot, kEmpty64, me);
+      if (prev == kEmpty64) return;
+      cur = prev;
+    }
+    if (sh_key_equal(sh_key_of(v, cur), key, v.S)) {
+      atomicMin_system(table + slot, me);  // a stored state (no candidate bit) always stays
+      return;
+    }
+    slot = (slot + 1) & v.mask;
+  }
+  atomicExch(v.err, 1);
+}
+
+// Second pass (after every rank's claims are complete): flag[c] = 1 iff candidate c holds the slot of its key.
+__global__ void sh_winner_kernel(const __grid_constant__ ShardView v, long m, const signed char *valid, int *flag,
+                                 unsigned long long *slot_out) {
+  const long c = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m) return;
+  int f = 0;
+  if (!valid || valid[c]) {
+    const int               *key = v.cand[v.rank] + (size_t) c * v.S;
+    const unsigned long long me = kCandBit | ((unsigned long long) v.rank << 40) | (unsigned long long) c;
+    int                      shard;
+    unsigned long long       slot;
+    sh_home(v, key, shard, slot);
+    const unsigned long long *table = v.table[shard];
+    for (unsigned long long probe = 0; probe <= v.mask; ++probe) {
+      const unsigned long long cur = sh_load(table + slot);
+      if (cur == kEmpty64) break;  // cannot happen for a claimed key
+      if (cur == me) { f = 1; slot_out[c] = ((unsigned long long) shard << 56) | slot; break; }
+      // another rank may already be replacing its winning candidates by stored states: either names an equal key
+      if (sh_key_equal(sh_key_of(v, cur), key, v.S)) break;
+      slot = (slot + 1) & v.mask;
+    }
+  }
+  flag[c] = f;
+}
+
+// Third pass: winners become states of THIS rank; the slot receives (rank, position) after the key is in place.
+__global__ void sh_append_kernel(const __grid_constant__ ShardView v, int *states, signed char *status, long n_old, long m,
+                                 const int *flag, const int *pos, const unsigned long long *slot_in) {
+  const long c = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m || !flag[c]) return;
+  const long dst = n_old + pos[c];
+  const int *key = v.cand[v.rank] + (size_t) c * v.S;
+  for (int s = 0; s < v.S; ++s) states[(size_t) dst * v.S + s] = key[s];
+  status[dst] = 1;
+  __threadfence_system();
+  const unsigned long long sl = slot_in[c];
+  atomicExch_system(v.table[(int) (sl >> 56)] + (sl & ((1ull << 56) - 1)), ((unsigned long long) v.rank << 40) | (unsigned long long) dst);
+}
+
+// Rebuild: every stored state of this rank claims a slot (all keys are distinct).
+__global__ void sh_rehash_kernel(const __grid_constant__ ShardView v, long n) {
+  const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int               *key = v.states[v.rank] + (size_t) i * v.S;
+  const unsigned long long me = ((unsigned long long) v.rank << 40) | (unsigned long long) i;
+  int                      shard;
+  unsigned long long       slot;
+  sh_home(v, key, shard, slot);
+  unsigned long long *table = v.table[shard];
+  for (unsigned long long probe = 0; probe <= v.mask; ++probe) {
+    if (atomicCAS_system(table + slot, kEmpty64, me) == kEmpty64) return;
+    slot = (slot + 1) & v.mask;
+  }
+  atomicExch(v.err, 1);
+}
+
+// State2Index on the striped directory: global index = starts[owner] + position
+__device__ __forceinline__ int sh_lookup(const ShardView &v, const int *key) {
+  for (int s = 0; s < v.S; ++s)
+    if (key[s] < 0) return -1;
+  int                shard;
+  unsigned long long slot;
+  sh_home(v, key, shard, slot);
+  const unsigned long long *table = v.table[shard];
+  for (unsigned long long probe = 0; probe <= v.mask; ++probe) {
+    const unsigned long long cur = __ldcg(table + slot);
+    if (cur == kEmpty64) return -1;
+    if (sh_key_equal(sh_key_of(v, cur), key, v.S)) return v.starts[(int) ((cur >> 40) & 0xFFFFull)] + (int) (cur & kIdxMask);
+    slot = (slot + 1) & v.mask;
+  }
+  return -1;
+}
+__global__ void sh_lookup_kernel(const __grid_constant__ ShardView v, const int *X, long m, int *idx) {
+  const long j = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  int key[kMaxS];
+  for (int s = 0; s < v.S; ++s) key[s] = X[(size_t) j * v.S + s];
+  idx[j] = sh_lookup(v, key);
+}
+__global__ void sh_lookup_shifted_kernel(const __grid_constant__ ShardView v, long first_local, long count, SmallVec nu,
+                                         int sign, int *idx) {
+  const long j = (long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  int        key[kMaxS];
+  const int *x = v.states[v.rank] + (size_t) (first_local + j) * v.S;
+  for (int s = 0; s < v.S; ++s) key[s] = x[s] + sign * nu.v[s];
+  idx[j] = sh_lookup(v, key);
+}
+
 inline unsigned blocks_for(long m) { return (unsigned) ((m + 255) / 256); }
 
 }  // namespace
@@ -308,6 +470,20 @@ struct fspset_s {
   void        *d_cub = nullptr;        size_t cub_bytes = 0;
   bool             expanded = false;   // Expand() has run: status 0 <=> all children inside the set
   std::vector<int> expanded_bounds;    // bounds at the last Expand()
+  long             base = 0;           // global index of local state 0 (0 unless sharded)
+  int             *d_rem = nullptr;    // fspset_remember_local
+  long             n_rem = 0;
+  // ---- sharded mode: n / cap / d_states / d_status / d_cand describe the LOCAL block ----
+  bool               sharded = false;
+  fspcomm_s         *comm = nullptr;
+  int                rank = 0, size = 1;
+  long               n_glob = 0;
+  std::vector<long>  counts, starts;   // states per rank now / BLOCK layout after the last re-balance (size + 1)
+  void              *win_data[FSP_P2P_MAX_RANKS] = {nullptr};   // [states cap*S int | status cap bytes], same cap on all ranks
+  void              *win_cand[FSP_P2P_MAX_RANKS] = {nullptr};   // candidate keys of the batch in flight
+  void              *win_table[FSP_P2P_MAX_RANKS] = {nullptr};  // tsize 64-bit slots per rank
+  size_t             data_bytes = 0, cand_bytes = 0, table_bytes = 0;
+  int               *d_err = nullptr;  // probe bound exceeded (a full shard)
 };
 
 namespace {
@@ -441,6 +617,290 @@ int host_validity(fspset_s *h, long m, std::vector<int> &cand_host, std::vector<
   return 0;
 }
 
+
+// ---- sharded mode, host side (every function below is COLLECTIVE: same call sequence and arguments on all ranks) ----
+ShardView make_view(const fspset_s *h) {
+  ShardView v;
+  memset(&v, 0, sizeof(v));
+  v.size = h->size; v.rank = h->rank; v.S = h->S;
+  v.mask = h->tsize ? h->tsize - 1 : 0;
+  for (int p = 0; p < h->size; ++p) {
+    v.table[p] = (unsigned long long *) h->win_table[p];
+    v.states[p] = (const int *) h->win_data[p];
+    v.cand[p] = (const int *) h->win_cand[p];
+  }
+  for (int p = 0; p <= h->size; ++p) v.starts[p] = (int) h->starts[(size_t) p];
+  v.err = h->d_err;
+  return v;
+}
+
+int sh_barrier(fspset_s *h) { return fspcomm_barrier(h->comm, nullptr); }
+
+int sh_check(fspset_s *h, const char *where) {
+  int e = 0;
+  FSP_CUDA_CHECK(cudaMemcpy(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (e) { set_error("fspset (sharded), %s: a directory shard is full", where); return -1; }
+  return fspcomm_check(h->comm);
+}
+
+int sh_gather(fspset_s *h, long mine, std::vector<long> &all) {
+  all.assign((size_t) h->size, 0);
+  return fspcomm_gather_long(h->comm, mine, all.data());
+}
+
+size_t sh_data_bytes(const fspset_s *h, long cap) {
+  return (((size_t) cap * h->S * sizeof(int) + (size_t) cap) + 255) / 256 * 256;
+}
+
+// local block -> a window of capacity new_cap (the old window is released)
+int sh_data_resize(fspset_s *h, long new_cap) {
+  void *nw[kMaxRanksS] = {nullptr};
+  const size_t bytes = sh_data_bytes(h, new_cap);
+  if (fspcomm_window_create(h->comm, bytes, nw)) return -1;
+  int         *ns = (int *) nw[h->rank];
+  signed char *nst = (signed char *) (ns + (size_t) new_cap * h->S);
+  if (h->n > 0) {
+    FSP_CUDA_CHECK(cudaMemcpy(ns, h->d_states, sizeof(int) * (size_t) h->n * h->S, cudaMemcpyDeviceToDevice));
+    FSP_CUDA_CHECK(cudaMemcpy(nst, h->d_status, (size_t) h->n, cudaMemcpyDeviceToDevice));
+  }
+  FSP_CUDA_CHECK(cudaDeviceSynchronize());
+  if (h->win_data[h->rank] && fspcomm_window_destroy(h->comm, h->win_data)) return -1;
+  for (int p = 0; p < h->size; ++p) h->win_data[p] = nw[p];
+  h->d_states = ns; h->d_status = nst; h->cap = new_cap; h->data_bytes = bytes;
+  return 0;
+}
+
+int sh_rehash_all(fspset_s *h, const char *where) {
+  if (sh_barrier(h)) return -1;  // every shard is cleared / every block is in place
+  if (h->n > 0) {
+    sh_rehash_kernel<<<blocks_for(h->n), 256>>>(make_view(h), h->n);
+    FSP_LAUNCH_CHECK();
+  }
+  if (sh_barrier(h)) return -1;
+  return sh_check(h, where);
+}
+
+int sh_table_resize(fspset_s *h, unsigned long long want) {
+  void *nw[kMaxRanksS] = {nullptr};
+  const size_t bytes = sizeof(unsigned long long) * want;
+  if (fspcomm_window_create(h->comm, bytes, nw)) return -1;
+  FSP_CUDA_CHECK(cudaMemset(nw[h->rank], 0xFF, bytes));
+  FSP_CUDA_CHECK(cudaDeviceSynchronize());
+  if (h->win_table[h->rank] && fspcomm_window_destroy(h->comm, h->win_table)) return -1;
+  for (int p = 0; p < h->size; ++p) h->win_table[p] = nw[p];
+  h->tsize = want; h->table_bytes = bytes;
+  return sh_rehash_all(h, "table growth");
+}
+
+int sh_cand_resize(fspset_s *h, long m) {
+  void *nw[kMaxRanksS] = {nullptr};
+  const size_t bytes = (sizeof(int) * (size_t) m * h->S + 255) / 256 * 256;
+  if (h->win_cand[h->rank] && fspcomm_window_destroy(h->comm, h->win_cand)) return -1;
+  if (fspcomm_window_create(h->comm, bytes, nw)) return -1;
+  for (int p = 0; p < h->size; ++p) h->win_cand[p] = nw[p];
+  h->d_cand = (int *) nw[h->rank];
+  h->cand_bytes = bytes;
+  pfree(h->d_valid); pfree(h->d_slot);
+  h->d_valid = nullptr; h->d_slot = nullptr;
+  FSP_CUDA_CHECK(pmalloc(&h->d_valid, (size_t) m));
+  FSP_CUDA_CHECK(pmalloc(&h->d_slot, sizeof(unsigned long long) * (size_t) m));
+  h->cand_cap = m;
+  return 0;
+}
+
+// room for `max_loc_after` states on the fullest rank, `glob_after` states in the directory, `max_batch` candidates
+int sh_reserve(fspset_s *h, long max_loc_after, long glob_after, long max_batch) {
+  if (glob_after >= 0x7FFFFFF0L) { set_error("fspset: more than 2^31 states"); return -1; }
+  if (max_loc_after > h->cap) {
+    const long nc = std::max(max_loc_after, h->cap + h->cap / 2 + 1024);
+    if (sh_data_resize(h, nc)) return -1;
+  }
+  unsigned long long want = h->tsize ? h->tsize : 1024;
+  const unsigned long long per_shard = (unsigned long long) ((glob_after + h->size - 1) / h->size);
+  while (per_shard * 5 / 2 + 64 > want) want *= 2;  // average load <= 0.4; the shards of a good hash differ by O(sqrt)
+  if (want != h->tsize && sh_table_resize(h, want)) return -1;
+  if (max_batch > h->cand_cap && sh_cand_resize(h, std::max(max_batch, 4096L))) return -1;
+  return 0;
+}
+
+// One batch: the m local candidates in h->d_cand (validity in h->d_valid unless all_valid).  m may be 0 on this rank.
+int sh_insert_batch(fspset_s *h, long m, bool all_valid) {
+  const ShardView     v = make_view(h);
+  const signed char *valid = all_valid ? nullptr : h->d_valid;
+  if (sh_barrier(h)) return -1;  // every rank's candidates are written, the previous batch is complete
+  if (m > 0) {
+    sh_insert_kernel<<<blocks_for(m), 256>>>(v, m, valid);
+    FSP_LAUNCH_CHECK();
+  }
+  if (sh_barrier(h)) return -1;  // all claims are in
+  if (m > 0) {
+    if (ensure_flags(h, m)) return -1;
+    sh_winner_kernel<<<blocks_for(m), 256>>>(v, m, valid, h->d_flag, h->d_slot);
+    FSP_LAUNCH_CHECK();
+    long total = 0;
+    if (scan_flags(h, m, &total)) return -1;
+    if (total > 0) {
+      if (h->n + total > h->cap) { set_error("fspset (sharded): local capacity %ld exceeded", h->cap); return -1; }
+      sh_append_kernel<<<blocks_for(m), 256>>>(v, h->d_states, h->d_status, h->n, m, h->d_flag, h->d_pos, h->d_slot);
+      FSP_LAUNCH_CHECK();
+      h->n += total;
+    }
+  }
+  if (sh_barrier(h)) return -1;  // winners are stored everywhere; the candidate buffers may be overwritten
+  return sh_check(h, "insertion");
+}
+
+// Re-balance to the BLOCK layout (h->counts must be current).  The rank-concatenated order of the states is kept:
+// rank r pulls positions [T_r, T_r+1) of the concatenation out of the peers' windows; then the directory is rebuilt.
+int sh_rebalance(fspset_s *h) {
+  const int N = h->size;
+  long      n = 0;
+  std::vector<long> C((size_t) N + 1, 0), T((size_t) N + 1, 0);
+  for (int r = 0; r < N; ++r) { C[(size_t) r + 1] = C[(size_t) r] + h->counts[(size_t) r]; }
+  n = C[(size_t) N];
+  const long base = n / N, rem = n % N;
+  for (int r = 0; r < N; ++r) T[(size_t) r + 1] = T[(size_t) r] + base + (r < rem ? 1 : 0);
+  h->n_glob = n;
+  const bool same = C == T;
+  if (!same) {
+    const long   new_cap = std::max(h->cap, base + 1 + 1024);
+    void        *nw[kMaxRanksS] = {nullptr};
+    const size_t bytes = sh_data_bytes(h, new_cap);
+    if (fspcomm_window_create(h->comm, bytes, nw)) return -1;
+    FSP_CUDA_CHECK(cudaDeviceSynchronize());
+    if (sh_barrier(h)) return -1;  // every block is final, every new window exists
+    FSP_CUDA_CHECK(cudaDeviceSynchronize());
+    int         *ns = (int *) nw[h->rank];
+    signed char *nst = (signed char *) (ns + (size_t) new_cap * h->S);
+    const long   lo_me = T[(size_t) h->rank], hi_me = T[(size_t) h->rank + 1];
+    for (int q = 0; q < N; ++q) {
+      const long lo = std::max(lo_me, C[(size_t) q]), hi = std::min(hi_me, C[(size_t) q + 1]);
+      if (lo >= hi) continue;
+      const int         *src = (const int *) h->win_data[q];
+      const signed char *src_st = (const signed char *) (src + (size_t) h->cap * h->S);
+      FSP_CUDA_CHECK(cudaMemcpyAsync(ns + (size_t) (lo - lo_me) * h->S, src + (size_t) (lo - C[(size_t) q]) * h->S,
+                                     sizeof(int) * (size_t) (hi - lo) * h->S, cudaMemcpyDefault, 0));
+      FSP_CUDA_CHECK(cudaMemcpyAsync(nst + (lo - lo_me), src_st + (lo - C[(size_t) q]), (size_t) (hi - lo), cudaMemcpyDefault, 0));
+    }
+    FSP_CUDA_CHECK(cudaDeviceSynchronize());
+    if (fspcomm_window_destroy(h->comm, h->win_data)) return -1;  // (synchronises the ranks first: all pulls are done)
+    for (int p = 0; p < N; ++p) h->win_data[p] = nw[p];
+    h->d_states = ns; h->d_status = nst; h->cap = new_cap; h->data_bytes = bytes;
+    h->n = hi_me - lo_me;
+    for (int r = 0; r < N; ++r) h->counts[(size_t) r] = T[(size_t) r + 1] - T[(size_t) r];
+  }
+  h->base = T[(size_t) h->rank];
+  h->starts = T;
+  if (!same) {
+    FSP_CUDA_CHECK(cudaMemsetAsync(h->win_table[h->rank], 0xFF, h->table_bytes, 0));
+    if (sh_rehash_all(h, "re-balance")) return -1;
+  }
+  return 0;
+}
+
+int sh_refresh_counts(fspset_s *h) {
+  if (sh_gather(h, h->n, h->counts)) return -1;
+  h->n_glob = 0;
+  for (long c : h->counts) h->n_glob += c;
+  return 0;
+}
+
+// AddStates / the lattice: `fill(b, mb)` writes the candidates [b, b + mb) of this rank's list into h->d_cand
+template <class Fill>
+int sh_add(fspset_s *h, long m, Fill fill) {
+  std::vector<long> ms;
+  if (sh_gather(h, m, ms)) return -1;
+  long maxM = 0, sumM = 0, maxN = 0;
+  for (int p = 0; p < h->size; ++p) { maxM = std::max(maxM, ms[(size_t) p]); sumM += ms[(size_t) p]; maxN = std::max(maxN, h->counts[(size_t) p]); }
+  if (maxM == 0) return 0;
+  if (sh_reserve(h, maxN + maxM, h->n_glob + sumM, std::min(kBatch, maxM))) return -1;
+  for (long b = 0; b < maxM; b += kBatch) {
+    const long mb = std::max(0L, std::min(kBatch, m - b));
+    if (mb > 0 && fill(b, mb)) return -1;
+    if (sh_insert_batch(h, mb, true)) return -1;
+  }
+  if (sh_refresh_counts(h)) return -1;
+  return sh_rebalance(h);
+}
+
+int sh_expand(fspset_s *h, int *&d_frontier, signed char *&d_fstatus) {
+  const int use_default = h->lhs ? 0 : 1;
+  const int N = h->size;
+  if (h->n > 0) {
+    reactivate_kernel<<<blocks_for(h->n), 256>>>(h->d_status, h->n);
+    FSP_LAUNCH_CHECK();
+  }
+  long                     fcap = 0;
+  std::vector<int>         cand_host, fval;
+  std::vector<signed char> valid_host;
+  std::vector<long>        nFs;
+  while (true) {
+    const long n = h->n;
+    long       nF = 0;
+    if (n > 0) {
+      if (ensure_flags(h, n)) return -1;
+      status_flag_kernel<<<blocks_for(n), 256>>>(h->d_status, n, 1, h->d_flag);
+      FSP_LAUNCH_CHECK();
+      if (scan_flags(h, n, &nF)) return -1;
+    }
+    if (sh_gather(h, nF, nFs)) return -1;
+    if (sh_refresh_counts(h)) return -1;
+    long sumF = 0, maxF = 0, maxN = 0;
+    for (int p = 0; p < N; ++p) { sumF += nFs[(size_t) p]; maxF = std::max(maxF, nFs[(size_t) p]); maxN = std::max(maxN, h->counts[(size_t) p]); }
+    if (sumF == 0) break;
+    // one rank holds far more than its share (the frontier of a BFS-ordered BLOCK layout sits on the last ranks):
+    // re-balance before growing further, then look at the frontier again (statuses travel with the states)
+    if (maxN > (h->n_glob / N + 1) * 5 / 4 + (1L << 16)) {
+      if (sh_rebalance(h)) return -1;
+      continue;
+    }
+    if (nF > fcap) {
+      pfree(d_frontier); pfree(d_fstatus);
+      d_frontier = nullptr; d_fstatus = nullptr;
+      fcap = nF + nF / 2;
+      FSP_CUDA_CHECK(pmalloc(&d_frontier, sizeof(int) * fcap));
+      FSP_CUDA_CHECK(pmalloc(&d_fstatus, fcap));
+    }
+    if (nF > 0) {
+      frontier_fill_kernel<<<blocks_for(n), 256>>>(h->d_flag, h->d_pos, n, d_frontier);
+      FSP_LAUNCH_CHECK();
+      FSP_CUDA_CHECK(cudaMemset(d_fstatus, 0, nF));
+    }
+    const Bounds bd = bounds_of(h);
+    for (int j = 0; j < h->R; ++j) {
+      const SmallVec nu = nu_of(h, j);
+      for (long i0 = 0; i0 < maxF; i0 += kBatch) {
+        const long m = std::max(0L, std::min(kBatch, nF - i0));
+        // room for this batch: exact counts (one small gather) + the batch sizes, which every rank can derive
+        if (sh_refresh_counts(h)) return -1;
+        long maxM = 0, sumM = 0, fullest = 0;
+        for (int p = 0; p < N; ++p) {
+          const long mp = std::max(0L, std::min(kBatch, nFs[(size_t) p] - i0));
+          maxM = std::max(maxM, mp); sumM += mp;
+          fullest = std::max(fullest, h->counts[(size_t) p] + mp);
+        }
+        if (sh_reserve(h, fullest, h->n_glob + sumM, maxM)) return -1;
+        if (m > 0) {
+          children_kernel<<<blocks_for(m), 256>>>(h->d_states, d_frontier, i0, m, h->S, h->K, nu, bd, use_default, h->d_cand,
+                                                  h->d_valid, d_fstatus);
+          FSP_LAUNCH_CHECK();
+          if (!use_default) {
+            if (host_validity(h, m, cand_host, fval, valid_host)) return -1;
+            apply_valid_kernel<<<blocks_for(m), 256>>>(h->d_valid, i0, m, d_fstatus);
+            FSP_LAUNCH_CHECK();
+          }
+        }
+        if (sh_insert_batch(h, m, false)) return -1;
+      }
+    }
+    if (nF > 0) {
+      set_frontier_status_kernel<<<blocks_for(nF), 256>>>(h->d_status, d_frontier, d_fstatus, nF);
+      FSP_LAUNCH_CHECK();
+    }
+  }
+  return sh_rebalance(h);  // h->counts is current: nothing was added since the last gather
+}
+
 }  // namespace
 
 extern "C" {
@@ -456,10 +916,60 @@ int fspset_create(fspset_t *out, int S, int R, const int *SM) {
 
 int fspset_destroy(fspset_t h) {
   if (!h) return 0;
-  pfree(h->d_states); pfree(h->d_status); pfree(h->d_table); pfree(h->d_cand); pfree(h->d_valid);
-  pfree(h->d_flag); pfree(h->d_pos); pfree(h->d_slot); pfree(h->d_cub);
+  if (h->sharded) {
+    // the windows go back to the communicator's pool: destructors are not collective
+    cudaDeviceSynchronize();
+    fspcomm_window_retire(h->comm, h->win_data, h->data_bytes);
+    fspcomm_window_retire(h->comm, h->win_cand, h->cand_bytes);
+    fspcomm_window_retire(h->comm, h->win_table, h->table_bytes);
+    pfree(h->d_err);
+  } else {
+    pfree(h->d_states); pfree(h->d_status); pfree(h->d_table); pfree(h->d_cand);
+  }
+  pfree(h->d_valid); pfree(h->d_flag); pfree(h->d_pos); pfree(h->d_slot); pfree(h->d_cub); pfree(h->d_rem);
   delete h;
   return 0;
+}
+
+int fspset_set_sharded(fspset_t h, fspcomm_s *comm) {
+  if (h->n > 0 || h->d_table || h->sharded) { set_error("fspset_set_sharded: the set is not empty"); return -1; }
+  int rank = 0, size = 1;
+  fspcomm_rank(comm, &rank, &size);
+  if (size == 1) return 0;
+  if (!fspcomm_p2p_enabled(comm)) { set_error("fspset_set_sharded: the communicator has no peer memory"); return -1; }
+  if (size > kMaxRanksS) { set_error("fspset_set_sharded: more than %d ranks", kMaxRanksS); return -1; }
+  FSP_CUDA_CHECK(pmalloc(&h->d_err, sizeof(int)));
+  FSP_CUDA_CHECK(cudaMemset(h->d_err, 0, sizeof(int)));
+  h->sharded = true; h->comm = comm; h->rank = rank; h->size = size;
+  h->counts.assign((size_t) size, 0);
+  h->starts.assign((size_t) size + 1, 0);
+  return 0;
+}
+int fspset_is_sharded(fspset_t h) { return h && h->sharded ? 1 : 0; }
+int fspset_layout(fspset_t h, long *starts_host, long *n_local) {
+  if (h->sharded) for (int p = 0; p <= h->size; ++p) starts_host[p] = h->starts[(size_t) p];
+  else { starts_host[0] = 0; starts_host[1] = h->n; }
+  if (n_local) *n_local = h->n;
+  return 0;
+}
+
+int fspset_remember_local(fspset_t h) {
+  pfree(h->d_rem);
+  h->d_rem = nullptr;
+  h->n_rem = h->n;
+  if (h->n > 0) {
+    FSP_CUDA_CHECK(pmalloc(&h->d_rem, sizeof(int) * (size_t) h->n * h->S));
+    FSP_CUDA_CHECK(cudaMemcpy(h->d_rem, h->d_states, sizeof(int) * (size_t) h->n * h->S, cudaMemcpyDeviceToDevice));
+  }
+  return 0;
+}
+int fspset_remembered_indices(fspset_t h, int *idx_host, long n_expected) {
+  if (n_expected != h->n_rem) { set_error("fspset_remembered_indices: %ld states were remembered, not %ld", h->n_rem, n_expected); return -1; }
+  int rc = 0;
+  if (h->n_rem > 0) rc = fspset_state2index(h, h->n_rem, h->d_rem, 1, idx_host, 0);
+  pfree(h->d_rem);
+  h->d_rem = nullptr; h->n_rem = 0;
+  return rc;
 }
 
 int fspset_set_shape(fspset_t h, int K, fspset_constr_fn lhs, const int *bounds, void *args) {
@@ -482,6 +992,12 @@ int fspset_set_bounds(fspset_t h, int K, const int *bounds) {
 
 int fspset_add_states(fspset_t h, int num_species, long m, const int *X, int on_device) {
   if (num_species != h->S) return -1;  // StateSetBase.cpp:190-192
+  if (h->sharded)  // collective: every rank passes its own list (StateSetBase.cpp:176-178); duplicates across ranks are shed
+    return sh_add(h, m, [&](long b, long mb) {
+      FSP_CUDA_CHECK(cudaMemcpy(h->d_cand, X + (size_t) b * h->S, sizeof(int) * mb * h->S,
+                                on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+      return 0;
+    });
   for (long b = 0; b < m; b += kBatch) {
     long mb = std::min(kBatch, m - b);
     if (ensure_cand(h, mb)) return -1;
@@ -499,6 +1015,15 @@ int fspset_add_box_lattice(fspset_t h, const int *upper) {
     dims.v[s] = s < h->S ? upper[s] + 1 : 1;
     total *= dims.v[s];
     if (total >= 0x7FFFFFF0L) { set_error("fspset_add_box_lattice: lattice exceeds 2^31 states"); return -1; }
+  }
+  if (h->sharded) {  // every rank contributes its BLOCK of the lattice ordinals
+    const long lo = total / h->size * h->rank + std::min<long>(h->rank, total % h->size);
+    const long cnt = total / h->size + (h->rank < total % h->size ? 1 : 0);
+    return sh_add(h, cnt, [&](long b, long mb) {
+      lattice_kernel<<<blocks_for(mb), 256>>>(lo + b, mb, h->S, dims, h->d_cand);
+      FSP_LAUNCH_CHECK();
+      return 0;
+    });
   }
   if (ensure_states(h, h->n + total)) return -1;
   for (long b = 0; b < total; b += kBatch) {
@@ -565,17 +1090,17 @@ static int expand_impl(fspset_t h, int *&d_frontier, signed char *&d_fstatus) {
 }
 
 int fspset_expand(fspset_t h) {
-  if (h->n == 0) return 0;
+  if ((h->sharded ? h->n_glob : h->n) == 0) return 0;
   if ((int) h->bounds.size() != h->K || h->K == 0) { set_error("fspset_expand: shape not set"); return -1; }
   int         *d_frontier = nullptr;
   signed char *d_fstatus = nullptr;
-  const int    rc = expand_impl(h, d_frontier, d_fstatus);
+  const int    rc = h->sharded ? sh_expand(h, d_frontier, d_fstatus) : expand_impl(h, d_frontier, d_fstatus);
   pfree(d_frontier); pfree(d_fstatus);
   if (rc == 0) { h->expanded = true; h->expanded_bounds = h->bounds; }
   return rc;
 }
 
-int fspset_num_states(fspset_t h, int *n) { *n = (int) h->n; return 0; }
+int fspset_num_states(fspset_t h, int *n) { *n = (int) (h->sharded ? h->n_glob : h->n); return 0; }
 
 int fspset_state2index(fspset_t h, long m, const int *X, int x_on_device, int *idx, int idx_on_device) {
   if (m <= 0) return 0;
@@ -590,7 +1115,10 @@ int fspset_state2index(fspset_t h, long m, const int *X, int x_on_device, int *i
     FSP_CUDA_CHECK(pmalloc(&tI, sizeof(int) * m));
     dI = tI;
   }
-  if (h->n == 0 || !h->d_table) {
+  if (h->sharded && h->n_glob > 0) {
+    sh_lookup_kernel<<<blocks_for(m), 256>>>(make_view(h), dX, m, dI);
+    FSP_LAUNCH_CHECK();
+  } else if (h->n == 0 || !h->d_table) {
     FSP_CUDA_CHECK(cudaMemset(dI, 0xFF, sizeof(int) * m));
   } else {
     lookup_kernel<<<blocks_for(m), 256>>>(h->d_table, h->tsize - 1, h->d_states, dX, m, h->S, dI);
@@ -605,6 +1133,12 @@ int fspset_lookup_shifted(fspset_t h, const int *nu_host, int sign, long first, 
   if (count <= 0) return 0;
   SmallVec nu;
   for (int s = 0; s < kMaxS; ++s) nu.v[s] = s < h->S ? nu_host[s] : 0;
+  if (h->sharded) {
+    if (first < h->base || first + count > h->base + h->n) { set_error("fspset_lookup_shifted: rows outside the local block"); return -1; }
+    sh_lookup_shifted_kernel<<<blocks_for(count), 256>>>(make_view(h), first - h->base, count, nu, sign, idx_dev);
+    FSP_LAUNCH_CHECK();
+    return 0;
+  }
   lookup_shifted_kernel<<<blocks_for(count), 256>>>(h->d_table, h->tsize - 1, h->d_states, first, count, h->S, nu,
                                                     sign, idx_dev);
   FSP_LAUNCH_CHECK();
@@ -613,6 +1147,7 @@ int fspset_lookup_shifted(fspset_t h, const int *nu_host, int sign, long first, 
 
 int fspset_check_constraints_shifted(fspset_t h, const int *nu_host, long first, long count, int *satisfied_dev) {
   if (count <= 0) return 0;
+  first -= h->base;  // sharded: global -> local row
   SmallVec nu;
   for (int s = 0; s < kMaxS; ++s) nu.v[s] = s < h->S ? nu_host[s] : 0;
   if (!h->lhs) {
@@ -642,14 +1177,20 @@ int fspset_check_constraints_shifted(fspset_t h, const int *nu_host, long first,
   return 0;
 }
 
-int fspset_states_dev(fspset_t h, const int **states_dev) { *states_dev = h->d_states; return 0; }
+// indexed by GLOBAL state index (sharded: only the local block [base, base + n) is backed by memory)
+int fspset_states_dev(fspset_t h, const int **states_dev) {
+  *states_dev = h->d_states ? h->d_states - (ptrdiff_t) h->base * h->S : nullptr;
+  return 0;
+}
 
 int fspset_copy_states(fspset_t h, long first, long count, int *out) {
+  first -= h->base;
   if (count > 0)
     FSP_CUDA_CHECK(cudaMemcpy(out, h->d_states + (size_t) first * h->S, sizeof(int) * count * h->S, cudaMemcpyDeviceToHost));
   return 0;
 }
 int fspset_copy_status(fspset_t h, long first, long count, signed char *out) {
+  first -= h->base;
   if (count > 0) FSP_CUDA_CHECK(cudaMemcpy(out, h->d_status + first, count, cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -657,6 +1198,7 @@ int fspset_copy_status(fspset_t h, long first, long count, signed char *out) {
 int fspset_eval_separable(fspset_t h, double rate, const int *order_host, const double *tables_dev, const int *tab_off_host,
                           const int *tab_len_host, const int *nu_host, int sign, long first, long count, double *out_dev) {
   if (count <= 0) return 0;
+  first -= h->base;
   SmallVec nu, ord, off, len;
   for (int s = 0; s < kMaxS; ++s) {
     nu.v[s] = s < h->S ? nu_host[s] : 0;
@@ -686,6 +1228,7 @@ int fspset_sink_lists(fspset_t h, const int *nu_host, long first, long count, in
                       long *counts_host) {
   for (int k = 0; k < h->K; ++k) counts_host[k] = 0;
   if (count <= 0) return 0;
+  first -= h->base;
   SmallVec nu;
   for (int s = 0; s < kMaxS; ++s) nu.v[s] = s < h->S ? nu_host[s] : 0;
   bool use_status = h->expanded && (int) h->expanded_bounds.size() == h->K;
@@ -763,6 +1306,7 @@ int fspset_sink_lists(fspset_t h, const int *nu_host, long first, long count, in
 int fspset_num_boundary_states(fspset_t h, long first, long count, long *n) {
   *n = count;
   if (count <= 0 || !h->expanded) return 0;
+  first -= h->base;
   if (ensure_flags(h, count)) return -1;
   status_nonzero_flag_kernel<<<blocks_for(count), 256>>>(h->d_status + first, count, h->d_flag);
   FSP_LAUNCH_CHECK();

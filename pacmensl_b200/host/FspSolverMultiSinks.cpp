@@ -102,7 +102,11 @@ DiscreteDistribution FspSolverMultiSinks::Advance_(PetscReal t_final, PetscReal 
       // existing state never changes, so State2Index(states_old) is the identity on [old_start, old_start + n_old).
       const int n_old = state_set_->GetNumLocalStates();
       const int old_start = state_set_->GetLocalStart();
+      const bool sharded = state_set_->IsSharded();
       t0 = now_s();
+      // a sharded set re-numbers when it re-balances: the old block is looked up again after the expansion
+      // (State2Index(states_old), :174-176 of the reference)
+      if (sharded) { ierr = state_set_->RememberLocalStates(); PACMENSLCHKERRTHROW(ierr); }
       state_set_->SetShapeBounds(fsp_bounds_);
       ierr = state_set_->Expand();
       PACMENSLCHKERRTHROW(ierr);
@@ -122,7 +126,8 @@ DiscreteDistribution FspSolverMultiSinks::Advance_(PetscReal t_final, PetscReal 
       // Generate the expanded vector and scatter forward the current solution (:174-205)
       t0 = now_s();
       std::vector<PetscInt> new_locations_vals((size_t) n_old);
-      for (int i = 0; i < n_old; ++i) new_locations_vals[i] = old_start + i;
+      if (sharded) { ierr = state_set_->RememberedIndices(new_locations_vals); PACMENSLCHKERRTHROW(ierr); }
+      else for (int i = 0; i < n_old; ++i) new_locations_vals[i] = old_start + i;
       if (my_rank_ == comm_size_ - 1) {
         Int i_end_new = state_set_->GetNumGlobalStates() + (Int) sinks_.n_elem;
         for (auto i{0}; i < (int) sinks_.n_elem; ++i) new_locations_vals.push_back(i_end_new - ((Int) sinks_.n_elem) + i);
@@ -185,6 +190,7 @@ PacmenslErrorCode FspSolverMultiSinks::SetUp() {
   if (!state_set_) {
     double t0 = now_s();
     state_set_ = std::make_shared<StateSetConstrained>(comm_);
+    if (sharded_set_) state_set_->SetSharded(true);
     state_set_->SetStoichiometryMatrix(model_.stoichiometry_matrix_);
     if (has_custom_constraints_) state_set_->SetShape(fsp_constr_funs_, fsp_bounds_, fsp_constr_args_);
     else state_set_->SetShapeBounds(fsp_bounds_);

@@ -67,6 +67,8 @@ class PACMENSL_API FspSolverMultiSinks {
   /// (DESIGN.md section 7).  FSP_WARM_RESTART=carry keeps the plain carry-over of the old history (measured +30 .. +50 %:
   /// the new states enter at 0 with weights 1/atol and no derivative history).  KrylovFsp always restarts as the
   /// reference does.
+  /// Extension: build the state set sharded over the ranks (StateSetBase::SetSharded); before SetUp()
+  PacmenslErrorCode SetShardedStateSet(bool on) { sharded_set_ = on; return 0; }
   PacmenslErrorCode SetWarmRestart(bool on) { warm_restart_ = on; if (ode_solver_) ode_solver_->SetWarmRestart(on); return 0; }
 
   std::shared_ptr<const StateSetBase> GetStateSet();
@@ -138,6 +140,7 @@ class PACMENSL_API FspSolverMultiSinks {
   std::string ts_type_ = "";
   bool        custom_krylov_ = false;
   bool        warm_restart_ = false;
+  bool        sharded_set_ = false;
   int         q_iop_ = -1;
   int         m_min_ = 25, m_max_ = 60;
 

@@ -216,13 +216,17 @@ SensDiscreteDistribution SensFspSolverMultiSinks::Advance_(PetscReal t_final, Pe
           fsp_bounds_(i) = (int) std::round(double(fsp_bounds_(i)) * (fsp_expasion_factors_(i) + 1.0e0) + 0.5e0);
       const int n_old = state_set_->GetNumLocalStates();
       const int old_start = state_set_->GetLocalStart();
+      const bool sharded = state_set_->IsSharded();
+      if (sharded) { ierr = state_set_->RememberLocalStates(); PACMENSLCHKERRTHROW(ierr); }
       state_set_->SetShapeBounds(fsp_bounds_);
       ierr = state_set_->Expand(); PACMENSLCHKERRTHROW(ierr);
       A_->Destroy();
       ierr = A_->GenerateValues(*state_set_, model_); PACMENSLCHKERRTHROW(ierr);
-      // existing states keep their global index (replicated directory): State2Index(states_old) is the identity shift
+      // existing states keep their global index (replicated directory): State2Index(states_old) is the identity shift;
+      // a sharded set re-numbers when it re-balances, so the old block is looked up again (:174-205 of the reference)
       std::vector<PetscInt> new_locations_vals((size_t) n_old);
-      for (int i = 0; i < n_old; ++i) new_locations_vals[i] = old_start + i;
+      if (sharded) { ierr = state_set_->RememberedIndices(new_locations_vals); PACMENSLCHKERRTHROW(ierr); }
+      else for (int i = 0; i < n_old; ++i) new_locations_vals[i] = old_start + i;
       if (my_rank_ == comm_size_ - 1) {
         Int i_end_new = state_set_->GetNumGlobalStates() + (Int) sinks_.n_elem;
         for (int i{0}; i < (int) sinks_.n_elem; ++i) new_locations_vals.push_back(i_end_new - ((Int) sinks_.n_elem) + i);

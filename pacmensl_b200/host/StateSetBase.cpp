@@ -1,6 +1,7 @@
 #include "StateSetBase.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <iostream>
 
 namespace pacmensl {
@@ -64,6 +65,32 @@ PacmenslErrorCode StateSetBase::ensure_device_set() {
     num_reactions_ = 0;
   }
   FSPCHKERRQ(fspset_create(&dset_, num_species_, num_reactions_, stoichiometry_matrix_.memptr()));
+  static const bool env_sharded = [] { const char *e = std::getenv("FSP_SHARDED_SET"); return e && e[0] == '1'; }();
+  if ((want_sharded_ || env_sharded) && comm_size_ > 1 && comm_ && fspcomm_p2p_enabled(comm_->nccl))
+    FSPCHKERRQ(fspset_set_sharded(dset_, comm_->nccl));
+  return 0;
+}
+
+PacmenslErrorCode StateSetBase::SetSharded(bool on) {
+  if (dset_) {
+    if (my_rank_ == 0) std::cout << "SetSharded() must be called before states are added; ignored.\n";
+    return 0;
+  }
+  want_sharded_ = on;
+  return 0;
+}
+
+PacmenslErrorCode StateSetBase::RememberLocalStates() {
+  if (!dset_) { n_remembered_ = 0; return 0; }
+  FSPCHKERRQ(fspset_remember_local(dset_));
+  n_remembered_ = num_local_states_;
+  return 0;
+}
+PacmenslErrorCode StateSetBase::RememberedIndices(std::vector<int> &indices) {
+  indices.assign((size_t) n_remembered_, -1);
+  if (!dset_) return 0;
+  FSPCHKERRQ(fspset_remembered_indices(dset_, indices.data(), n_remembered_));
+  n_remembered_ = 0;
   return 0;
 }
 
@@ -75,6 +102,13 @@ PacmenslErrorCode StateSetBase::update_layout() {
   const int base = n / comm_size_, rem = n % comm_size_;
   ind_starts_.assign(comm_size_ + 1, 0);
   for (int r = 0; r < comm_size_; ++r) ind_starts_[r + 1] = ind_starts_[r] + base + (r < rem ? 1 : 0);
+  if (fspset_is_sharded(dset_)) {  // the device set made the same split when it re-balanced; take its word
+    std::vector<long> st((size_t) comm_size_ + 1, 0);
+    long              n_loc = 0;
+    FSPCHKERRQ(fspset_layout(dset_, st.data(), &n_loc));
+    for (int r = 0; r <= comm_size_; ++r) ind_starts_[r] = (int) st[(size_t) r];
+    if (n_loc != ind_starts_[my_rank_ + 1] - ind_starts_[my_rank_]) PACMENSLCHKERRQ(-1);
+  }
   local_start_ = ind_starts_[my_rank_];
   num_local_states_ = ind_starts_[my_rank_ + 1] - local_start_;
   host_states_valid_ = false;
@@ -90,6 +124,12 @@ PacmenslErrorCode StateSetBase::AddStates(const arma::Mat<int> &X) {
   PACMENSLCHKERRQ(ierr);
   if (comm_size_ == 1) {
     if (X.n_cols > 0) FSPCHKERRQ(fspset_add_states(dset_, (int) X.n_rows, (long) X.n_cols, X.memptr(), 0));
+    return update_layout();
+  }
+  if (fspset_is_sharded(dset_)) {
+    // collective inside: every rank inserts its own list into the striped directory, duplicates across ranks are shed
+    // there, and the set is re-balanced to the BLOCK layout
+    FSPCHKERRQ(fspset_add_states(dset_, (int) X.n_rows, (long) X.n_cols, X.memptr(), 0));
     return update_layout();
   }
   // Multi-GPU: each rank may pass its own (possibly overlapping) list (:176-178 of the reference); the replicated

@@ -55,6 +55,17 @@ class PACMENSL_API StateSetBase {
   int GetLocalStart() const { return local_start_; }
   /// ownership start of every rank (+ N at the end): ind_starts_ of the reference
   const std::vector<int> &GetLayout() const { return ind_starts_; }
+  /// Extension: distribute the construction like the reference does (src/StateSet/StateSetBase.cpp:134-154,188-258):
+  /// every rank keeps only its block of states, explores the frontier states it owns, and the directory is striped
+  /// over the GPUs' HBM (include/fsp_b200.h: fspset_set_sharded).  Must be called before the first state is added;
+  /// needs > 1 rank with peer memory, otherwise the replicated directory stays.  FSP_SHARDED_SET=1 turns it on for every
+  /// multi-GPU set.  Global indices then change when the set grows (as in the reference): see RememberLocalStates.
+  PacmenslErrorCode SetSharded(bool on = true);
+  bool IsSharded() const { return dset_ && fspset_is_sharded(dset_) != 0; }
+  /// State2Index(states_old) of FspSolverMultiSinks.cpp:174-205 without the host round trip: remember the local block
+  /// before Expand(), ask for the new global indices of those states afterwards.
+  PacmenslErrorCode RememberLocalStates();
+  PacmenslErrorCode RememberedIndices(std::vector<int> &indices);
 
  protected:
   MPI_Comm comm_ = MPI_COMM_NULL;
@@ -69,6 +80,8 @@ class PACMENSL_API StateSetBase {
   double           lb_threshold_ = 0.2;
 
   fspset_t               dset_ = nullptr;
+  bool                   want_sharded_ = false;
+  long                   n_remembered_ = 0;
   mutable arma::Mat<int> local_states_;
   mutable bool           host_states_valid_ = false;
 

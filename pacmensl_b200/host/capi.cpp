@@ -65,6 +65,19 @@ int pfsp_set_create(void **set) {
   PFSP_CATCH
 }
 int pfsp_set_destroy(void *set) { delete static_cast<StateSetConstrained *>(set); return 0; }
+int pfsp_set_set_sharded(void *set, int on) { return static_cast<StateSetConstrained *>(set)->SetSharded(on != 0); }
+int pfsp_set_is_sharded(void *set) { return static_cast<StateSetConstrained *>(set)->IsSharded() ? 1 : 0; }
+int pfsp_set_remember_local(void *set) { return static_cast<StateSetConstrained *>(set)->RememberLocalStates(); }
+int pfsp_set_remembered_indices(void *set, int n, int *idx) {
+  PFSP_TRY
+  std::vector<int> v;
+  int ierr = static_cast<StateSetConstrained *>(set)->RememberedIndices(v);
+  if (ierr) return ierr;
+  if ((int) v.size() != n) return -1;
+  std::copy(v.begin(), v.end(), idx);
+  return 0;
+  PFSP_CATCH
+}
 int pfsp_set_stoichiometry(void *set, int S, int R, const int *SM) {
   return static_cast<StateSetConstrained *>(set)->SetStoichiometryMatrix(colmajor(SM, S, R));
 }
@@ -258,6 +271,7 @@ int pfsp_solver_set_krylov(void *solver, int q_iop, int m_min, int m_max) {
   return s->SetKrylovDimRange(m_min, m_max);
 }
 int pfsp_solver_set_warm_restart(void *solver, int on) { return static_cast<SolverBox *>(solver)->solver->SetWarmRestart(on != 0); }
+int pfsp_solver_set_sharded_state_set(void *solver, int on) { return static_cast<SolverBox *>(solver)->solver->SetShardedStateSet(on != 0); }
 int pfsp_solver_num_warm_restarts(void *solver, int *n) { *n = static_cast<SolverBox *>(solver)->solver->GetNumWarmRestarts(); return 0; }
 int pfsp_solver_setup(void *solver) {
   PFSP_TRY

@@ -16,9 +16,9 @@ ORDERS = np.array([[0, 1, 0, 0, 0, 0], [0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 0, 1]], 
 
 
 class Lattice:
-    def __init__(self, upper, tv=False, expand=True):
+    def __init__(self, upper, tv=False, expand=True, sharded=False):
         self.upper = [int(u) for u in upper]
-        self.set = api.StateSet(SM)
+        self.set = api.StateSet(SM, sharded=sharded)
         assert self.set.set_shape(self.upper) == 0
         self.set.add_box_lattice(self.upper)
         if expand:  # closure check + status bookkeeping, as the reference's AddStates -> Expand sequence

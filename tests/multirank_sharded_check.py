@@ -1,0 +1,157 @@
+"""Sharded state-space construction on N GPUs (one rank per GPU, run under torchrun):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/multirank_sharded_check.py
+
+The set is built with StateSetBase::SetSharded (every rank keeps and expands only its block, the directory is striped over
+the GPUs' HBM and probed through peer memory) and checked against the CPU oracle:
+1. the union of the ranks' blocks is exactly the oracle's state set (no state missing, none twice), the layout is the
+   contiguous equal-count BLOCK split, State2Index of every state -- asked on every rank -- is its position in the
+   rank-concatenated listing, absent / negative states give -1;
+2. the partitioned Action on the sharded sets == oracle by state key (tests/parity_leg.py), including a set large enough
+   (hog1p, 857 808 states) that the expansion re-balances in the middle of the BFS;
+3. repeated expansion with growing bounds (the driver's pattern) keeps 1. true, and the remembered-block lookup returns
+   the new positions of the old states;
+4. adaptive FSP solves (Krylov, BDF; default and host-callback constraints) on sharded sets agree with the same solves
+   on the replicated directory, state by state.
+Rank 0 prints "SHARDED OK" on success.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import parity_leg  # noqa: E402
+
+
+def gather_rows(local, dev, S):
+    flat = parity_leg._gather(torch.from_numpy(np.ascontiguousarray(local).reshape(-1)).to(dev), dist, dev, torch.int32)
+    return flat.reshape(-1, S)
+
+
+def check_set(api, O, dev, name, bounds_seq, rank, world):
+    """Build the fixture's set sharded, expanding through bounds_seq; compare with the oracle after every expansion."""
+    m = api.Model(fixture=name)
+    fx = m.fixture
+    st = api.StateSet(m.stoichiometry(), sharded=True)
+    assert st.set_shape(bounds_seq[0], lhs_c=fx["lhs"]) == 0
+    assert st.add_states(fx["x0"].reshape(1, -1)) == 0
+    ok = st.is_sharded()
+    so = O.StateSet(fixture=name, bounds=list(bounds_seq[0])) if rank == 0 else None
+    for k, b in enumerate(bounds_seq):
+        if k > 0:
+            assert st.set_bounds(b) == 0
+        assert st.expand() == 0
+        n_local, N, start = st.sizes()
+        mine = st.states()
+        allst = gather_rows(mine, dev, st.S)
+        # layout: contiguous equal-count split, ranks below N % world own one more
+        base, rem = divmod(N, world)
+        ok &= n_local == base + (1 if rank < rem else 0) and start == rank * base + min(rank, rem)
+        ok &= len(allst) == N
+        # the directory, asked on EVERY rank for EVERY state: position in the rank-concatenated listing
+        idx = st.state2index(allst)
+        ok &= bool((idx == np.arange(N)).all())
+        probe = np.array([[-1] + [0] * (st.S - 1), [10 ** 6] * st.S], dtype=np.int32)
+        ok &= bool((st.state2index(probe) == -1).all())
+        if rank == 0:
+            if k > 0:
+                so.set_bounds(list(b))
+            assert so.expand() == 0
+            perm = so.state2index(allst.astype(np.int32))
+            same = so.n == N and (perm >= 0).all() and len(np.unique(perm)) == N
+            print("sharded set %-16s bounds %-22s N=%-8d == oracle: %s" % (name, list(b), N, bool(same)))
+            ok &= bool(same)
+    return ok
+
+
+def solve_pair(api, dev, name, ode, t_final, tol, rank, bounds=None):
+    """The same adaptive solve on the replicated and on the sharded set; returns the L1 distance by state key."""
+    res = []
+    for sharded in (False, True):
+        s, m = api.fixture_solver(name, ode)
+        if bounds is not None:
+            s.set_initial_bounds(bounds)
+        if sharded:
+            s.set_sharded_state_set(True)
+        states, p = s.solve(t_final, tol)
+        S = states.shape[1]
+        allst = gather_rows(states.astype(np.int32), dev, S)
+        allp = parity_leg._gather(torch.from_numpy(np.ascontiguousarray(p)).to(dev), dist, dev, torch.float64)
+        res.append((allst, allp, s.stats()))
+        s.clear()
+    (sa, pa, sta), (sb, pb, stb) = res
+    da = {tuple(x): v for x, v in zip(sa.tolist(), pa)}
+    db = {tuple(x): v for x, v in zip(sb.tolist(), pb)}
+    keys = set(da) | set(db)
+    l1 = sum(abs(da.get(k, 0.0) - db.get(k, 0.0)) for k in keys)
+    if rank == 0:
+        print("solve %-14s %-6s replicated %d states / %d expansions, sharded %d / %d: ||dp||_1 = %.3e, sum p = %.12f" %
+              (name, "krylov" if ode == api.KRYLOV else "cvode", sta["n_states"], sta["expansions"], stb["n_states"],
+               stb["expansions"], l1, float(pb.sum())))
+    return l1, sta, stb, len(da) == len(sa) and len(db) == len(sb)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from pacmensl_b200 import api
+    api.init(local_rank, dist)
+    dev = torch.device("cuda", local_rank)
+    from oracle import oracle as O
+    ok = api.p2p_enabled()
+    if rank == 0:
+        print("peer-memory fast path: %s" % ("on" if ok else "off -- the sharded set needs it"))
+
+    # ---- 1 + 3: set contents, layout, directory; repeated expansion ----
+    ok &= check_set(api, O, dev, "toggle", [[10, 10], [14, 12], [40, 31]], rank, world)
+    ok &= check_set(api, O, dev, "toggle_custom", [[10, 10, 30], [13, 12, 40]], rank, world)  # host lhs callbacks
+    ok &= check_set(api, O, dev, "transcr_reg_6d", [[10, 6, 1, 2, 1, 1], [14, 9, 1, 3, 2, 2]], rank, world)
+    ok &= check_set(api, O, dev, "hog1p", [[3, 10, 10, 5, 5], [3, 17, 36, 13, 22]], rank, world)  # re-balances mid-BFS
+
+    # remembered block -> new positions (what the FSP driver uses to move the solution onto the expanded set)
+    m = api.Model(fixture="toggle")
+    st = api.StateSet(m.stoichiometry(), sharded=True)
+    assert st.set_shape([8, 8]) == 0 and st.add_states(m.fixture["x0"].reshape(1, -1)) == 0 and st.expand() == 0
+    old = st.states().copy()
+    assert st.remember_local() == 0
+    assert st.set_bounds([20, 17]) == 0 and st.expand() == 0
+    idx = st.remembered_indices()
+    ok &= bool((idx == st.state2index(old)).all()) and bool((idx >= 0).all())
+    if rank == 0:
+        print("remembered block of %d states -> new global indices [%d .. %d], consistent with State2Index: %s" %
+              (len(old), idx.min() if len(idx) else -1, idx.max() if len(idx) else -1, bool((idx == st.state2index(old)).all())))
+    del st
+
+    # ---- 2: Action parity on sharded sets ----
+    cases = list(parity_leg.DEFAULT_CASES) + [("hog1p", [3, 17, 36, 13, 22], (25.0,))]
+    par = parity_leg.run(api, dist, dev, cases=cases, verbose=True, sharded=True)
+    ok &= par["ok"] if rank == 0 else True
+
+    # ---- 4: adaptive solves, sharded vs replicated ----
+    for name, ode, tf, tol, bounds, bound in (("pure_birth", api.KRYLOV, 10.0, 1e-6, None, 1e-8),
+                                              ("pure_birth", api.CVODE, 10.0, 1e-6, None, 1e-7),
+                                              ("toggle_custom", api.KRYLOV, 100.0, 1e-6, [10, 10, 30], 1e-8),
+                                              ("repressilator", api.KRYLOV, 1.0, 1e-4, None, 1e-8)):
+        l1, sta, stb, uniq = solve_pair(api, dev, name, ode, tf, tol, rank, bounds)
+        ok &= l1 <= bound and uniq and sta["n_states"] == stb["n_states"] and sta["expansions"] == stb["expansions"]
+
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("SHARDED OK" if flag.item() == 1.0 else "SHARDED FAILED")
+    dist.barrier()
+    api.finalize()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,17 +39,17 @@ def _gather(local, dist, dev, dtype):
     return np.concatenate([o[: sizes[r]].cpu().numpy() for r, o in enumerate(outs)])
 
 
-def run_case(api, dist, dev, name, bounds, times, reps=3, seed=99):
+def run_case(api, dist, dev, name, bounds, times, reps=3, seed=99, sharded=False):
     """Returns (states_rel_err, sinks_rel_err, n_states) on rank 0 (zeros elsewhere)."""
     import torch
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
     if name.startswith("birth_death_3d"):
         from pacmensl_b200.lattice import Lattice
-        lat = Lattice(bounds, tv=name.endswith("_tv"))
+        lat = Lattice(bounds, tv=name.endswith("_tv"), sharded=sharded)
         st, mat = lat.set, lat.mat
     else:
-        st, mat = api.fixture_set_and_matrix(name, bounds=np.asarray(bounds, dtype=np.int32))
+        st, mat = api.fixture_set_and_matrix(name, bounds=np.asarray(bounds, dtype=np.int32), sharded=sharded)
     n_local, N, start = st.sizes()
     n_rows = mat.n_rows
     K = 0
@@ -104,16 +104,16 @@ def run_case(api, dist, dev, name, bounds, times, reps=3, seed=99):
     return e_states, e_sinks, N
 
 
-def run(api, dist, dev, cases=None, verbose=False):
+def run(api, dist, dev, cases=None, verbose=False, sharded=False):
     """Runs all cases; returns {"max_rel_err", "sinks_rel_err", "cases": {...}, "ok"} (meaningful on rank 0)."""
     out = {"max_rel_err": 0.0, "sinks_rel_err": 0.0, "tol": TOL, "cases": {}}
     rank = dist.get_rank() if dist is not None else 0
     for name, bounds, times in (cases or DEFAULT_CASES):
-        es, ek, n = run_case(api, dist, dev, name, bounds, times)
+        es, ek, n = run_case(api, dist, dev, name, bounds, times, sharded=sharded)
         out["cases"][name] = {"states": n, "rel_err": es, "sinks_rel_err": ek}
         out["max_rel_err"] = max(out["max_rel_err"], es)
         out["sinks_rel_err"] = max(out["sinks_rel_err"], ek)
         if verbose and rank == 0:
-            print("action parity %-18s N=%-7d rel_err states %.2e sinks %.2e" % (name, n, es, ek))
+            print("action parity %-18s N=%-7d rel_err states %.2e sinks %.2e%s" % (name, n, es, ek, "  (sharded set)" if sharded else ""))
     out["ok"] = bool(out["max_rel_err"] <= TOL and out["sinks_rel_err"] <= TOL)
     return out
