@@ -482,8 +482,13 @@ struct fspset_s {
   void              *win_data[FSP_P2P_MAX_RANKS] = {nullptr};   // [states cap*S int | status cap bytes], same cap on all ranks
   void              *win_cand[FSP_P2P_MAX_RANKS] = {nullptr};   // candidate keys of the batch in flight
   void              *win_table[FSP_P2P_MAX_RANKS] = {nullptr};  // tsize 64-bit slots per rank
+  void              *win_spare[FSP_P2P_MAX_RANKS] = {nullptr};  // second data window of the same capacity: re-balance target
+  bool               have_spare = false;
   size_t             data_bytes = 0, cand_bytes = 0, table_bytes = 0;
   int               *d_err = nullptr;  // probe bound exceeded (a full shard)
+  // FSP_SET_TRACE=1: what the collective construction spent its time on
+  struct Trace { long waves = 0, batches = 0, data_resizes = 0, table_resizes = 0, cand_resizes = 0, rebalances = 0;
+                 double t_resize = 0, t_rebalance = 0, t_batches = 0, t_total = 0; } tr;
 };
 
 namespace {
@@ -619,6 +624,14 @@ int host_validity(fspset_s *h, long m, std::vector<int> &cand_host, std::vector<
 
 
 // ---- sharded mode, host side (every function below is COLLECTIVE: same call sequence and arguments on all ranks) ----
+bool sh_trace() { static const bool on = [] { const char *e = getenv("FSP_SET_TRACE"); return e && e[0] == '1'; }(); return on; }
+double sh_now() {
+  if (!sh_trace()) return 0.0;
+  cudaDeviceSynchronize();
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+}
 ShardView make_view(const fspset_s *h) {
   ShardView v;
   memset(&v, 0, sizeof(v));
@@ -665,6 +678,10 @@ int sh_data_resize(fspset_s *h, long new_cap) {
   }
   FSP_CUDA_CHECK(cudaDeviceSynchronize());
   if (h->win_data[h->rank] && fspcomm_window_destroy(h->comm, h->win_data)) return -1;
+  if (h->have_spare) {  // wrong capacity now
+    if (fspcomm_window_destroy(h->comm, h->win_spare)) return -1;
+    h->have_spare = false;
+  }
   for (int p = 0; p < h->size; ++p) h->win_data[p] = nw[p];
   h->d_states = ns; h->d_status = nst; h->cap = new_cap; h->data_bytes = bytes;
   return 0;
@@ -711,20 +728,39 @@ int sh_cand_resize(fspset_s *h, long m) {
 // room for `max_loc_after` states on the fullest rank, `glob_after` states in the directory, `max_batch` candidates
 int sh_reserve(fspset_s *h, long max_loc_after, long glob_after, long max_batch) {
   if (glob_after >= 0x7FFFFFF0L) { set_error("fspset: more than 2^31 states"); return -1; }
+  // every resize re-creates a peer window (allocation, IPC handle exchange, mapping by every peer: milliseconds), so
+  // capacities start generous and double
+  const double t0 = sh_now();
   if (max_loc_after > h->cap) {
-    const long nc = std::max(max_loc_after, h->cap + h->cap / 2 + 1024);
+    const long nc = std::max(std::max(max_loc_after, 2 * h->cap), 1L << 16);
     if (sh_data_resize(h, nc)) return -1;
+    h->tr.data_resizes += 1;
   }
-  unsigned long long want = h->tsize ? h->tsize : 1024;
+  unsigned long long want = h->tsize ? h->tsize : (1ull << 16);
   const unsigned long long per_shard = (unsigned long long) ((glob_after + h->size - 1) / h->size);
   while (per_shard * 5 / 2 + 64 > want) want *= 2;  // average load <= 0.4; the shards of a good hash differ by O(sqrt)
-  if (want != h->tsize && sh_table_resize(h, want)) return -1;
-  if (max_batch > h->cand_cap && sh_cand_resize(h, std::max(max_batch, 4096L))) return -1;
+  if (want != h->tsize) {
+    if (sh_table_resize(h, want)) return -1;
+    h->tr.table_resizes += 1;
+  }
+  if (max_batch > h->cand_cap) {
+    if (sh_cand_resize(h, std::max(std::max(max_batch, 2 * h->cand_cap), 1L << 18))) return -1;
+    h->tr.cand_resizes += 1;
+  }
+  h->tr.t_resize += sh_now() - t0;
   return 0;
 }
 
 // One batch: the m local candidates in h->d_cand (validity in h->d_valid unless all_valid).  m may be 0 on this rank.
+int sh_insert_batch_impl(fspset_s *h, long m, bool all_valid);
 int sh_insert_batch(fspset_s *h, long m, bool all_valid) {
+  const double t0 = sh_now();
+  const int    rc = sh_insert_batch_impl(h, m, all_valid);
+  h->tr.t_batches += sh_now() - t0;
+  h->tr.batches += 1;
+  return rc;
+}
+int sh_insert_batch_impl(fspset_s *h, long m, bool all_valid) {
   const ShardView     v = make_view(h);
   const signed char *valid = all_valid ? nullptr : h->d_valid;
   if (sh_barrier(h)) return -1;  // every rank's candidates are written, the previous batch is complete
@@ -752,7 +788,14 @@ int sh_insert_batch(fspset_s *h, long m, bool all_valid) {
 
 // Re-balance to the BLOCK layout (h->counts must be current).  The rank-concatenated order of the states is kept:
 // rank r pulls positions [T_r, T_r+1) of the concatenation out of the peers' windows; then the directory is rebuilt.
+int sh_rebalance_impl(fspset_s *h);
 int sh_rebalance(fspset_s *h) {
+  const double t0 = sh_now();
+  const int    rc = sh_rebalance_impl(h);
+  h->tr.t_rebalance += sh_now() - t0;
+  return rc;
+}
+int sh_rebalance_impl(fspset_s *h) {
   const int N = h->size;
   long      n = 0;
   std::vector<long> C((size_t) N + 1, 0), T((size_t) N + 1, 0);
@@ -763,10 +806,17 @@ int sh_rebalance(fspset_s *h) {
   h->n_glob = n;
   const bool same = C == T;
   if (!same) {
-    const long   new_cap = std::max(h->cap, base + 1 + 1024);
+    h->tr.rebalances += 1;
+    // target: the spare window (same capacity as the current one, created at the first re-balance after a growth and
+    // kept: the two swap roles, so a re-balance costs no allocation / handle exchange / mapping)
+    const long   new_cap = h->cap;  // >= the fullest rank's count >= every target count
     void        *nw[kMaxRanksS] = {nullptr};
     const size_t bytes = sh_data_bytes(h, new_cap);
-    if (fspcomm_window_create(h->comm, bytes, nw)) return -1;
+    if (h->have_spare) {
+      for (int p = 0; p < N; ++p) nw[p] = h->win_spare[p];
+    } else if (fspcomm_window_create(h->comm, bytes, nw)) {
+      return -1;
+    }
     FSP_CUDA_CHECK(cudaDeviceSynchronize());
     if (sh_barrier(h)) return -1;  // every block is final, every new window exists
     FSP_CUDA_CHECK(cudaDeviceSynchronize());
@@ -783,8 +833,10 @@ int sh_rebalance(fspset_s *h) {
       FSP_CUDA_CHECK(cudaMemcpyAsync(nst + (lo - lo_me), src_st + (lo - C[(size_t) q]), (size_t) (hi - lo), cudaMemcpyDefault, 0));
     }
     FSP_CUDA_CHECK(cudaDeviceSynchronize());
-    if (fspcomm_window_destroy(h->comm, h->win_data)) return -1;  // (synchronises the ranks first: all pulls are done)
-    for (int p = 0; p < N; ++p) h->win_data[p] = nw[p];
+    // the old window becomes the spare: nobody writes to it before the next re-balance, whose barrier comes after every
+    // rank has finished these pulls
+    for (int p = 0; p < N; ++p) { h->win_spare[p] = h->win_data[p]; h->win_data[p] = nw[p]; }
+    h->have_spare = true;
     h->d_states = ns; h->d_status = nst; h->cap = new_cap; h->data_bytes = bytes;
     h->n = hi_me - lo_me;
     for (int r = 0; r < N; ++r) h->counts[(size_t) r] = T[(size_t) r + 1] - T[(size_t) r];
@@ -823,7 +875,20 @@ int sh_add(fspset_s *h, long m, Fill fill) {
   return sh_rebalance(h);
 }
 
+int sh_expand_impl(fspset_s *h, int *&d_frontier, signed char *&d_fstatus);
 int sh_expand(fspset_s *h, int *&d_frontier, signed char *&d_fstatus) {
+  h->tr = fspset_s::Trace();
+  const double t0 = sh_now();
+  const int    rc = sh_expand_impl(h, d_frontier, d_fstatus);
+  h->tr.t_total = sh_now() - t0;
+  if (sh_trace() && h->rank == 0)
+    printf("[set] sharded Expand -> %ld states: %.1f ms | %ld waves, %ld batches %.1f ms | resizes data %ld table %ld cand %ld: %.1f ms | "
+           "%ld re-balances (incl. the final one) %.1f ms\n", h->n_glob, 1e3 * h->tr.t_total, h->tr.waves, h->tr.batches,
+           1e3 * h->tr.t_batches, h->tr.data_resizes, h->tr.table_resizes, h->tr.cand_resizes, 1e3 * h->tr.t_resize, h->tr.rebalances,
+           1e3 * h->tr.t_rebalance);
+  return rc;
+}
+int sh_expand_impl(fspset_s *h, int *&d_frontier, signed char *&d_fstatus) {
   const int use_default = h->lhs ? 0 : 1;
   const int N = h->size;
   if (h->n > 0) {
@@ -848,6 +913,7 @@ int sh_expand(fspset_s *h, int *&d_frontier, signed char *&d_fstatus) {
     long sumF = 0, maxF = 0, maxN = 0;
     for (int p = 0; p < N; ++p) { sumF += nFs[(size_t) p]; maxF = std::max(maxF, nFs[(size_t) p]); maxN = std::max(maxN, h->counts[(size_t) p]); }
     if (sumF == 0) break;
+    h->tr.waves += 1;
     // one rank holds far more than its share (the frontier of a BFS-ordered BLOCK layout sits on the last ranks):
     // re-balance before growing further, then look at the frontier again (statuses travel with the states)
     if (maxN > (h->n_glob / N + 1) * 5 / 4 + (1L << 16)) {
@@ -866,32 +932,35 @@ int sh_expand(fspset_s *h, int *&d_frontier, signed char *&d_fstatus) {
       FSP_LAUNCH_CHECK();
       FSP_CUDA_CHECK(cudaMemset(d_fstatus, 0, nF));
     }
+    // One batch = the children of a chunk of the frontier under ALL reactions (reaction-major inside the batch): the
+    // order of discovery need not match the single-rank set, and each batch costs three barriers.
     const Bounds bd = bounds_of(h);
-    for (int j = 0; j < h->R; ++j) {
-      const SmallVec nu = nu_of(h, j);
-      for (long i0 = 0; i0 < maxF; i0 += kBatch) {
-        const long m = std::max(0L, std::min(kBatch, nF - i0));
-        // room for this batch: exact counts (one small gather) + the batch sizes, which every rank can derive
-        if (sh_refresh_counts(h)) return -1;
-        long maxM = 0, sumM = 0, fullest = 0;
-        for (int p = 0; p < N; ++p) {
-          const long mp = std::max(0L, std::min(kBatch, nFs[(size_t) p] - i0));
-          maxM = std::max(maxM, mp); sumM += mp;
-          fullest = std::max(fullest, h->counts[(size_t) p] + mp);
-        }
-        if (sh_reserve(h, fullest, h->n_glob + sumM, maxM)) return -1;
-        if (m > 0) {
-          children_kernel<<<blocks_for(m), 256>>>(h->d_states, d_frontier, i0, m, h->S, h->K, nu, bd, use_default, h->d_cand,
-                                                  h->d_valid, d_fstatus);
-          FSP_LAUNCH_CHECK();
-          if (!use_default) {
-            if (host_validity(h, m, cand_host, fval, valid_host)) return -1;
-            apply_valid_kernel<<<blocks_for(m), 256>>>(h->d_valid, i0, m, d_fstatus);
-            FSP_LAUNCH_CHECK();
-          }
-        }
-        if (sh_insert_batch(h, m, false)) return -1;
+    const long   chunkF = std::max(1L, kBatch / std::max(1, h->R));
+    for (long i0 = 0; i0 < maxF; i0 += chunkF) {
+      const long mF = std::max(0L, std::min(chunkF, nF - i0));
+      const long m = mF * h->R;
+      // room for this batch: exact counts (one small gather) + the batch sizes, which every rank can derive
+      if (sh_refresh_counts(h)) return -1;
+      long maxM = 0, sumM = 0, fullest = 0;
+      for (int p = 0; p < N; ++p) {
+        const long mp = std::max(0L, std::min(chunkF, nFs[(size_t) p] - i0)) * h->R;
+        maxM = std::max(maxM, mp); sumM += mp;
+        fullest = std::max(fullest, h->counts[(size_t) p] + mp);
       }
+      if (sh_reserve(h, fullest, h->n_glob + sumM, maxM)) return -1;
+      for (int j = 0; j < h->R && mF > 0; ++j) {
+        children_kernel<<<blocks_for(mF), 256>>>(h->d_states, d_frontier, i0, mF, h->S, h->K, nu_of(h, j), bd, use_default,
+                                                 h->d_cand + (size_t) j * mF * h->S, h->d_valid + (size_t) j * mF, d_fstatus);
+        FSP_LAUNCH_CHECK();
+      }
+      if (!use_default && m > 0) {
+        if (host_validity(h, m, cand_host, fval, valid_host)) return -1;
+        for (int j = 0; j < h->R; ++j) {
+          apply_valid_kernel<<<blocks_for(mF), 256>>>(h->d_valid + (size_t) j * mF, i0, mF, d_fstatus);
+          FSP_LAUNCH_CHECK();
+        }
+      }
+      if (sh_insert_batch(h, m, false)) return -1;
     }
     if (nF > 0) {
       set_frontier_status_kernel<<<blocks_for(nF), 256>>>(h->d_status, d_frontier, d_fstatus, nF);
@@ -920,6 +989,7 @@ int fspset_destroy(fspset_t h) {
     // the windows go back to the communicator's pool: destructors are not collective
     cudaDeviceSynchronize();
     fspcomm_window_retire(h->comm, h->win_data, h->data_bytes);
+    if (h->have_spare) fspcomm_window_retire(h->comm, h->win_spare, h->data_bytes);
     fspcomm_window_retire(h->comm, h->win_cand, h->cand_bytes);
     fspcomm_window_retire(h->comm, h->win_table, h->table_bytes);
     pfree(h->d_err);

@@ -79,6 +79,10 @@ def run_case(api, dist, dev, name, bounds, times, reps=3, seed=99, sharded=False
             perm = so.state2index(states_g.astype(np.int32))
             if not ((perm >= 0).all() and len(np.unique(perm)) == N):  # the two state sets differ
                 e_states, perm = float("inf"), None
+    if dist is not None:
+        # rank 0 may have spent seconds in the oracle: the other ranks wait HERE (no time limit), not inside the Action's
+        # device-side flag waits, which give up after FSP_SPIN_TIMEOUT_MS (20 s) and poison the result
+        dist.barrier()
     for t in times:
         xd = torch.from_numpy(xl).to(dev)
         yd = torch.empty_like(xd)
