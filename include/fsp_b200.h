@@ -467,6 +467,7 @@ FSP_API int fspcomm_window_destroy(fspcomm_t c, void **peers);
 FSP_API int fspcomm_window_retire(fspcomm_t c, void **peers, size_t bytes);
 /* stream-ordered barrier over all ranks / synchronising gather of one integer per rank */
 FSP_API int fspcomm_barrier(fspcomm_t c, void *stream);
+FSP_API int fspcomm_barrier_sync(fspcomm_t c); /* host-synchronising, through NCCL, no time limit */
 FSP_API int fspcomm_gather_long(fspcomm_t c, long mine, long *all_host);
 /* The whole multi-GPU Action (src/Matrix/FspMatrixBase.cpp:36-62 with the ghost VecScatter of MatMult on MATMPISELL,
  * and the sink VecScatter ADD of FspMatrixConstrained.cpp:57-60) as ONE launch on one stream, no events, no NCCL:

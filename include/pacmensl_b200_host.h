@@ -43,8 +43,8 @@ FSP_API int pfsp_set_create(void **set);
 FSP_API int pfsp_set_destroy(void *set);
 /* Extension (multi-GPU): distributed construction as in src/StateSet/StateSetBase.cpp:134-154,188-258 -- every rank
  * keeps and expands only its block of states, the directory is striped over the GPUs (fsp_b200.h: fspset_set_sharded).
- * Call before the first pfsp_set_add_states; a no-op on one rank or without peer memory.  FSP_SHARDED_SET=1 in the
- * environment turns it on for every set. */
+ * Call before the first pfsp_set_add_states; a no-op on one rank or without peer memory.  On > 1 rank this is the
+ * default; on = 0 (or FSP_SHARDED_SET=0 in the environment) keeps the replicated directory. */
 FSP_API int pfsp_set_set_sharded(void *set, int on);
 FSP_API int pfsp_set_is_sharded(void *set);
 /* State2Index(states_old) of src/Fsp/FspSolverMultiSinks.cpp:174-176 on the device: remember the local block before

@@ -179,6 +179,7 @@ SIGNATURES = {
     "fspcomm_window_destroy": (ci, [vp, vpp]),
     "fspcomm_window_retire": (ci, [vp, vpp, C.c_size_t]),
     "fspcomm_barrier": (ci, [vp, vp]),
+    "fspcomm_barrier_sync": (ci, [vp]),
     "fspcomm_gather_long": (ci, [vp, cl, lp]),
     "fspmat_action_halo": (ci, [vp, dp, vp, vp, vp, vp, vp]),
     "fspmat_halo_fused_supported": (ci, [vp]),

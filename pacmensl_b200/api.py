@@ -139,15 +139,15 @@ def p2p_enabled():
 
 
 class StateSet:
-    def __init__(self, SM, sharded=False):
+    def __init__(self, SM, sharded=None):
         SM = np.asarray(SM, dtype=np.int32)  # S x R as written in the reference
         self.S, self.R = SM.shape
         self._sm = np.ascontiguousarray(SM.T)
         h = vp()
         check(lib().pfsp_set_create(C.byref(h)), "pfsp_set_create")
         self.h = h
-        if sharded:  # multi-GPU: distributed construction, striped directory (a no-op on one rank)
-            check(lib().pfsp_set_set_sharded(self.h, 1), "SetSharded")
+        if sharded is not None:  # multi-GPU: distributed construction + striped directory (default) or replicated
+            check(lib().pfsp_set_set_sharded(self.h, 1 if sharded else 0), "SetSharded")
         check(lib().pfsp_set_stoichiometry(self.h, self.S, self.R, _ip(self._sm)), "SetStoichiometryMatrix")
         self._keep = []
 
@@ -423,7 +423,7 @@ class FspSolver:
         return lib().pfsp_solver_clear(self.h)
 
 
-def fixture_set_and_matrix(name, bounds=None, model=None, constrained=True, sharded=False):
+def fixture_set_and_matrix(name, bounds=None, model=None, constrained=True, sharded=None):
     """StateSetConstrained (x0 added, Expand()ed within `bounds`) + generated FspMatrix of a named workload."""
     m = model or Model(fixture=name)
     fx = m.fixture

@@ -654,6 +654,12 @@ int fspcomm_barrier(fspcomm_t c, void *stream) {
   return fspcomm_allreduce_sum(c, c->coll + kMaxRanks, 1, stream);
 }
 
+// Host-synchronising barrier through NCCL: no time limit, for points where ranks may be seconds apart (host callbacks).
+int fspcomm_barrier_sync(fspcomm_t c) {
+  if (!c || c->size == 1) return 0;
+  return agree(c, true) < 0 ? -1 : 0;
+}
+
 // Collective, synchronising: all_host[p] = the value rank p passed (|value| < 2^53).
 int fspcomm_gather_long(fspcomm_t c, long mine, long *all_host) {
   if (!c || c->size == 1) { all_host[0] = mine; return 0; }

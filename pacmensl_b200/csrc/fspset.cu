@@ -763,7 +763,11 @@ int sh_insert_batch(fspset_s *h, long m, bool all_valid) {
 int sh_insert_batch_impl(fspset_s *h, long m, bool all_valid) {
   const ShardView     v = make_view(h);
   const signed char *valid = all_valid ? nullptr : h->d_valid;
-  if (sh_barrier(h)) return -1;  // every rank's candidates are written, the previous batch is complete
+  // every rank's candidates are written, the previous batch is complete.  With a host constraint callback the ranks can
+  // be seconds apart here (the rank that owns the frontier evaluated it): meet through NCCL, which has no time limit,
+  // before the flag barrier, whose device-side wait gives up after FSP_SPIN_TIMEOUT_MS
+  if (h->lhs && fspcomm_barrier_sync(h->comm)) return -1;
+  if (sh_barrier(h)) return -1;
   if (m > 0) {
     sh_insert_kernel<<<blocks_for(m), 256>>>(v, m, valid);
     FSP_LAUNCH_CHECK();

@@ -190,7 +190,7 @@ PacmenslErrorCode FspSolverMultiSinks::SetUp() {
   if (!state_set_) {
     double t0 = now_s();
     state_set_ = std::make_shared<StateSetConstrained>(comm_);
-    if (sharded_set_) state_set_->SetSharded(true);
+    if (sharded_set_ >= 0) state_set_->SetSharded(sharded_set_ != 0);
     state_set_->SetStoichiometryMatrix(model_.stoichiometry_matrix_);
     if (has_custom_constraints_) state_set_->SetShape(fsp_constr_funs_, fsp_bounds_, fsp_constr_args_);
     else state_set_->SetShapeBounds(fsp_bounds_);

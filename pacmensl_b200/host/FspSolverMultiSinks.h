@@ -68,7 +68,7 @@ class PACMENSL_API FspSolverMultiSinks {
   /// the new states enter at 0 with weights 1/atol and no derivative history).  KrylovFsp always restarts as the
   /// reference does.
   /// Extension: build the state set sharded over the ranks (StateSetBase::SetSharded); before SetUp()
-  PacmenslErrorCode SetShardedStateSet(bool on) { sharded_set_ = on; return 0; }
+  PacmenslErrorCode SetShardedStateSet(bool on) { sharded_set_ = on ? 1 : 0; return 0; }
   PacmenslErrorCode SetWarmRestart(bool on) { warm_restart_ = on; if (ode_solver_) ode_solver_->SetWarmRestart(on); return 0; }
 
   std::shared_ptr<const StateSetBase> GetStateSet();
@@ -140,7 +140,7 @@ class PACMENSL_API FspSolverMultiSinks {
   std::string ts_type_ = "";
   bool        custom_krylov_ = false;
   bool        warm_restart_ = false;
-  bool        sharded_set_ = false;
+  int         sharded_set_ = -1;  ///< -1: the state set's default
   int         q_iop_ = -1;
   int         m_min_ = 25, m_max_ = 60;
 

@@ -65,8 +65,9 @@ PacmenslErrorCode StateSetBase::ensure_device_set() {
     num_reactions_ = 0;
   }
   FSPCHKERRQ(fspset_create(&dset_, num_species_, num_reactions_, stoichiometry_matrix_.memptr()));
-  static const bool env_sharded = [] { const char *e = std::getenv("FSP_SHARDED_SET"); return e && e[0] == '1'; }();
-  if ((want_sharded_ || env_sharded) && comm_size_ > 1 && comm_ && fspcomm_p2p_enabled(comm_->nccl))
+  static const bool env_sharded = [] { const char *e = std::getenv("FSP_SHARDED_SET"); return !(e && e[0] == '0'); }();
+  const bool sharded = want_sharded_ >= 0 ? want_sharded_ != 0 : env_sharded;
+  if (sharded && comm_size_ > 1 && comm_ && fspcomm_p2p_enabled(comm_->nccl))
     FSPCHKERRQ(fspset_set_sharded(dset_, comm_->nccl));
   return 0;
 }
@@ -76,7 +77,7 @@ PacmenslErrorCode StateSetBase::SetSharded(bool on) {
     if (my_rank_ == 0) std::cout << "SetSharded() must be called before states are added; ignored.\n";
     return 0;
   }
-  want_sharded_ = on;
+  want_sharded_ = on ? 1 : 0;
   return 0;
 }
 

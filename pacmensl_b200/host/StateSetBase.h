@@ -58,8 +58,9 @@ class PACMENSL_API StateSetBase {
   /// Extension: distribute the construction like the reference does (src/StateSet/StateSetBase.cpp:134-154,188-258):
   /// every rank keeps only its block of states, explores the frontier states it owns, and the directory is striped
   /// over the GPUs' HBM (include/fsp_b200.h: fspset_set_sharded).  Must be called before the first state is added;
-  /// needs > 1 rank with peer memory, otherwise the replicated directory stays.  FSP_SHARDED_SET=1 turns it on for every
-  /// multi-GPU set.  Global indices then change when the set grows (as in the reference): see RememberLocalStates.
+  /// needs > 1 rank with peer memory, otherwise the replicated directory stays.  This is the DEFAULT on > 1 rank;
+  /// SetSharded(false) or FSP_SHARDED_SET=0 keep the replicated directory (every rank holds and expands the whole set).
+  /// Global indices of a sharded set change when it grows (as in the reference): see RememberLocalStates.
   PacmenslErrorCode SetSharded(bool on = true);
   bool IsSharded() const { return dset_ && fspset_is_sharded(dset_) != 0; }
   /// State2Index(states_old) of FspSolverMultiSinks.cpp:174-205 without the host round trip: remember the local block
@@ -80,7 +81,7 @@ class PACMENSL_API StateSetBase {
   double           lb_threshold_ = 0.2;
 
   fspset_t               dset_ = nullptr;
-  bool                   want_sharded_ = false;
+  int                    want_sharded_ = -1;  ///< -1: default (FSP_SHARDED_SET, else on), 0 / 1: SetSharded()
   long                   n_remembered_ = 0;
   mutable arma::Mat<int> local_states_;
   mutable bool           host_states_valid_ = false;

@@ -16,7 +16,7 @@ ORDERS = np.array([[0, 1, 0, 0, 0, 0], [0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 0, 1]], 
 
 
 class Lattice:
-    def __init__(self, upper, tv=False, expand=True, sharded=False):
+    def __init__(self, upper, tv=False, expand=True, sharded=None):
         self.upper = [int(u) for u in upper]
         self.set = api.StateSet(SM, sharded=sharded)
         assert self.set.set_shape(self.upper) == 0

@@ -77,8 +77,7 @@ def solve_pair(api, dev, name, ode, t_final, tol, rank, bounds=None):
         s, m = api.fixture_solver(name, ode)
         if bounds is not None:
             s.set_initial_bounds(bounds)
-        if sharded:
-            s.set_sharded_state_set(True)
+        s.set_sharded_state_set(sharded)
         states, p = s.solve(t_final, tol)
         S = states.shape[1]
         allst = gather_rows(states.astype(np.int32), dev, S)

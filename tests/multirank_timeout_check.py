@@ -21,7 +21,9 @@ def main():
     from pacmensl_b200.lattice import Lattice
     api.init(local_rank, dist)
     ok = api.p2p_enabled()
-    lat = Lattice([21, 17, 13])
+    # replicated set: the collective (sharded) construction has device-side barriers of its own, which the 300 ms limit
+    # of this test would cut short whenever the ranks' first kernels load a few hundred ms apart
+    lat = Lattice([21, 17, 13], sharded=False)
     x = torch.rand(lat.n_rows, dtype=torch.float64, device=dev)
     y = torch.empty_like(x)
     lat.action(0.0, x, y)            # a healthy Action on every rank

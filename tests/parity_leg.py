@@ -39,7 +39,7 @@ def _gather(local, dist, dev, dtype):
     return np.concatenate([o[: sizes[r]].cpu().numpy() for r, o in enumerate(outs)])
 
 
-def run_case(api, dist, dev, name, bounds, times, reps=3, seed=99, sharded=False):
+def run_case(api, dist, dev, name, bounds, times, reps=3, seed=99, sharded=None):
     """Returns (states_rel_err, sinks_rel_err, n_states) on rank 0 (zeros elsewhere)."""
     import torch
     rank = dist.get_rank() if dist is not None else 0
@@ -108,7 +108,7 @@ def run_case(api, dist, dev, name, bounds, times, reps=3, seed=99, sharded=False
     return e_states, e_sinks, N
 
 
-def run(api, dist, dev, cases=None, verbose=False, sharded=False):
+def run(api, dist, dev, cases=None, verbose=False, sharded=None):
     """Runs all cases; returns {"max_rel_err", "sinks_rel_err", "cases": {...}, "ok"} (meaningful on rank 0)."""
     out = {"max_rel_err": 0.0, "sinks_rel_err": 0.0, "tol": TOL, "cases": {}}
     rank = dist.get_rank() if dist is not None else 0
@@ -118,6 +118,6 @@ def run(api, dist, dev, cases=None, verbose=False, sharded=False):
         out["max_rel_err"] = max(out["max_rel_err"], es)
         out["sinks_rel_err"] = max(out["sinks_rel_err"], ek)
         if verbose and rank == 0:
-            print("action parity %-18s N=%-7d rel_err states %.2e sinks %.2e%s" % (name, n, es, ek, "  (sharded set)" if sharded else ""))
+            print("action parity %-18s N=%-7d rel_err states %.2e sinks %.2e%s" % (name, n, es, ek, "  (sharded set)" if sharded else ("  (replicated set)" if sharded is False else "")))
     out["ok"] = bool(out["max_rel_err"] <= TOL and out["sinks_rel_err"] <= TOL)
     return out

@@ -25,7 +25,7 @@ def test_partitioned_action_and_solves(cuda, nranks):
     assert r.returncode == 0 and "MULTIRANK OK" in r.stdout
 
 
-@pytest.mark.parametrize("prog", ["test_mat", "test_fss", "test_ode", "test_fsp_solver"])
+@pytest.mark.parametrize("prog", ["test_mat", "test_fss", "test_ode", "test_fsp_solver", "test_sensmat", "test_sensfsp_solver"])
 def test_cpp_programs_two_ranks(cuda, prog):
     if _ngpu(cuda) < 2:
         pytest.skip("needs 2 GPUs")
@@ -49,12 +49,13 @@ def test_sharded_state_set(cuda, nranks):
 
 
 @pytest.mark.parametrize("prog", ["test_fss", "test_mat", "test_fsp_solver"])
-def test_cpp_programs_two_ranks_sharded_sets(cuda, prog):
-    # the reference's own multi-rank test programs with every state set built sharded (FSP_SHARDED_SET=1)
+def test_cpp_programs_two_ranks_replicated_sets(cuda, prog):
+    # the state sets of test_cpp_programs_two_ranks are sharded (the multi-GPU default); here the same programs with the
+    # replicated directory (FSP_SHARDED_SET=0: every rank holds and expands the whole set)
     if _ngpu(cuda) < 2:
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([os.path.join(ROOT, "tools", "launch_ranks.sh"), "2", os.path.join(ROOT, "build", "tests", prog)],
-                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, FSP_SHARDED_SET="1"))
+                       capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, FSP_SHARDED_SET="0"))
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0 and "0 failed" in r.stdout
 
