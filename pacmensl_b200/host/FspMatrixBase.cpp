@@ -676,6 +676,15 @@ PacmenslErrorCode FspMatrixBase::ActionHost(PetscReal t, const double *x_host, d
   while ((int) ev_cmp_.size() < C + 1) { void *e = nullptr; FSPCHKERRQ(fsp_event_create(&e)); ev_cmp_.push_back(e); }
   const double *coefs = time_coefficients_.memptr();
   if (comm_size_ > 1) return ActionHostPartitioned_(coefs, x_host, y_host, C, chunk);
+  // FSP_HOST_TRACE=1: the time line of the pipeline (event times relative to the first upload), for tuning
+  static const bool host_trace = [] { const char *e = std::getenv("FSP_HOST_TRACE"); return e && e[0] == '1'; }();
+  std::vector<void *> ev_down;
+  void               *ev_start = nullptr;
+  if (host_trace) {
+    FSPCHKERRQ(fsp_event_create(&ev_start));
+    for (int k = 0; k < C; ++k) { void *e = nullptr; FSPCHKERRQ(fsp_event_create(&e)); ev_down.push_back(e); }
+    FSPCHKERRQ(fsp_event_record(ev_start, up_stream_));
+  }
   // stage 1: all uploads, in order (chunk k of x, the sink entries ride with the last chunk)
   for (int k = 0; k < C; ++k) {
     const long b = std::min<long>(ns, (long) k * chunk), e = (k == C - 1) ? n : std::min<long>(ns, (long) (k + 1) * chunk);
@@ -693,6 +702,7 @@ PacmenslErrorCode FspMatrixBase::ActionHost(PetscReal t, const double *x_host, d
     FSPCHKERRQ(fsp_event_record(ev_cmp_[c], host_compute_stream_));
     FSPCHKERRQ(fsp_stream_wait_event(down_stream_, ev_cmp_[c]));
     FSPCHKERRQ(fsp_memcpy_d2h_async(y_host + b, hy_.get() + b, sizeof(double) * (e - b), down_stream_));
+    if (host_trace) FSPCHKERRQ(fsp_event_record(ev_down[c], down_stream_));
   }
   if (n > ns) {  // sink rows need all of x
     FSPCHKERRQ(fsp_stream_wait_event(host_compute_stream_, ev_up_[C - 1]));
@@ -704,6 +714,21 @@ PacmenslErrorCode FspMatrixBase::ActionHost(PetscReal t, const double *x_host, d
   FSPCHKERRQ(fsp_stream_sync(down_stream_));
   FSPCHKERRQ(fsp_stream_sync(host_compute_stream_));
   FSPCHKERRQ(fsp_stream_sync(up_stream_));
+  if (host_trace) {
+    static int calls = 0;
+    if (++calls == 3) {  // a warm call
+      printf("[host pipeline] %d chunks of %ld rows: chunk | x up by | rows done by | y down by  (ms after the first upload was queued)\n", C, chunk);
+      for (int c = 0; c < C; ++c) {
+        float u = 0, m = 0, d = 0;
+        fsp_event_elapsed_ms(ev_start, ev_up_[c], &u);
+        fsp_event_elapsed_ms(ev_start, ev_cmp_[c], &m);
+        fsp_event_elapsed_ms(ev_start, ev_down[c], &d);
+        printf("[host pipeline] %3d | %7.3f | %7.3f | %7.3f | needs x up to chunk %ld\n", c, u, m, d, std::min<long>(C - 1, std::max<long>(host_chunk_need_[c], 0) / chunk));
+      }
+    }
+    for (void *e : ev_down) fsp_event_destroy(e);
+    fsp_event_destroy(ev_start);
+  }
   return 0;
 }
 
