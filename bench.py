@@ -525,6 +525,9 @@ def main():
                                "them into the peers' ghost windows (CUDA IPC over NVLink) + epoch flag, row CTAs wait in device code "
                                "only where a warp meets a ghost column, sink slots summed by the owner; no NCCL call per Action"
                                if p2p else "NCCL halo exchange + K-double sink all-reduce per Action")),
+                       "state_set": "one block" if world == 1 else (
+                           "sharded construction: each rank built its block, directory striped over the GPUs' HBM (peer windows)"
+                           if lat.set.is_sharded() else "replicated directory (every rank built the whole set)"),
                        "kernel_variant": args.variant, "build_seconds": round(t_build, 2),
                        "timing": "device barrier (all-reduce) on the launching stream, then CUDA events around exactly K steps; max over ranks"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

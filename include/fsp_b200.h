@@ -247,6 +247,11 @@ struct fspcomm_s;
 FSP_API int fspset_set_sharded(fspset_t h, struct fspcomm_s *comm);
 FSP_API int fspset_is_sharded(fspset_t h);
 FSP_API int fspset_layout(fspset_t h, long *starts_host /* n_ranks + 1 */, long *n_local);
+/* host arithmetic of the re-balance, no device access: BLOCK layout of sum(counts) states and the segments rank `rank`
+ * pulls (seg_len[k] states from position seg_off[k] of rank seg_src[k] to its own position seg_dst[k]); arrays of
+ * n_ranks (+ 1 for starts) entries */
+FSP_API int fspset_rebalance_plan(int n_ranks, const long *counts, int rank, long *starts, long *seg_src, long *seg_off,
+                                  long *seg_dst, long *seg_len, int *n_seg, int *already_balanced);
 /* keep a device copy of the local block of states / afterwards: their current global indices (host array of the
  * remembered length), the copy is released.  StateSetBase::State2Index(states_old) of FspSolverMultiSinks.cpp:174-205. */
 FSP_API int fspset_remember_local(fspset_t h);

@@ -126,6 +126,7 @@ SIGNATURES = {
     "fspset_set_sharded": (ci, [vp, vp]),
     "fspset_is_sharded": (ci, [vp]),
     "fspset_layout": (ci, [vp, lp, lp]),
+    "fspset_rebalance_plan": (ci, [ci, lp, ci, lp, lp, lp, lp, lp, ip, ip]),
     "fspset_remember_local": (ci, [vp]),
     "fspset_remembered_indices": (ci, [vp, ip, cl]),
     "fspset_eval_mass_action": (ci, [vp, cd, ip, ip, ci, cl, cl, vp]),

@@ -801,14 +801,12 @@ int sh_rebalance(fspset_s *h) {
 }
 int sh_rebalance_impl(fspset_s *h) {
   const int N = h->size;
-  long      n = 0;
-  std::vector<long> C((size_t) N + 1, 0), T((size_t) N + 1, 0);
-  for (int r = 0; r < N; ++r) { C[(size_t) r + 1] = C[(size_t) r] + h->counts[(size_t) r]; }
-  n = C[(size_t) N];
-  const long base = n / N, rem = n % N;
-  for (int r = 0; r < N; ++r) T[(size_t) r + 1] = T[(size_t) r] + base + (r < rem ? 1 : 0);
-  h->n_glob = n;
-  const bool same = C == T;
+  std::vector<long> T((size_t) N + 1, 0), seg_src((size_t) N), seg_off((size_t) N), seg_dst((size_t) N), seg_len((size_t) N);
+  int               n_seg = 0, same_i = 0;
+  if (fspset_rebalance_plan(N, h->counts.data(), h->rank, T.data(), seg_src.data(), seg_off.data(), seg_dst.data(), seg_len.data(),
+                            &n_seg, &same_i)) return -1;
+  h->n_glob = T[(size_t) N];
+  const bool same = same_i != 0;
   if (!same) {
     h->tr.rebalances += 1;
     // target: the spare window (same capacity as the current one, created at the first re-balance after a growth and
@@ -827,14 +825,12 @@ int sh_rebalance_impl(fspset_s *h) {
     int         *ns = (int *) nw[h->rank];
     signed char *nst = (signed char *) (ns + (size_t) new_cap * h->S);
     const long   lo_me = T[(size_t) h->rank], hi_me = T[(size_t) h->rank + 1];
-    for (int q = 0; q < N; ++q) {
-      const long lo = std::max(lo_me, C[(size_t) q]), hi = std::min(hi_me, C[(size_t) q + 1]);
-      if (lo >= hi) continue;
-      const int         *src = (const int *) h->win_data[q];
+    for (int k = 0; k < n_seg; ++k) {  // pull: seg_len states from position seg_off of rank seg_src to my position seg_dst
+      const int         *src = (const int *) h->win_data[seg_src[(size_t) k]];
       const signed char *src_st = (const signed char *) (src + (size_t) h->cap * h->S);
-      FSP_CUDA_CHECK(cudaMemcpyAsync(ns + (size_t) (lo - lo_me) * h->S, src + (size_t) (lo - C[(size_t) q]) * h->S,
-                                     sizeof(int) * (size_t) (hi - lo) * h->S, cudaMemcpyDefault, 0));
-      FSP_CUDA_CHECK(cudaMemcpyAsync(nst + (lo - lo_me), src_st + (lo - C[(size_t) q]), (size_t) (hi - lo), cudaMemcpyDefault, 0));
+      FSP_CUDA_CHECK(cudaMemcpyAsync(ns + (size_t) seg_dst[(size_t) k] * h->S, src + (size_t) seg_off[(size_t) k] * h->S,
+                                     sizeof(int) * (size_t) seg_len[(size_t) k] * h->S, cudaMemcpyDefault, 0));
+      FSP_CUDA_CHECK(cudaMemcpyAsync(nst + seg_dst[(size_t) k], src_st + seg_off[(size_t) k], (size_t) seg_len[(size_t) k], cudaMemcpyDefault, 0));
     }
     FSP_CUDA_CHECK(cudaDeviceSynchronize());
     // the old window becomes the spare: nobody writes to it before the next re-balance, whose barrier comes after every
@@ -1020,6 +1016,36 @@ int fspset_set_sharded(fspset_t h, fspcomm_s *comm) {
   return 0;
 }
 int fspset_is_sharded(fspset_t h) { return h && h->sharded ? 1 : 0; }
+
+// Host arithmetic of the re-balance (no device access: also exercised on CPU by tests/test_sharded_plan.py).
+// counts[r] states on rank r now; the rank-concatenated listing is re-cut into the BLOCK layout starts[0..n_ranks]
+// (ranks below n mod n_ranks own one more); rank `rank` pulls segment k = seg_len[k] states from position seg_off[k] of
+// rank seg_src[k] to its own position seg_dst[k] (at most n_ranks segments, ascending).
+int fspset_rebalance_plan(int n_ranks, const long *counts, int rank, long *starts, long *seg_src, long *seg_off, long *seg_dst,
+                          long *seg_len, int *n_seg, int *already_balanced) {
+  if (n_ranks <= 0 || rank < 0 || rank >= n_ranks) return -1;
+  std::vector<long> C((size_t) n_ranks + 1, 0);
+  for (int r = 0; r < n_ranks; ++r) {
+    if (counts[r] < 0) return -1;
+    C[(size_t) r + 1] = C[(size_t) r] + counts[r];
+  }
+  const long n = C[(size_t) n_ranks], base = n / n_ranks, rem = n % n_ranks;
+  starts[0] = 0;
+  for (int r = 0; r < n_ranks; ++r) starts[r + 1] = starts[r] + base + (r < rem ? 1 : 0);
+  int same = 1;
+  for (int r = 0; r <= n_ranks; ++r) same &= starts[r] == C[(size_t) r] ? 1 : 0;
+  *already_balanced = same;
+  const long lo_me = starts[rank], hi_me = starts[rank + 1];
+  int        k = 0;
+  for (int q = 0; q < n_ranks; ++q) {
+    const long lo = std::max(lo_me, C[(size_t) q]), hi = std::min(hi_me, C[(size_t) q + 1]);
+    if (lo >= hi) continue;
+    seg_src[k] = q; seg_off[k] = lo - C[(size_t) q]; seg_dst[k] = lo - lo_me; seg_len[k] = hi - lo;
+    ++k;
+  }
+  *n_seg = k;
+  return 0;
+}
 int fspset_layout(fspset_t h, long *starts_host, long *n_local) {
   if (h->sharded) for (int p = 0; p <= h->size; ++p) starts_host[p] = h->starts[(size_t) p];
   else { starts_host[0] = 0; starts_host[1] = h->n; }
