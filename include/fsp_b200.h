@@ -182,6 +182,11 @@ FSP_API int fspvec_scatter_range(double *p_new_dev, long n_new, const double *va
                                  long own_start, void *stream);
 /* out[i] = x[idx[i]]  (MakeDiscreteDistribution_ scatter, src/Fsp/FspSolverMultiSinks.cpp:703-735) */
 FSP_API int fspvec_gather(double *out_dev, const double *x_dev, const int *idx_dev, long n, void *stream);
+/* Multi-GPU ExpandVec routing (src/Sys/PetscWrap.cpp:10-45): the n entries (idx[i], val[i]) sorted by the rank owning
+ * global index idx[i] under starts_host[0..n_ranks] (entries outside are dropped); counts_host[r] = entries for rank r,
+ * rank r's segment starts at sum(counts[0..r)) of idx_sorted / val_sorted.  Synchronises the stream. */
+FSP_API int fspvec_route_by_owner(const int *idx_dev, const double *val_dev, long n, const long *starts_host, int n_ranks,
+                                  int *idx_sorted_dev, double *val_sorted_dev, long *counts_host, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * State set on the device: state list + hash directory.

@@ -106,6 +106,7 @@ SIGNATURES = {
     "fspvec_norm1_h": (ci, [dp, vp, cl, vp]),
     "fspvec_scatter": (ci, [vp, cl, vp, vp, cl, vp]),
     "fspvec_gather": (ci, [vp, vp, vp, cl, vp]),
+    "fspvec_route_by_owner": (ci, [vp, vp, cl, lp, ci, vp, vp, lp, vp]),
     "fspvec_scatter_range": (ci, [vp, cl, vp, vp, cl, cl, vp]),
     "fspset_create": (ci, [vpp, ci, ci, ip]),
     "fspset_destroy": (ci, [vp]),

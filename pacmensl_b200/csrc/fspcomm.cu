@@ -416,8 +416,13 @@ int fspcomm_halo_exchange(fspcomm_t c, const double *send, const long *send_coun
   FSP_NCCL_CHECK(g_nccl.GroupStart());
   long so = 0, ro = 0;
   for (int p = 0; p < c->size; ++p) {
-    if (send_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Send(send + so, (size_t) send_counts[p], ncclFloat64, p, c->comm, st));
-    if (recv_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Recv(ghost + ro, (size_t) recv_counts[p], ncclFloat64, p, c->comm, st));
+    if (p == c->rank) {  // the own segment never touches the network
+      if (send_counts[p] > 0 && send_counts[p] == recv_counts[p])
+        FSP_CUDA_CHECK(cudaMemcpyAsync(ghost + ro, send + so, sizeof(double) * (size_t) send_counts[p], cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (send_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Send(send + so, (size_t) send_counts[p], ncclFloat64, p, c->comm, st));
+      if (recv_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Recv(ghost + ro, (size_t) recv_counts[p], ncclFloat64, p, c->comm, st));
+    }
     so += send_counts[p];
     ro += recv_counts[p];
   }
@@ -458,8 +463,13 @@ int fspcomm_exchange_int(fspcomm_t c, const int *send, const long *send_counts, 
   FSP_NCCL_CHECK(g_nccl.GroupStart());
   long so = 0, ro = 0;
   for (int p = 0; p < c->size; ++p) {
-    if (send_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Send(send + so, (size_t) send_counts[p], ncclInt32, p, c->comm, st));
-    if (recv_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Recv(recv + ro, (size_t) recv_counts[p], ncclInt32, p, c->comm, st));
+    if (p == c->rank) {
+      if (send_counts[p] > 0 && send_counts[p] == recv_counts[p])
+        FSP_CUDA_CHECK(cudaMemcpyAsync(recv + ro, send + so, sizeof(int) * (size_t) send_counts[p], cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (send_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Send(send + so, (size_t) send_counts[p], ncclInt32, p, c->comm, st));
+      if (recv_counts[p] > 0) FSP_NCCL_CHECK(g_nccl.Recv(recv + ro, (size_t) recv_counts[p], ncclInt32, p, c->comm, st));
+    }
     so += send_counts[p];
     ro += recv_counts[p];
   }

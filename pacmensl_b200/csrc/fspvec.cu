@@ -6,6 +6,7 @@
 // pointers allow it, grids sized as a multiple of the SM count, and two-stage fixed-shape reductions
 // (per-block partials -> last block sums them in a fixed order), so results are deterministic.
 #include <cooperative_groups.h>
+#include <cub/cub.cuh>
 
 #include "fsp_common.cuh"
 
@@ -150,6 +151,36 @@ struct ScatterRangeF {
     if (g[i] >= 0 && j >= 0 && j < n_new) pn[j] = v[i];
   }
 };
+struct OwnerStarts { long s[FSP_P2P_MAX_RANKS + 1]; int n; };
+// key = owner of global index idx[i] (n = outside every block: sorted to the end and dropped)
+struct OwnerKeyF {
+  const int *idx; OwnerStarts st; unsigned char *key; int *pos;
+  __device__ void operator()(long i) const {
+    const long g = idx[i];
+    int        r = st.n;
+    if (g >= 0 && g < st.s[st.n]) {
+      r = 0;
+      while (g >= st.s[r + 1]) ++r;
+    }
+    key[i] = (unsigned char) r;
+    pos[i] = (int) i;
+  }
+};
+struct PackPairF {
+  int *oi; double *ov; const int *idx; const double *val; const int *perm;
+  __device__ void operator()(long i) const { const int j = perm[i]; oi[i] = idx[j]; ov[i] = val[j]; }
+};
+// bounds[r] = first position of key >= r in the sorted keys (r = 0 .. n_ranks)
+__global__ void owner_bounds_kernel(const unsigned char *key, int n, int n_ranks, int *bounds) {
+  const int r = threadIdx.x;
+  if (r > n_ranks) return;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int) key[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  bounds[r] = lo;
+}
 struct GatherF {
   double *o; const double *x; const int *idx;
   __device__ void operator()(long i) const { int j = idx[i]; o[i] = j >= 0 ? x[j] : 0.0; }
@@ -871,6 +902,47 @@ int fspvec_scatter_range(double *pn, long n_new, const double *v, const int *g, 
 }
 int fspvec_gather(double *o, const double *x, const int *idx, long n, void *s) {
   return launch_map(GatherF{o, x, idx}, n, s);
+}
+
+// Multi-GPU ExpandVec (src/Sys/PetscWrap.cpp:10-45, VecScatter to the new layout): sort the entries (idx[i], val[i]) by the
+// rank that owns global index idx[i] under `starts` (n_ranks + 1 offsets), so that each peer's share is one contiguous
+// segment to send; entries outside [0, starts[n_ranks]) are dropped.  counts_host[r] = entries for rank r.
+int fspvec_route_by_owner(const int *idx, const double *val, long n, const long *starts_host, int n_ranks, int *idx_sorted,
+                          double *val_sorted, long *counts_host, void *s) {
+  for (int r = 0; r < n_ranks; ++r) counts_host[r] = 0;
+  if (n <= 0) return 0;
+  if (n_ranks > FSP_P2P_MAX_RANKS || n >= 0x7FFFFFF0L) { set_error("fspvec_route_by_owner: too many ranks or entries"); return -1; }
+  cudaStream_t st = resolve_stream(s);
+  OwnerStarts  os;
+  os.n = n_ranks;
+  for (int r = 0; r <= n_ranks; ++r) os.s[r] = starts_host[r];
+  unsigned char *key = nullptr, *key2 = nullptr;
+  int           *pos = nullptr, *pos2 = nullptr, *bounds = nullptr;
+  void          *tmp = nullptr;
+  int            rc = -1;
+  do {
+    if (pmalloc(&key, (size_t) n) != cudaSuccess || pmalloc(&key2, (size_t) n) != cudaSuccess ||
+        pmalloc(&pos, sizeof(int) * (size_t) n) != cudaSuccess || pmalloc(&pos2, sizeof(int) * (size_t) n) != cudaSuccess ||
+        pmalloc(&bounds, sizeof(int) * (FSP_P2P_MAX_RANKS + 2)) != cudaSuccess) { set_error("fspvec_route_by_owner: allocation failed"); break; }
+    if (launch_map(OwnerKeyF{idx, os, key, pos}, n, s)) break;
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, key, key2, pos, pos2, (int) n, 0, 5, st);
+    if (pmalloc(&tmp, need) != cudaSuccess) { set_error("fspvec_route_by_owner: allocation failed"); break; }
+    if (cub::DeviceRadixSort::SortPairs(tmp, need, key, key2, pos, pos2, (int) n, 0, 5, st) != cudaSuccess) { set_error("fspvec_route_by_owner: sort failed"); break; }
+    count_launch();
+    owner_bounds_kernel<<<1, 32, 0, st>>>(key2, (int) n, n_ranks, bounds);
+    if (cudaGetLastError() != cudaSuccess) { set_error("fspvec_route_by_owner: launch failed"); break; }
+    count_launch();
+    if (launch_map(PackPairF{idx_sorted, val_sorted, idx, val, pos2}, n, s)) break;
+    int hb[FSP_P2P_MAX_RANKS + 2];
+    if (cudaMemcpyAsync(hb, bounds, sizeof(int) * (n_ranks + 1), cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+    if (cudaStreamSynchronize(st) != cudaSuccess) break;
+    for (int r = 0; r < n_ranks; ++r) counts_host[r] = hb[r + 1] - hb[r];
+    rc = 0;
+  } while (0);
+  if (rc) cudaGetLastError();
+  pfree(key); pfree(key2); pfree(pos); pfree(pos2); pfree(bounds); pfree(tmp);
+  return rc;
 }
 
 }  // extern "C"

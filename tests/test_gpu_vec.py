@@ -100,3 +100,31 @@ def test_scatter_gather_expandvec(cuda, L, oracle):
     back = torch.empty(n_old, dtype=torch.float64, device="cuda")
     assert L.fspvec_gather(P(back), P(pn), P(idd), n_old, s) == 0
     assert (back.cpu().numpy() == p).all()
+
+
+@pytest.mark.parametrize("n,n_ranks", [(1, 2), (5000, 2), (70001, 5), (300000, 16)])
+def test_route_by_owner(cuda, L, n, n_ranks):
+    # multi-GPU ExpandVec routing: entries sorted by the rank that owns their new global index, per-rank counts,
+    # out-of-range indices dropped; inside a segment the original order is kept (stable sort)
+    torch = cuda
+    rng = np.random.default_rng(n)
+    N = 4 * n + 7
+    cuts = np.sort(rng.integers(0, N + 1, size=n_ranks - 1))
+    starts = np.concatenate([[0], cuts, [N]]).astype(np.int64)   # some ranks may own nothing
+    idx = rng.integers(-3, N + 3, size=n).astype(np.int32)
+    val = rng.random(n)
+    idd, vd = torch.from_numpy(idx).cuda(), torch.from_numpy(val).cuda()
+    oi = torch.empty(n, dtype=torch.int32, device="cuda")
+    ov = torch.empty(n, dtype=torch.float64, device="cuda")
+    counts = (C.c_long * n_ranks)()
+    st = (C.c_long * (n_ranks + 1))(*[int(v) for v in starts])
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.fspvec_route_by_owner(P(idd), P(vd), n, st, n_ranks, P(oi), P(ov), counts, s) == 0
+    oi, ov = oi.cpu().numpy(), ov.cpu().numpy()
+    off = 0
+    for r in range(n_ranks):
+        sel = (idx >= starts[r]) & (idx < starts[r + 1]) & (idx >= 0)
+        assert counts[r] == int(sel.sum())
+        assert (oi[off: off + counts[r]] == idx[sel]).all() and (ov[off: off + counts[r]] == val[sel]).all()
+        off += counts[r]
+    assert off == int(((idx >= 0) & (idx < N)).sum())
