@@ -606,12 +606,15 @@ int fsphalo_check(fsphalo_t h) { return h ? check_peer_error(h->c, "fsphalo_chec
 int fspcomm_check(fspcomm_t c) { return (c && c->p2p) ? check_peer_error(c, "fspcomm_check") : 0; }
 
 // ---- general peer-memory windows (sharded state set: fspset.cu) ------------------------------------
-// Collective.  peers[p] = this process' mapping of rank p's window (peers[rank] = the local allocation), all of
-// `bytes` bytes.  A retired window of the same size is reused when there is one (identical sequence on all ranks).
+// Collective.  peers[p] = this process' mapping of rank p's window (peers[rank] = the local allocation), all of at
+// least `bytes` bytes.  A retired window of a fitting size is reused when there is one (identical sequence on all ranks);
+// its content is whatever the previous user left.
 int fspcomm_window_create(fspcomm_t c, size_t bytes, void **peers) {
   if (!c || !c->p2p) { set_error("fspcomm_window_create: peer memory is not enabled on this communicator"); return -1; }
+  // first fit among the pooled windows (the pool has the same content in the same order on every rank); a window up to
+  // four times larger than asked for is acceptable, so that the pool is actually reused when sizes drift
   for (size_t i = 0; i < c->retired.size(); ++i)
-    if (c->retired[i].bytes == bytes) {
+    if (c->retired[i].bytes >= bytes && c->retired[i].bytes / 4 <= bytes) {
       for (int p = 0; p < c->size; ++p) peers[p] = c->retired[i].peer[p];
       c->retired.erase(c->retired.begin() + (long) i);
       return 0;
