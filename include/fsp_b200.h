@@ -476,6 +476,12 @@ FSP_API int fspcomm_window_create(fspcomm_t c, size_t bytes, void **peers);
 FSP_API int fspcomm_window_destroy(fspcomm_t c, void **peers);
 FSP_API int fspcomm_window_retire(fspcomm_t c, void **peers, size_t bytes);
 /* stream-ordered barrier over all ranks / synchronising gather of one integer per rank */
+/* Personalised all-to-all of variable-size segments (esz = 4 or 8 bytes per element; send / recv hold the segments for /
+ * from rank 0, 1, ... back to back).  With peer memory the senders store into the receivers' windows over NVLink; else
+ * (or FSP_A2A=nccl) grouped ncclSend/ncclRecv.  Collective, synchronises the stream.  Replaces the MPI point-to-point
+ * traffic of the reference's VecScatter set-up (MatAssembly) and of ExpandVec (src/Sys/PetscWrap.cpp:10-45). */
+FSP_API int fspcomm_alltoallv(fspcomm_t c, const void *send_dev, const long *send_counts, void *recv_dev,
+                              const long *recv_counts, int esz, void *stream);
 FSP_API int fspcomm_barrier(fspcomm_t c, void *stream);
 FSP_API int fspcomm_barrier_sync(fspcomm_t c); /* host-synchronising, through NCCL, no time limit */
 FSP_API int fspcomm_gather_long(fspcomm_t c, long mine, long *all_host);

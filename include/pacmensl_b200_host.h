@@ -39,6 +39,8 @@ FSP_API int         pfsp_check(void);
 FSP_API const char *pfsp_last_error(void);
 
 /* ---- state set ---- */
+/* the library's world communicator as an fspcomm_t of fsp_b200.h (NULL on a single rank) */
+FSP_API void *pfsp_world_comm(void);
 FSP_API int pfsp_set_create(void **set);
 FSP_API int pfsp_set_destroy(void *set);
 /* Extension (multi-GPU): distributed construction as in src/StateSet/StateSetBase.cpp:134-154,188-258 -- every rank

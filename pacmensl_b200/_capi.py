@@ -180,6 +180,7 @@ SIGNATURES = {
     "fspcomm_window_create": (ci, [vp, C.c_size_t, vpp]),
     "fspcomm_window_destroy": (ci, [vp, vpp]),
     "fspcomm_window_retire": (ci, [vp, vpp, C.c_size_t]),
+    "fspcomm_alltoallv": (ci, [vp, vp, lp, vp, lp, ci, vp]),
     "fspcomm_barrier": (ci, [vp, vp]),
     "fspcomm_barrier_sync": (ci, [vp]),
     "fspcomm_gather_long": (ci, [vp, cl, lp]),

@@ -133,6 +133,13 @@ def health_check():
     return lib().pfsp_check()
 
 
+def world_comm():
+    """The library's world communicator (fspcomm_t of include/fsp_b200.h) for direct calls of the fspcomm_* functions."""
+    f = lib().pfsp_world_comm
+    f.restype = vp
+    return vp(f())
+
+
 def p2p_enabled():
     """True when halo exchange / small all-reduces run as fused peer-memory kernels (CUDA IPC over NVLink)."""
     return bool(lib().pfsp_p2p_enabled())

@@ -123,6 +123,7 @@ struct fspcomm_s {
   std::vector<PooledHalo> halo_pool;  // windows returned by fsphalo_destroy, identical order/capacity on all ranks
   std::vector<PeerWindow> retired;    // general windows given back without a collective (fspcomm_window_retire)
   double            *coll = nullptr;  // device scratch of fspcomm_barrier / fspcomm_gather_long (kMaxRanks + 1 doubles)
+  PeerWindow         a2a;             // receive window of fspcomm_alltoallv (grows by doubling)
 };
 
 struct fsphalo_s {
@@ -355,6 +356,7 @@ int fspcomm_destroy(fspcomm_t c) {
     c->halo_pool.clear();
     for (auto &w : c->retired) window_destroy(c, &w);
     c->retired.clear();
+    if (c->a2a.local) window_destroy(c, &c->a2a);
     if (c->coll) cudaFree(c->coll);
     c->coll = nullptr;
     window_destroy(c, &c->ctrl);
@@ -665,6 +667,65 @@ int fspcomm_barrier(fspcomm_t c, void *stream) {
   if (!c || c->size == 1) return 0;
   if (coll_scratch(c)) return -1;
   return fspcomm_allreduce_sum(c, c->coll + kMaxRanks, 1, stream);
+}
+
+// Personalised all-to-all of variable-size segments (set-up paths: the ghost id lists of GenerateValues, the routed
+// ExpandVec).  send holds the segments for rank 0, 1, ... back to back (send_counts elements of esz = 4 or 8 bytes each),
+// recv receives the segments from rank 0, 1, ... back to back.  Peer-memory path: every rank owns a receive window;
+// the senders store their segments straight into it over NVLink (peer copies), a flag barrier, one local copy out --
+// no NCCL point-to-point channels (whose lazy connection costs ~0.3 s at first use).  FSP_A2A=nccl or a communicator
+// without peer memory: grouped ncclSend / ncclRecv.  Collective; synchronises the stream before returning.
+int fspcomm_alltoallv(fspcomm_t c, const void *send, const long *send_counts, void *recv, const long *recv_counts, int esz,
+                      void *stream) {
+  if (esz != 4 && esz != 8) { set_error("fspcomm_alltoallv: element size %d", esz); return -1; }
+  cudaStream_t st = resolve_stream(stream);
+  if (!c || c->size == 1) {
+    if (send_counts[0] > 0 && send != recv)
+      FSP_CUDA_CHECK(cudaMemcpyAsync(recv, send, (size_t) esz * (size_t) send_counts[0], cudaMemcpyDeviceToDevice, st));
+    FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  }
+  static const bool force_nccl = [] { const char *e = getenv("FSP_A2A"); return e && !strcmp(e, "nccl"); }();
+  if (!c->p2p || force_nccl) {
+    if (esz == 4) return fspcomm_exchange_int(c, (const int *) send, send_counts, (int *) recv, recv_counts, stream);
+    if (fspcomm_halo_exchange(c, (const double *) send, send_counts, (double *) recv, recv_counts, stream)) return -1;
+    FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+    return 0;
+  }
+  const int P = c->size;
+  // where my segment starts inside each peer's receive window (in elements)
+  long recv_off[kMaxRanks + 1] = {0}, remote_off[kMaxRanks] = {0};
+  for (int p = 0; p < P; ++p) recv_off[p + 1] = recv_off[p] + recv_counts[p];
+  if (fspcomm_alltoall_counts(c, recv_off, remote_off, stream)) return -1;
+  // one window size for all ranks: the largest receive volume
+  long need_all[kMaxRanks];
+  if (fspcomm_gather_long(c, recv_off[P] * (long) esz, need_all)) return -1;
+  size_t need = 0;
+  for (int p = 0; p < P; ++p) need = std::max(need, (size_t) need_all[p]);
+  if (need > c->a2a.bytes) {
+    size_t bytes = std::max<size_t>(std::max<size_t>(need, 2 * c->a2a.bytes), (size_t) 1 << 20);
+    bytes = (bytes + 255) / 256 * 256;
+    if (c->a2a.local) {
+      cudaDeviceSynchronize();
+      if (agree(c, true) < 0) return -1;  // nobody is still writing into or reading from the old window
+      window_destroy(c, &c->a2a);
+    }
+    if (window_create(c, bytes, &c->a2a)) return -1;
+  }
+  // every rank has copied the previous call's data out of its window (that copy precedes this barrier on its stream)
+  if (fspcomm_barrier(c, stream)) return -1;
+  long so = 0;
+  for (int p = 0; p < P; ++p) {
+    if (send_counts[p] > 0)
+      FSP_CUDA_CHECK(cudaMemcpyAsync((char *) c->a2a.peer[p] + (size_t) remote_off[p] * esz, (const char *) send + (size_t) so * esz,
+                                     (size_t) send_counts[p] * esz, cudaMemcpyDefault, st));
+    so += send_counts[p];
+  }
+  if (fspcomm_barrier(c, stream)) return -1;  // all segments have landed everywhere
+  if (recv_off[P] > 0)
+    FSP_CUDA_CHECK(cudaMemcpyAsync(recv, c->a2a.local, (size_t) recv_off[P] * esz, cudaMemcpyDeviceToDevice, st));
+  FSP_CUDA_CHECK(cudaStreamSynchronize(st));
+  return check_peer_error(c, "fspcomm_alltoallv");
 }
 
 // Host-synchronising barrier through NCCL: no time limit, for points where ranks may be seconds apart (host callbacks).

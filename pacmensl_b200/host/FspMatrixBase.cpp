@@ -864,11 +864,23 @@ void FspMatrixBase::SetKernelVariant(int v) {
 int FspMatrixBase::SetupGhosts_(const StateSetBase &fsp, int *col_planes_dev, long n_entries) {
   // Build the per-peer ghost lists from the column entries outside the own block (what PETSc's
   // VecScatter set-up does for MATMPISELL) and rewrite col to the local/ghost encoding.
+  static const bool gen_trace = [] { const char *e = std::getenv("FSP_GEN_TRACE"); return e && e[0] == '1'; }();
+  double            t_phase = 0.0;
+  auto tick = [&](const char *what) {
+    if (!gen_trace) return;
+    fsp_device_sync();
+    PetscLogDouble now;
+    PetscTime(&now);
+    if (what && rank_ == 0) printf("[gen n=%d]   ghosts: %-24s %8.2f ms\n", (int) fsp.GetNumLocalStates(), what, 1e3 * (now - t_phase));
+    t_phase = now;
+  };
+  tick(nullptr);
   const std::vector<int> &layout = fsp.GetLayout();
   const int own_start = layout[rank_], own_end = layout[rank_ + 1];
   int *ghost_gid_dev = nullptr;
   long n_ghost = 0;
   FSPCHKERRQ(fspmat_build_ghosts(col_planes_dev, n_entries, own_start, own_end, &ghost_gid_dev, &n_ghost));
+  tick("select/sort/unique/remap");
   n_ghost_ = n_ghost;
   std::vector<int> gids((size_t) n_ghost);
   if (n_ghost > 0) FSPCHKERRQ(fsp_memcpy_d2h(gids.data(), ghost_gid_dev, sizeof(int) * n_ghost, nullptr));
@@ -881,22 +893,27 @@ int FspMatrixBase::SetupGhosts_(const StateSetBase &fsp, int *col_planes_dev, lo
   }
   // tell every peer which of its entries we need: exchange counts, then the index lists
   send_counts_.assign(comm_size_, 0);
+  tick("ids to host, owners");
   FSPCHKERRQ(fspcomm_alltoall_counts(comm_->nccl, recv_counts_.data(), send_counts_.data(), comm_->stream));
+  tick("count exchange");
   n_send_ = 0;
   for (int p = 0; p < comm_size_; ++p) n_send_ += send_counts_[p];
   DeviceBuffer<int> want;
   if (want.upload(gids.data(), gids.size())) return -1;
   if (send_idx_.resize((size_t) (n_send_ > 0 ? n_send_ : 1))) return -1;
   // we SEND our wanted global ids to their owners and RECEIVE the ids they want from us
-  FSPCHKERRQ(fspcomm_exchange_int(comm_->nccl, want.get(), recv_counts_.data(), send_idx_.get(), send_counts_.data(),
-                                  comm_->stream));
+  FSPCHKERRQ(fspcomm_alltoallv(comm_->nccl, want.get(), recv_counts_.data(), send_idx_.get(), send_counts_.data(), (int) sizeof(int),
+                               comm_->stream));
+  tick("id exchange (send/recv)");
   FSPCHKERRQ(fspmat_shift_indices(send_idx_.get(), n_send_, -own_start));  // global -> local
   if (ghost_buf_.resize((size_t) (n_ghost > 0 ? n_ghost : 1))) return -1;
   if (send_buf_.resize((size_t) (n_send_ > 0 ? n_send_ : 1))) return -1;
   // peer-memory halo (CUDA IPC windows over NVLink) when the communicator has it and the default overlap mode is on
   const char *mode = std::getenv("FSP_MULTIGPU_MODE");
   if (fspcomm_p2p_enabled(comm_->nccl) && (!mode || !std::strcmp(mode, "overlap")) && num_constraints_ <= FSP_P2P_MAX_SINKS) {
+    tick("buffers");
     FSPCHKERRQ(fsphalo_create(comm_->nccl, &halo_, send_idx_.get(), send_counts_.data(), recv_counts_.data(), num_constraints_));
+    tick("halo window");
   }
   return 0;
 }

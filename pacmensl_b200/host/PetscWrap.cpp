@@ -44,7 +44,8 @@ PacmenslErrorCode ExpandVec(Vec &p, const std::vector<PetscInt> &new_indices, co
   } else {
     // Multi-GPU: every entry travels once, to the rank that owns its new global index (the VecScatter of
     // src/Sys/PetscWrap.cpp:10-45).  The entries are sorted by owner on the device, the per-peer counts are exchanged, and
-    // the (index, value) segments go out with grouped NCCL send/recv; transient memory is proportional to the LOCAL size.
+    // the (index, value) segments are stored straight into the owners' receive windows over NVLink (fspcomm_alltoallv);
+    // transient memory is proportional to the LOCAL size.
     const long n_old = p->n_local;
     std::vector<long> sizes((size_t) size, 0), starts((size_t) size + 1, 0);
     FSPCHKERRQ(fspcomm_gather_long(comm->nccl, (long) new_local_size, sizes.data()));
@@ -63,8 +64,8 @@ PacmenslErrorCode ExpandVec(Vec &p, const std::vector<PetscInt> &new_indices, co
     DeviceBuffer<int>    idx_recv((size_t) std::max<long>(n_recv, 1));
     DeviceBuffer<double> val_recv((size_t) std::max<long>(n_recv, 1));
     if (!idx_recv.get() || !val_recv.get()) PACMENSLCHKERRQ(-1);
-    FSPCHKERRQ(fspcomm_exchange_int(comm->nccl, idx_sorted.get(), send_counts.data(), idx_recv.get(), recv_counts.data(), stream));
-    FSPCHKERRQ(fspcomm_halo_exchange(comm->nccl, val_sorted.get(), send_counts.data(), val_recv.get(), recv_counts.data(), stream));
+    FSPCHKERRQ(fspcomm_alltoallv(comm->nccl, idx_sorted.get(), send_counts.data(), idx_recv.get(), recv_counts.data(), (int) sizeof(int), stream));
+    FSPCHKERRQ(fspcomm_alltoallv(comm->nccl, val_sorted.get(), send_counts.data(), val_recv.get(), recv_counts.data(), (int) sizeof(double), stream));
     FSPCHKERRQ(fspvec_set(Pnew->d_data, 0.0, new_local_size, stream));
     if (n_recv > 0)
       FSPCHKERRQ(fspvec_scatter_range(Pnew->d_data, new_local_size, val_recv.get(), idx_recv.get(), n_recv, Pnew->own_start, stream));

@@ -51,6 +51,7 @@ int pfsp_init(int device, const char *nccl_id, int rank, int size) {
 }
 int pfsp_finalize(void) { return pacmensl_comm_world_finalize(); }
 int pfsp_p2p_enabled(void) { MPI_Comm w = MPI_COMM_WORLD; return (w && w->nccl) ? fspcomm_p2p_enabled(w->nccl) : 0; }
+void *pfsp_world_comm(void) { MPI_Comm w = MPI_COMM_WORLD; return w ? (void *) w->nccl : nullptr; }
 int pfsp_check(void) {
   if (fsp_device_sync()) return -1;
   MPI_Comm w = MPI_COMM_WORLD;

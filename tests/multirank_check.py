@@ -75,6 +75,34 @@ def main():
         ok &= (1.0 - float(tot)) <= 1e-6 + 1e-9 and float(tot) <= 1.0 + 1e-8
     s.clear()
 
+    # ---- 3. the personalised all-to-all of the set-up paths (ghost id lists, routed ExpandVec) vs torch.distributed ----
+    import ctypes as C
+    from pacmensl_b200 import _capi
+    L = _capi.lib()
+    comm = api.world_comm()
+    rng = np.random.default_rng(100 + rank)
+    a2a_ok = True
+    for trial, (dtype, esz) in enumerate(((torch.int32, 4), (torch.float64, 8), (torch.int32, 4), (torch.float64, 8))):
+        hi = 3 if trial < 2 else 200000   # tiny segments (some empty), then segments that make the window grow
+        sc = torch.from_numpy(rng.integers(0, hi, size=world)).to(torch.int64)
+        rc = torch.zeros(world, dtype=torch.int64)
+        sc_d, rc_d = sc.to(dev), rc.to(dev)
+        dist.all_to_all_single(rc_d, sc_d)
+        rc = rc_d.cpu()
+        send = (torch.rand(int(sc.sum()), device=dev, dtype=torch.float64) * 1e6).to(dtype)
+        want = torch.empty(int(rc.sum()), device=dev, dtype=dtype)
+        dist.all_to_all_single(want, send, output_split_sizes=rc.tolist(), input_split_sizes=sc.tolist())
+        got = torch.full((max(int(rc.sum()), 1),), -7, device=dev, dtype=dtype)
+        scc = (C.c_long * world)(*sc.tolist())
+        rcc = (C.c_long * world)(*rc.tolist())
+        ierr = L.fspcomm_alltoallv(comm, C.c_void_p(send.data_ptr()), scc, C.c_void_p(got.data_ptr()), rcc, esz, None)
+        a2a_ok &= ierr == 0 and bool((got[: int(rc.sum())] == want).all())
+    a2a = torch.tensor([1.0 if a2a_ok else 0.0], device=dev)
+    dist.all_reduce(a2a, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("fspcomm_alltoallv (peer windows) == torch all_to_all_single on %d ranks: %s" % (world, a2a.item() == 1.0))
+        ok &= a2a.item() == 1.0
+
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.broadcast(flag, 0)
     if rank == 0:
