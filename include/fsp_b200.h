@@ -469,6 +469,7 @@ FSP_API int fsphalo_next(fsphalo_t h, fsphalo_epoch *out, fsphalo_push *push);
  * since then were poisoned with NaN by the waiting kernels.  Call after a synchronisation that consumes results. */
 FSP_API int fsphalo_check(fsphalo_t h);
 FSP_API int fspcomm_check(fspcomm_t c);
+FSP_API int fspcomm_alive(fspcomm_t c); /* 1 until fspcomm_destroy(c); safe to call with a stale pointer */
 /* General peer-memory windows (used by the sharded state set).  create / destroy are collective; peers[p] is this
  * process' mapping of rank p's `bytes` bytes (peers[rank] = the local allocation).  retire is local: the window is
  * pooled for a later create of the same size and freed with the communicator. */

@@ -177,6 +177,7 @@ SIGNATURES = {
     "fsphalo_next": (ci, [vp, vp, vp]),
     "fsphalo_check": (ci, [vp]),
     "fspcomm_check": (ci, [vp]),
+    "fspcomm_alive": (ci, [vp]),
     "fspcomm_window_create": (ci, [vp, C.c_size_t, vpp]),
     "fspcomm_window_destroy": (ci, [vp, vpp]),
     "fspcomm_window_retire": (ci, [vp, vpp, C.c_size_t]),

@@ -18,6 +18,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <set>
 #include <vector>
 
 #include "fsp_common.cuh"
@@ -83,6 +85,16 @@ int load_nccl() {
     }                                                                                           \
   } while (0)
 
+}  // namespace
+
+// Live communicators: objects that outlive their communicator (a state set or an operator destroyed after
+// PACMENSLFinalize / pfsp_finalize, e.g. by a garbage collector at interpreter exit) must not touch it.
+namespace {
+std::mutex                     g_live_mutex;
+std::set<const void *>         g_live_comms;
+void comm_register(const void *c) { std::lock_guard<std::mutex> g(g_live_mutex); g_live_comms.insert(c); }
+void comm_unregister(const void *c) { std::lock_guard<std::mutex> g(g_live_mutex); g_live_comms.erase(c); }
+bool comm_alive(const void *c) { std::lock_guard<std::mutex> g(g_live_mutex); return c && g_live_comms.count(c) != 0; }
 }  // namespace
 
 // ---- peer-memory windows ---------------------------------------------------------------------------
@@ -336,12 +348,16 @@ int fspcomm_create(fspcomm_t *out, const char id[FSPCOMM_ID_BYTES], int rank, in
     // peer-memory fast path when every rank can map every peer; NCCL path otherwise
     if (p2p_setup(c)) { set_error("fspcomm_create: the peer-memory set-up collective failed"); cudaFree(c->stage); g_nccl.CommDestroy(c->comm); delete c; return -1; }
   }
+  comm_register(c);
   *out = c;
   return 0;
 }
 
+int fspcomm_alive(fspcomm_t c) { return comm_alive(c) ? 1 : 0; }
+
 int fspcomm_destroy(fspcomm_t c) {
   if (!c) return 0;
+  comm_unregister(c);
   if (c->p2p) {
     // every rank must be past its last peer store before any window is unmapped
     cudaDeviceSynchronize();
@@ -542,6 +558,12 @@ int fsphalo_create(fspcomm_t c, fsphalo_t *out, const int *send_idx_dev, const l
 
 int fsphalo_destroy(fsphalo_t h) {
   if (!h) return 0;
+  if (!comm_alive(h->c)) {  // the communicator (and with it the window) is gone already
+    if (h->block_counter) cudaFree(h->block_counter);
+    cudaGetLastError();
+    delete h;
+    return 0;
+  }
   // the window (with its epoch counter: the flags stay monotone) goes back to the pool; the kernels in flight keep
   // using it safely because every later user continues the same epoch sequence
   h->c->halo_pool.push_back(h->w);
@@ -645,7 +667,8 @@ int fspcomm_window_destroy(fspcomm_t c, void **peers) {
 // NOT collective: the window goes to the communicator's pool (reused by a later fspcomm_window_create of the same size,
 // unmapped and freed by fspcomm_destroy).  For destructors, whose order between ranks is not defined.
 int fspcomm_window_retire(fspcomm_t c, void **peers, size_t bytes) {
-  if (!c || !peers || !peers[c->rank]) return 0;
+  if (!comm_alive(c)) return 0;  // destroyed after its communicator: the process is going down, nothing to pool
+  if (!peers || !peers[c->rank]) return 0;
   PeerWindow w;
   w.bytes = bytes;
   w.local = peers[c->rank];
