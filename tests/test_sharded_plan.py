@@ -132,3 +132,115 @@ def test_rebalance_between_two_gloo_ranks():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+# ---- the whole sharded construction, as a host model on two gloo ranks, against the oracle's state set --------------
+# Rules restated from pacmensl_b200/csrc/fspset.cu (sharded mode): a state's directory shard is hash(state) mod N; every
+# rank generates the children of the frontier states IT owns; a key claimed by several candidates goes to the smallest
+# (is_candidate, rank, position) -- stored states beat candidates, then the lowest rank, then the lowest position;
+# winners are appended on the discovering rank with status 1; a frontier state ends with status 0 (all children inside)
+# or -1; after the BFS the blocks are re-cut by the product's own fspset_rebalance_plan.
+TOGGLE_SM = [[1, 1, -1, 0, 0, 0], [0, 0, 0, 1, 1, -1]]  # the toggle-switch fixture (pacmensl_b200/fixtures/fsp_models.h)
+
+
+def _shard(key, world):
+    return (key[0] * 1000003 + key[1] * 10007) % world   # any function of the key that all ranks agree on
+
+
+def _sharded_bfs_worker(rank, world, port, name, bounds, ret):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from pacmensl_b200 import _capi
+    lib = _capi.lib()
+    info = O.fixture_info(name)
+    SM = np.asarray(TOGGLE_SM, dtype=np.int64)           # S x R
+    x0 = tuple(int(v) for v in info["x0"])
+    S, R = SM.shape
+    b = np.asarray(bounds, dtype=np.int64)
+
+    def valid(x):
+        return all(v >= 0 for v in x) and all(x[s] <= b[s] for s in range(len(b)))
+
+    states, status = [], []                               # this rank's block
+    shard = {}                                            # my directory shard: key -> (rank, position)
+    if rank == 0:
+        states.append(x0); status.append(1)
+    if _shard(x0, world) == rank:
+        shard[x0] = (0, 0)
+    while True:
+        frontier = [i for i, s in enumerate(status) if s == 1]
+        tot = [None] * world
+        dist.all_gather_object(tot, len(frontier))
+        if sum(tot) == 0:
+            break
+        cand, fstat = [], {i: 0 for i in frontier}
+        for j in range(R):                                # reaction-major inside the batch
+            for i in frontier:
+                c = tuple(int(states[i][s] + SM[s, j]) for s in range(S))
+                if valid(c):
+                    cand.append(c)
+                else:
+                    fstat[i] = -1
+        # claims: every candidate goes to the shard of its key, tagged (rank, position in my candidate list)
+        out = [[] for _ in range(world)]
+        for pos, c in enumerate(cand):
+            out[_shard(c, world)].append((c, rank, pos))
+        allout = [None] * world
+        dist.all_gather_object(allout, out)
+        claims = [m for r in range(world) for m in allout[r][rank]]
+        winners = {}
+        for (c, r, pos) in claims:                        # atomicMin over (rank, position); stored states always stay
+            if c in shard:
+                continue
+            if c not in winners or (r, pos) < winners[c]:
+                winners[c] = (r, pos)
+        allwin = [None] * world
+        dist.all_gather_object(allwin, winners)
+        mine = sorted(pos for w in allwin for (c, (r, pos)) in w.items() if r == rank)
+        new_pos = {}
+        for pos in mine:                                  # winners are compacted in candidate order
+            new_pos[pos] = len(states)
+            states.append(cand[pos]); status.append(1)
+        # the shard owners store (rank, final position)
+        final = {cand[pos]: (rank, p) for pos, p in new_pos.items()}
+        allfinal = [None] * world
+        dist.all_gather_object(allfinal, final)
+        for f in allfinal:
+            for c, v in f.items():
+                if _shard(c, world) == rank:
+                    shard[c] = v
+        for i in frontier:
+            status[i] = fstat[i]
+    # re-balance with the product's plan
+    counts = [None] * world
+    dist.all_gather_object(counts, len(states))
+    windows = [None] * world
+    dist.all_gather_object(windows, states)
+    starts, segs, same = plan(lib, counts, rank)
+    new = [None] * (starts[rank + 1] - starts[rank])
+    for (q, off, dst, ln) in segs:
+        new[dst: dst + ln] = windows[q][off: off + ln]
+    blocks = [None] * world
+    dist.all_gather_object(blocks, new)
+    union = [x for blk in blocks for x in blk]
+    ok = len(union) == len(set(union))                    # no state twice
+    if rank == 0:
+        so = O.StateSet(fixture=name, bounds=list(bounds))
+        so.expand()
+        ok &= set(union) == set(map(tuple, so.states().tolist()))
+        ok &= [len(blk) for blk in blocks] == [starts[r + 1] - starts[r] for r in range(world)]
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_construction_model_on_two_gloo_ranks_equals_the_oracle_set():
+    import torch.multiprocessing as mp
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sharded_bfs_worker, args=(world, _free_port(), "toggle", [14, 11], ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
